@@ -1,0 +1,6 @@
+from .acquisition import Acquisition, AcquisitionAggregation, AcquisitionProduct, AcquisitionSum, MCMCAcquistion
+from .ei import ExpectedImprovement
+from .hvpoi import HVProbabilityOfImprovement
+from .lcb import LowerConfidenceBound
+from .pof import ProbabilityOfFeasibility
+from .poi import ProbabilityOfImprovement

@@ -1,0 +1,289 @@
+"""Acquisition base classes: the drop-in surface of gpflowopt/acquisition/acquisition.py on top of libgpfo.
+
+Kept from the reference: ``Acquisition(models, optimize_restarts)``, ``evaluate``, ``evaluate_with_gradients``,
+``build_acquisition``, ``set_data``, ``enable_scaling``, ``models``, ``data``, ``feasible_data_index``,
+``constraint_indices``, ``objective_indices``, ``_setup`` and the ``+`` / ``*`` operators, including the lazy
+``_needs_setup`` protocol (constraints are set up before objectives).
+
+Changed by design: ``build_acquisition(Xcand)`` receives a :class:`~gpflowopt_b200.engine.ProgramBuilder` instead
+of a TensorFlow tensor and appends postfix ops; evaluation is one call into the CUDA library.
+"""
+import copy
+from functools import wraps
+
+import numpy as np
+
+from ..domain import UnitCube
+from ..engine import Engine
+from ..gpr import GPR
+from ..scaling import DataScaler
+
+
+def setup_required(method):
+    """Runs model optimisation and ``_setup`` of the whole tree first if the root is flagged
+    (gpflowopt/acquisition/acquisition.py:32-54)."""
+    @wraps(method)
+    def runnable(instance, *args, **kwargs):
+        assert isinstance(instance, Acquisition)
+        hp = instance.highest_parent
+        if hp._needs_setup:
+            hp._needs_setup = False          # avoids recursion through feasible_data_index -> evaluate
+            hp._optimize_models()
+            hp._setup()
+        return method(instance, *args, **kwargs)
+    return runnable
+
+
+class Acquisition(object):
+    def __init__(self, models=[], optimize_restarts=5):
+        models = list(np.atleast_1d(models))
+        assert all(isinstance(m, (GPR, DataScaler)) for m in models), \
+            "only GP regression models are supported by the device path"
+        self._models = [m if isinstance(m, DataScaler) else DataScaler(m) for m in models]
+        assert optimize_restarts >= 0
+        self.optimize_restarts = optimize_restarts
+        self._parent = None
+        self._engine = None
+        self._needs_setup = True
+
+    # ---- tree plumbing -----------------------------------------------------------------------------------
+    @property
+    def highest_parent(self):
+        node = self
+        while node._parent is not None:
+            node = node._parent
+        return node
+
+    def _adopt(self, child):
+        child._parent = self
+        self.highest_parent._needs_setup = True
+
+    def _get_engine(self):
+        root = self.highest_parent
+        if root._engine is None or root._engine.ctx is None:
+            adopted = [m._engine for m in root.models if getattr(m, '_engine', None) is not None
+                       and m._engine.ctx is not None]
+            root._engine = adopted[0] if adopted else Engine()
+        return root._engine
+
+    # ---- reference API -----------------------------------------------------------------------------------
+    def _optimize_models(self):
+        """gpflowopt/acquisition/acquisition.py:92-122.  Hyper-parameter learning itself is the model's business
+        (``GPR.optimize`` keeps the given hyper-parameters); the restart / best-run protocol is preserved."""
+        if self.optimize_restarts == 0:
+            return
+        for model in self.models:
+            runs = []
+            for i in range(self.optimize_restarts):
+                if i > 0:
+                    model.randomize()
+                try:
+                    runs.append(model.optimize())
+                except Exception as e:                      # pragma: no cover
+                    print("Warning: optimization restart {0}/{1} failed".format(i + 1, self.optimize_restarts))
+            if not runs:
+                raise RuntimeError("All model hyperparameter optimization restarts failed, exiting.")
+            best_idx = int(np.argmin([r.fun for r in runs]))
+            model.set_state(runs[best_idx].x)
+
+    def build_acquisition(self, Xcand):
+        raise NotImplementedError
+
+    def enable_scaling(self, domain):
+        n_inputs = self.data[0].shape[1]
+        assert domain.size == n_inputs
+        for m in self.models:
+            m.input_transform = domain >> UnitCube(n_inputs)
+            m.normalize_output = True
+        self.highest_parent._needs_setup = True
+
+    def set_data(self, X, Y):
+        num_outputs_sum = 0
+        for model in self.models:
+            num_outputs = model.Y.shape[1]
+            Ypart = Y[:, num_outputs_sum:num_outputs_sum + num_outputs]
+            num_outputs_sum += num_outputs
+            model.X = X
+            model.Y = Ypart
+        self.highest_parent._needs_setup = True
+        return num_outputs_sum
+
+    @property
+    def models(self):
+        return list(self._models)
+
+    @property
+    def data(self):
+        return self.models[0].X.value, np.hstack([m.Y.value for m in self.models])
+
+    def constraint_indices(self):
+        return np.empty((0,), dtype=int)
+
+    def objective_indices(self):
+        return np.setdiff1d(np.arange(self.data[1].shape[1]), self.constraint_indices())
+
+    def feasible_data_index(self):
+        return np.ones(self.data[0].shape[0], dtype=bool)
+
+    def _setup(self):
+        pass
+
+    def _setup_constraints(self):
+        if self.constraint_indices().size > 0:
+            self._setup()
+
+    def _setup_objectives(self):
+        if self.constraint_indices().size == 0:
+            self._setup()
+
+    @setup_required
+    def evaluate_with_gradients(self, Xcand):
+        """Scores (N x 1) and their gradients w.r.t. the candidates (N x D)."""
+        return self._get_engine().evaluate(self, Xcand, gradients=True)
+
+    @setup_required
+    def evaluate(self, Xcand):
+        """Scores (N x 1)."""
+        return self._get_engine().evaluate(self, Xcand, gradients=False)
+
+    @setup_required
+    def argmax(self, Xcand):
+        """(best value, lowest index attaining it) over the candidate rows; scores stay on the device.
+        This is the fused form of ``np.argmin(-evaluate(X))`` in MCOptimizer._optimize (gpflowopt/optim.py:155-164)."""
+        return self._get_engine().argmax(self, Xcand)
+
+    def __add__(self, other):
+        if isinstance(other, AcquisitionSum):
+            return AcquisitionSum([self] + other.operands)
+        return AcquisitionSum([self, other])
+
+    def __mul__(self, other):
+        if isinstance(other, AcquisitionProduct):
+            return AcquisitionProduct([self] + other.operands)
+        return AcquisitionProduct([self, other])
+
+
+class AcquisitionAggregation(Acquisition):
+    """Reduces the scores of several acquisitions (gpflowopt/acquisition/acquisition.py:301-365)."""
+
+    def __init__(self, operands, oper):
+        super(AcquisitionAggregation, self).__init__()
+        assert all(isinstance(x, Acquisition) for x in operands)
+        assert oper in ('sum', 'prod')
+        self.operands = list(operands)
+        self._oper = oper
+        for o in self.operands:
+            self._adopt(o)
+
+    def _optimize_models(self):
+        for oper in self.operands:
+            oper._optimize_models()
+
+    @property
+    def models(self):
+        return [model for acq in self.operands for model in acq.models]
+
+    def enable_scaling(self, domain):
+        for oper in self.operands:
+            oper.enable_scaling(domain)
+
+    def set_data(self, X, Y):
+        offset = 0
+        for operand in self.operands:
+            offset += operand.set_data(X, Y[:, offset:])
+        return offset
+
+    def _setup_constraints(self):
+        for oper in self.operands:
+            if oper.constraint_indices().size > 0:
+                oper._setup_constraints()
+
+    def _setup_objectives(self):
+        for oper in self.operands:
+            oper._setup_objectives()
+
+    def _setup(self):
+        self._setup_constraints()        # first: objectives may depend on the constraint acquisitions
+        self._setup_objectives()
+
+    def constraint_indices(self):
+        offset = [0]
+        idx = []
+        for operand in self.operands:
+            idx.append(operand.constraint_indices())
+            offset.append(operand.data[1].shape[1])
+        return np.hstack([i + o for i, o in zip(idx, offset[:-1])]).astype(int)
+
+    def feasible_data_index(self):
+        return np.all(np.vstack([o.feasible_data_index() for o in self.operands]), axis=0)
+
+    def build_acquisition(self, Xcand):
+        return Xcand.reduce(self._oper, [operand.build_acquisition(Xcand) for operand in self.operands])
+
+    def __getitem__(self, item):
+        return self.operands[item]
+
+
+class AcquisitionSum(AcquisitionAggregation):
+    def __init__(self, operands):
+        super(AcquisitionSum, self).__init__(operands, 'sum')
+
+    def __add__(self, other):
+        if isinstance(other, AcquisitionSum):
+            return AcquisitionSum(self.operands + other.operands)
+        return AcquisitionSum(self.operands + [other])
+
+
+class AcquisitionProduct(AcquisitionAggregation):
+    def __init__(self, operands):
+        super(AcquisitionProduct, self).__init__(operands, 'prod')
+
+    def __mul__(self, other):
+        if isinstance(other, AcquisitionProduct):
+            return AcquisitionProduct(self.operands + other.operands)
+        return AcquisitionProduct(self.operands + [other])
+
+
+class MCMCAcquistion(AcquisitionSum):
+    """Mean of an acquisition over hyper-parameter draws (gpflowopt/acquisition/acquisition.py:396-458).
+
+    Drawing the samples (GPflow's HMC) is outside this path: pass them as ``hyper_draws`` (n_slices x n_hypers
+    free-state rows per model, see ``GPR.get_free_state``); the evaluation = SUM over copies then SCALE 1/n on
+    the device."""
+
+    def __init__(self, acquisition, n_slices, hyper_draws=None, **kwargs):
+        assert isinstance(acquisition, Acquisition)
+        assert n_slices > 0
+        copies = [acquisition] + [copy.deepcopy(acquisition) for _ in range(n_slices - 1)]
+        for c in copies[1:]:
+            c.optimize_restarts = 0
+            c._engine = None
+            for m in c._models:
+                m._engine = None
+        super(MCMCAcquistion, self).__init__(copies)
+        self._sample_opt = kwargs
+        if hyper_draws is not None:
+            self.set_hyper_draws(hyper_draws)
+
+    def set_hyper_draws(self, hyper_draws):
+        hyper_draws = np.atleast_2d(hyper_draws)
+        assert hyper_draws.shape[0] == len(self.operands)
+        for draw, oper in zip(hyper_draws, self.operands):
+            offset = 0
+            for m in oper.models:
+                n = m.get_free_state().size
+                m.set_state(draw[offset:offset + n])
+                offset += n
+        self.highest_parent._needs_setup = True
+
+    def _optimize_models(self):
+        self.operands[0]._optimize_models()
+
+    def set_data(self, X, Y):
+        for operand in self.operands:
+            offset = operand.set_data(X, Y)
+        return offset
+
+    def build_acquisition(self, Xcand):
+        node = super(MCMCAcquistion, self).build_acquisition(Xcand)
+        return Xcand.scale(node, 1. / len(self.operands))

@@ -1,0 +1,550 @@
+// C-ABI of libgpfo.so (see include/gpfo.h).  One ctx = one device + one stream; not thread-safe.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include "gpfo_internal.cuh"
+
+#define FB 64
+#define RMAX_KERNEL 4
+
+struct GpHost {
+    bool valid = false;
+    int M = 0, Mp = 0, Mf = 0, D = 0, R = 0, kind = 0, slot0 = 0;
+    double *dX = nullptr, *dell = nullptr, *dXs = nullptr, *dxn = nullptr, *dY = nullptr, *dV = nullptr;
+    double *dL = nullptr, *dLinv = nullptr, *dpacked = nullptr;
+    int packed_rbc = 0;
+    size_t cap_mf = 0, cap_d = 0, cap_r = 0, cap_packed = 0;
+    GpDev hdev;
+    GpDev* ddev = nullptr;
+};
+
+struct gpfo_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    GpHost gps[GPFO_MAX_GPS];
+    int ngps = 0;
+    ProgramDev hprog;
+    ProgramDev* dprog = nullptr;
+    bool prog_set = false;
+    // cells
+    CellsDev cells;
+    double* dpf = nullptr;
+    int32_t *dlb = nullptr, *dub = nullptr;
+    bool cells_set = false;
+    // scratch
+    double* dXc = nullptr; size_t cap_xc = 0;
+    double* dvalues = nullptr; size_t cap_values = 0;
+    double *dmom_mean = nullptr, *dmom_var = nullptr; size_t cap_mom = 0;
+    double* dpart_val = nullptr; long long* dpart_idx = nullptr; int cap_parts = 0;
+    double* dbest_val = nullptr; long long* dbest_idx = nullptr;
+    int* dflag = nullptr;
+    cudaEvent_t ev[8];
+    gpfo_timings tm;
+    int variant = 0;
+};
+
+static const char* k_status[] = {"ok", "matrix not positive definite", "bad shape", "CUDA error",
+                                 "unsupported model or feature", "bad acquisition program", "invalid state"};
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                              \
+            return GPFO_ERR_CUDA;                                                                        \
+        }                                                                                                \
+    } while (0)
+
+static int fail(gpfo_ctx* ctx, int code, const std::string& msg) {
+    ctx->err = msg;
+    return code;
+}
+
+template <typename T>
+static cudaError_t ensure(T** p, size_t* cap, size_t need) {
+    if (*cap >= need && *p) return cudaSuccess;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    cudaError_t e = cudaMalloc((void**)p, need * sizeof(T));
+    if (e == cudaSuccess) *cap = need;
+    return e;
+}
+
+static bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+extern "C" {
+
+int gpfo_version(void) { return GPFO_VERSION; }
+
+const char* gpfo_status_string(int status) {
+    if (status < 0 || status > GPFO_ERR_STATE) return "unknown status";
+    return k_status[status];
+}
+
+const char* gpfo_last_error(const gpfo_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int gpfo_ctx_create(int device, gpfo_ctx** out) {
+    if (!out) return GPFO_ERR_BAD_SHAPE;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return GPFO_ERR_CUDA; }
+    if (device < 0 || device >= ndev) return GPFO_ERR_BAD_SHAPE;
+    if (cudaSetDevice(device) != cudaSuccess) return GPFO_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GPFO_ERR_CUDA;
+    if (prop.major != 10) {
+        fprintf(stderr, "libgpfo: device %d is sm_%d%d; this library is built for sm_100a only\n", device, prop.major,
+                prop.minor);
+        return GPFO_ERR_UNSUPPORTED;
+    }
+    gpfo_ctx* ctx = new gpfo_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    memset(&ctx->tm, 0, sizeof(ctx->tm));
+    memset(&ctx->hprog, 0, sizeof(ctx->hprog));
+    memset(&ctx->cells, 0, sizeof(ctx->cells));
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&ctx->dprog, sizeof(ProgramDev)) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&ctx->dbest_val, sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&ctx->dbest_idx, sizeof(long long)) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&ctx->dflag, sizeof(int)) == cudaSuccess;
+    if (!ok) { delete ctx; return GPFO_ERR_CUDA; }
+    *out = ctx;
+    return GPFO_OK;
+}
+
+static void free_gp(GpHost& g) {
+    cudaFree(g.dX); cudaFree(g.dell); cudaFree(g.dXs); cudaFree(g.dxn); cudaFree(g.dY); cudaFree(g.dV);
+    cudaFree(g.dL); cudaFree(g.dLinv); cudaFree(g.dpacked); cudaFree(g.ddev);
+    g = GpHost();
+}
+
+int gpfo_ctx_destroy(gpfo_ctx* ctx) {
+    if (!ctx) return GPFO_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < GPFO_MAX_GPS; ++i) free_gp(ctx->gps[i]);
+    cudaFree(ctx->dprog); cudaFree(ctx->dpf); cudaFree(ctx->dlb); cudaFree(ctx->dub);
+    cudaFree(ctx->dXc); cudaFree(ctx->dvalues); cudaFree(ctx->dmom_mean); cudaFree(ctx->dmom_var);
+    cudaFree(ctx->dpart_val); cudaFree(ctx->dpart_idx); cudaFree(ctx->dbest_val); cudaFree(ctx->dbest_idx);
+    cudaFree(ctx->dflag);
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return GPFO_OK;
+}
+
+static int effective_variant(const gpfo_ctx* ctx, int64_t N) {
+    if (ctx->variant >= 1 && ctx->variant <= 3) return ctx->variant;
+    // automatic: 16-candidate tiles once they fill the machine, 8-candidate tiles for small batches
+    return (N >= (int64_t)16 * ctx->num_sms) ? 1 : 2;
+}
+
+static int repack(gpfo_ctx* ctx, GpHost& g, int rbc) {
+    PackGeom geom;
+    geom.nrb = g.Mp / 8;
+    geom.rbc = rbc;
+    geom.nchunks = (geom.nrb + rbc - 1) / rbc;
+    const size_t need = (size_t)pg_total_blocks(geom) * 64;
+    CK(ensure(&g.dpacked, &g.cap_packed, need));
+    gpfo_pack_linv(ctx->stream, g.dLinv, g.Mf, geom, g.dpacked);
+    CK(cudaGetLastError());
+    g.packed_rbc = rbc;
+    g.hdev.geom = geom;
+    g.hdev.packed = g.dpacked;
+    CK(cudaMemcpyAsync(g.ddev, &g.hdev, sizeof(GpDev), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GPFO_OK;
+}
+
+int gpfo_gp_set(gpfo_ctx* ctx, int gp_id, int64_t M64, int D, int R, const double* X, const double* Y,
+                int kernel_kind, int ard, const double* lengthscales, double kern_variance, double noise_variance,
+                const double* in_scale, const double* in_shift, const double* out_scale, const double* out_shift,
+                int slot0) {
+    if (!ctx) return GPFO_ERR_STATE;
+    cudaSetDevice(ctx->device);
+    if (gp_id < 0 || gp_id >= GPFO_MAX_GPS) return fail(ctx, GPFO_ERR_BAD_SHAPE, "gp_id out of range");
+    if (M64 < 1 || M64 > 65536) return fail(ctx, GPFO_ERR_BAD_SHAPE, "M must be in [1, 65536]");
+    if (D < 1 || D > GPFO_MAX_DIM) return fail(ctx, GPFO_ERR_BAD_SHAPE, "D must be in [1, 64]");
+    if (R < 1 || R > RMAX_KERNEL) return fail(ctx, GPFO_ERR_UNSUPPORTED, "R (output columns per GP) must be in [1, 4]");
+    if (slot0 < 0 || slot0 + R > GPFO_MAX_SLOTS) return fail(ctx, GPFO_ERR_BAD_SHAPE, "moment slot out of range");
+    if (kernel_kind < GPFO_KERN_RBF || kernel_kind > GPFO_KERN_MATERN32)
+        return fail(ctx, GPFO_ERR_UNSUPPORTED, "kernel must be RBF, Matern52 or Matern32");
+    if (!X || !Y || !lengthscales) return fail(ctx, GPFO_ERR_BAD_SHAPE, "null input");
+    if (!(kern_variance > 0.0) || !(noise_variance >= 0.0)) return fail(ctx, GPFO_ERR_BAD_SHAPE, "variances must be positive");
+    const int M = (int)M64;
+    GpHost& g = ctx->gps[gp_id];
+    const int Mp = (M + 7) / 8 * 8, Mf = (M + FB - 1) / FB * FB;
+    if ((size_t)Mf > g.cap_mf || (size_t)D > g.cap_d || (size_t)R > g.cap_r) {
+        free_gp(g);
+        size_t c = 0;
+        CK(ensure(&g.dX, &c, (size_t)Mf * D)); c = 0;
+        CK(ensure(&g.dell, &c, (size_t)D)); c = 0;
+        CK(ensure(&g.dXs, &c, (size_t)Mf * D)); c = 0;
+        CK(ensure(&g.dxn, &c, (size_t)Mf)); c = 0;
+        CK(ensure(&g.dY, &c, (size_t)Mf * R)); c = 0;
+        CK(ensure(&g.dV, &c, (size_t)Mf * R)); c = 0;
+        CK(ensure(&g.dL, &c, (size_t)Mf * Mf)); c = 0;
+        CK(ensure(&g.dLinv, &c, (size_t)Mf * Mf));
+        CK(cudaMalloc((void**)&g.ddev, sizeof(GpDev)));
+        g.cap_mf = Mf; g.cap_d = D; g.cap_r = R;
+    }
+    g.valid = false;
+    g.M = M; g.Mp = Mp; g.Mf = Mf; g.D = D; g.R = R; g.kind = kernel_kind; g.slot0 = slot0;
+    memset(&g.hdev, 0, sizeof(GpDev));
+    double ell[GPFO_MAX_DIM];
+    for (int d = 0; d < D; ++d) {
+        ell[d] = ard ? lengthscales[d] : lengthscales[0];
+        if (!(ell[d] > 0.0)) return fail(ctx, GPFO_ERR_BAD_SHAPE, "lengthscales must be positive");
+        g.hdev.ell[d] = ell[d];
+        g.hdev.inv_ell[d] = 1.0 / ell[d];
+        g.hdev.in_scale[d] = in_scale ? in_scale[d] : 1.0;
+        g.hdev.in_shift[d] = in_shift ? in_shift[d] : 0.0;
+    }
+    for (int r = 0; r < R; ++r) {
+        g.hdev.out_scale[r] = out_scale ? out_scale[r] : 1.0;
+        g.hdev.out_shift[r] = out_shift ? out_shift[r] : 0.0;
+        if (g.hdev.out_scale[r] == 0.0) return fail(ctx, GPFO_ERR_BAD_SHAPE, "out_scale must be non-zero");
+    }
+    cudaStream_t st = ctx->stream;
+    CK(cudaEventRecord(ctx->ev[0], st));
+    CK(cudaMemsetAsync(g.dX, 0, (size_t)Mf * D * sizeof(double), st));
+    CK(cudaMemsetAsync(g.dY, 0, (size_t)Mf * R * sizeof(double), st));
+    CK(cudaMemcpyAsync(g.dX, X, (size_t)M * D * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(g.dY, Y, (size_t)M * R * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(g.dell, ell, (size_t)D * sizeof(double), cudaMemcpyHostToDevice, st));
+    gpfo_prepare_inputs(st, g.dX, M, Mf, D, g.dell, g.dXs, g.dxn);
+    CK(cudaGetLastError());
+    int rc = gpfo_factor_device(st, M, Mf, D, R, kernel_kind, kern_variance, noise_variance, g.dXs, g.dxn, g.dL,
+                                g.dLinv, g.dY, g.dV, ctx->dflag, &ctx->err);
+    if (rc != GPFO_OK) return rc;
+    g.hdev.M = M; g.hdev.Mp = Mp; g.hdev.D = D; g.hdev.R = R; g.hdev.kind = kernel_kind; g.hdev.slot0 = slot0;
+    g.hdev.variance = kern_variance;
+    g.hdev.Xs = g.dXs; g.hdev.xn = g.dxn; g.hdev.V = g.dV;
+    rc = repack(ctx, g, gpfo_contract_rbc(ctx->variant));
+    if (rc != GPFO_OK) return rc;
+    CK(cudaEventRecord(ctx->ev[1], st));
+    CK(cudaEventSynchronize(ctx->ev[1]));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->tm.factor_ms = ms;
+    g.valid = true;
+    if (gp_id + 1 > ctx->ngps) ctx->ngps = gp_id + 1;
+    return GPFO_OK;
+}
+
+int gpfo_gp_count_set(gpfo_ctx* ctx, int n_gps) {
+    if (!ctx) return GPFO_ERR_STATE;
+    if (n_gps < 0 || n_gps > GPFO_MAX_GPS) return fail(ctx, GPFO_ERR_BAD_SHAPE, "n_gps out of range");
+    cudaSetDevice(ctx->device);
+    for (int i = n_gps; i < GPFO_MAX_GPS; ++i)
+        if (ctx->gps[i].valid || ctx->gps[i].dL) free_gp(ctx->gps[i]);
+    ctx->ngps = n_gps;
+    return GPFO_OK;
+}
+
+int gpfo_gp_get_factor(gpfo_ctx* ctx, int gp_id, double* L, double* Linv, double* V) {
+    if (!ctx) return GPFO_ERR_STATE;
+    if (gp_id < 0 || gp_id >= GPFO_MAX_GPS || !ctx->gps[gp_id].valid) return fail(ctx, GPFO_ERR_STATE, "gp not set");
+    cudaSetDevice(ctx->device);
+    GpHost& g = ctx->gps[gp_id];
+    const size_t w = (size_t)g.M * sizeof(double);
+    if (L) CK(cudaMemcpy2D(L, w, g.dL, (size_t)g.Mf * sizeof(double), w, g.M, cudaMemcpyDeviceToHost));
+    if (Linv) CK(cudaMemcpy2D(Linv, w, g.dLinv, (size_t)g.Mf * sizeof(double), w, g.M, cudaMemcpyDeviceToHost));
+    if (V) CK(cudaMemcpy(V, g.dV, (size_t)g.M * g.R * sizeof(double), cudaMemcpyDeviceToHost));
+    return GPFO_OK;
+}
+
+int gpfo_program_set(gpfo_ctx* ctx, const int32_t* ops, int nops, const double* params, int nparams) {
+    if (!ctx) return GPFO_ERR_STATE;
+    cudaSetDevice(ctx->device);
+    if (nops < 1 || nops > GPFO_MAX_OPS || nparams < 0 || nparams > GPFO_MAX_PARAMS || !ops)
+        return fail(ctx, GPFO_ERR_BAD_PROGRAM, "program size out of range");
+    ProgramDev p;
+    memset(&p, 0, sizeof(p));
+    int sp = 0, nslots = 0, hv = 0;
+    for (int i = 0; i < nops; ++i) {
+        const int op = ops[4 * i], a = ops[4 * i + 1], b = ops[4 * i + 2], c = ops[4 * i + 3];
+        switch (op) {
+            case GPFO_OP_EI: case GPFO_OP_POI: case GPFO_OP_POF: case GPFO_OP_LCB:
+                if (c < 0 || c >= nparams) return fail(ctx, GPFO_ERR_BAD_PROGRAM, "leaf parameter index out of range");
+                /* fallthrough */
+            case GPFO_OP_MEAN: case GPFO_OP_VAR:
+                if (a < 0 || a >= GPFO_MAX_SLOTS) return fail(ctx, GPFO_ERR_BAD_PROGRAM, "moment slot out of range");
+                if (a + 1 > nslots) nslots = a + 1;
+                ++sp;
+                break;
+            case GPFO_OP_HVPOI:
+                if (hv) return fail(ctx, GPFO_ERR_UNSUPPORTED, "at most one HVPoI leaf per program");
+                if (a < 0 || b < 2 || b > 6 || a + b > GPFO_MAX_SLOTS)
+                    return fail(ctx, GPFO_ERR_BAD_PROGRAM, "HVPoI needs 2..6 objectives in valid slots");
+                if (a + b > nslots) nslots = a + b;
+                hv = 1; ++sp;
+                break;
+            case GPFO_OP_SUM: case GPFO_OP_PROD:
+                if (a < 1 || a > sp) return fail(ctx, GPFO_ERR_BAD_PROGRAM, "aggregation pops more than the stack holds");
+                sp -= a - 1;
+                break;
+            case GPFO_OP_SCALE:
+                if (sp < 1 || c < 0 || c >= nparams) return fail(ctx, GPFO_ERR_BAD_PROGRAM, "bad SCALE");
+                break;
+            default:
+                return fail(ctx, GPFO_ERR_BAD_PROGRAM, "unknown opcode");
+        }
+        if (sp > 8) return fail(ctx, GPFO_ERR_BAD_PROGRAM, "program stack deeper than 8");
+    }
+    if (sp != 1) return fail(ctx, GPFO_ERR_BAD_PROGRAM, "program must leave exactly one value");
+    p.nops = nops; p.nslots = nslots; p.has_hvpoi = hv;
+    memcpy(p.ops, ops, sizeof(int32_t) * 4 * nops);
+    if (nparams) memcpy(p.params, params, sizeof(double) * nparams);
+    ctx->hprog = p;
+    CK(cudaMemcpyAsync(ctx->dprog, &ctx->hprog, sizeof(ProgramDev), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->prog_set = true;
+    return GPFO_OK;
+}
+
+int gpfo_cells_set(gpfo_ctx* ctx, const double* pf_ext, int n_ext_rows, int R, const int32_t* lb, const int32_t* ub,
+                   int64_t C) {
+    if (!ctx) return GPFO_ERR_STATE;
+    cudaSetDevice(ctx->device);
+    if (!pf_ext || n_ext_rows < 2 || R < 2 || R > 6 || C < 0 || (C > 0 && (!lb || !ub)))
+        return fail(ctx, GPFO_ERR_BAD_SHAPE, "bad cell tables");
+    if (gpfo_hvpoi_smem_bytes(n_ext_rows, R) > 227 * 1024)
+        return fail(ctx, GPFO_ERR_UNSUPPORTED, "Pareto front too large for the shared-memory Phi table");
+    for (int64_t i = 0; i < C * R; ++i)
+        if (lb[i] < 0 || lb[i] >= n_ext_rows || ub[i] < 0 || ub[i] >= n_ext_rows)
+            return fail(ctx, GPFO_ERR_BAD_SHAPE, "cell index outside pf_ext");
+    cudaFree(ctx->dpf); cudaFree(ctx->dlb); cudaFree(ctx->dub);
+    ctx->dpf = nullptr; ctx->dlb = ctx->dub = nullptr; ctx->cells_set = false;
+    CK(cudaMalloc((void**)&ctx->dpf, (size_t)n_ext_rows * R * sizeof(double)));
+    CK(cudaMalloc((void**)&ctx->dlb, (size_t)(C > 0 ? C : 1) * R * sizeof(int32_t)));
+    CK(cudaMalloc((void**)&ctx->dub, (size_t)(C > 0 ? C : 1) * R * sizeof(int32_t)));
+    CK(cudaMemcpy(ctx->dpf, pf_ext, (size_t)n_ext_rows * R * sizeof(double), cudaMemcpyHostToDevice));
+    if (C > 0) {
+        CK(cudaMemcpy(ctx->dlb, lb, (size_t)C * R * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->dub, ub, (size_t)C * R * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    ctx->cells.n_ext = n_ext_rows; ctx->cells.R = R; ctx->cells.C = C;
+    ctx->cells.pf_ext = ctx->dpf; ctx->cells.lb = ctx->dlb; ctx->cells.ub = ctx->dub;
+    ctx->cells_set = true;
+    return GPFO_OK;
+}
+
+// Stages candidates on the device (if needed) and makes sure scratch buffers are large enough.
+static int stage_candidates(gpfo_ctx* ctx, const double* X, int64_t N, int D, const double** dX) {
+    if (is_device_ptr(X)) { *dX = X; ctx->tm.h2d_ms = 0.0; return GPFO_OK; }
+    CK(ensure(&ctx->dXc, &ctx->cap_xc, (size_t)N * D));
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dXc, X, (size_t)N * D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    *dX = ctx->dXc;
+    return GPFO_OK;
+}
+
+static int ensure_parts(gpfo_ctx* ctx, int n) {
+    if (ctx->cap_parts >= n) return GPFO_OK;
+    cudaFree(ctx->dpart_val); cudaFree(ctx->dpart_idx);
+    ctx->dpart_val = nullptr; ctx->dpart_idx = nullptr; ctx->cap_parts = 0;
+    CK(cudaMalloc((void**)&ctx->dpart_val, (size_t)n * sizeof(double)));
+    CK(cudaMalloc((void**)&ctx->dpart_idx, (size_t)n * sizeof(long long)));
+    ctx->cap_parts = n;
+    return GPFO_OK;
+}
+
+int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_values, double* out_grads,
+              double* best_value, int64_t* best_index) {
+    if (!ctx) return GPFO_ERR_STATE;
+    cudaSetDevice(ctx->device);
+    if (!ctx->prog_set) return fail(ctx, GPFO_ERR_STATE, "gpfo_eval before gpfo_program_set");
+    if (ctx->ngps < 1) return fail(ctx, GPFO_ERR_STATE, "gpfo_eval before gpfo_gp_set");
+    if (N < 0) return fail(ctx, GPFO_ERR_BAD_SHAPE, "N < 0");
+    // which slots are produced by the registered GPs?
+    bool have[GPFO_MAX_SLOTS] = {false};
+    for (int g = 0; g < ctx->ngps; ++g) {
+        const GpHost& gp = ctx->gps[g];
+        if (!gp.valid) return fail(ctx, GPFO_ERR_STATE, "a GP below gp count was never set");
+        if (gp.D != D) return fail(ctx, GPFO_ERR_BAD_SHAPE, "candidate dimension does not match the models");
+        for (int r = 0; r < gp.R; ++r) have[gp.slot0 + r] = true;
+    }
+    for (int s = 0; s < ctx->hprog.nslots; ++s)
+        if (!have[s]) return fail(ctx, GPFO_ERR_STATE, "program references a moment slot no GP produces");
+    if (ctx->hprog.has_hvpoi && !ctx->cells_set) return fail(ctx, GPFO_ERR_STATE, "HVPoI program without gpfo_cells_set");
+    if (out_grads) return fail(ctx, GPFO_ERR_UNSUPPORTED, "gradient kernel not available in this build");
+    if (N == 0) {
+        if (best_index) *best_index = -1;
+        if (best_value) *best_value = 0.0;
+        memset(&ctx->tm.h2d_ms, 0, sizeof(double) * 4);
+        ctx->tm.launches = 0;
+        return GPFO_OK;
+    }
+    if (!Xcand) return fail(ctx, GPFO_ERR_BAD_SHAPE, "null candidates");
+    cudaStream_t st = ctx->stream;
+    const double* dX = nullptr;
+    int rc = stage_candidates(ctx, Xcand, N, D, &dX);
+    if (rc != GPFO_OK) return rc;
+    const bool host_in = (dX != Xcand);
+
+    const int variant = effective_variant(ctx, N);
+    const int rbc = gpfo_contract_rbc(variant);
+    for (int g = 0; g < ctx->ngps; ++g)
+        if (ctx->gps[g].packed_rbc != rbc) { rc = repack(ctx, ctx->gps[g], rbc); if (rc != GPFO_OK) return rc; }
+
+    const bool hv = ctx->hprog.has_hvpoi != 0;
+    const bool need_mom = hv || ctx->ngps > 1;
+    EvalIO io;
+    memset(&io, 0, sizeof(io));
+    io.X = dX; io.N = N;
+    if (need_mom) {
+        const size_t need = (size_t)GPFO_MAX_SLOTS * N;
+        if (ctx->cap_mom < need) {
+            cudaFree(ctx->dmom_mean); cudaFree(ctx->dmom_var);
+            ctx->dmom_mean = ctx->dmom_var = nullptr; ctx->cap_mom = 0;
+            CK(cudaMalloc((void**)&ctx->dmom_mean, need * sizeof(double)));
+            CK(cudaMalloc((void**)&ctx->dmom_var, need * sizeof(double)));
+            ctx->cap_mom = need;
+        }
+        io.mom_mean = ctx->dmom_mean; io.mom_var = ctx->dmom_var;
+    }
+    const bool dev_out = out_values && is_device_ptr(out_values);
+    if (out_values) {
+        if (dev_out) io.values = out_values;
+        else { CK(ensure(&ctx->dvalues, &ctx->cap_values, (size_t)N)); io.values = ctx->dvalues; }
+    }
+    const int grid = gpfo_contract_grid(variant, N, ctx->num_sms);
+    const int hv_grid = gpfo_hvpoi_grid(N, ctx->num_sms);
+    rc = ensure_parts(ctx, grid > hv_grid ? grid : hv_grid);
+    if (rc != GPFO_OK) return rc;
+    io.part_val = ctx->dpart_val; io.part_idx = ctx->dpart_idx;
+
+    int launches = 0;
+    float hot_ms = 0.f;
+    CK(cudaEventRecord(ctx->ev[4], st));
+    for (int g = 0; g < ctx->ngps; ++g) {
+        EvalIO gio = io;
+        gio.write_moments = need_mom ? 1 : 0;
+        gio.run_program = (!hv && g == ctx->ngps - 1) ? 1 : 0;
+        CK(cudaEventRecord(ctx->ev[6], st));
+        CK(gpfo_contract_launch(st, variant, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
+        CK(cudaEventRecord(ctx->ev[7], st));
+        ++launches;
+        if (ctx->ngps > 1) {                 // per-GP timing needs a sync only when events are reused
+            CK(cudaEventSynchronize(ctx->ev[7]));
+            float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); hot_ms += ms;
+        }
+    }
+    int nparts = grid;
+    if (hv) {
+        EvalIO hio = io;
+        hio.run_program = 1;
+        int slot_first = 0;
+        for (int i = 0; i < ctx->hprog.nops; ++i)
+            if (ctx->hprog.ops[4 * i] == GPFO_OP_HVPOI) {
+                slot_first = ctx->hprog.ops[4 * i + 1];
+                if (ctx->hprog.ops[4 * i + 2] != ctx->cells.R)
+                    return fail(ctx, GPFO_ERR_BAD_SHAPE, "HVPoI objective count does not match the cell tables");
+            }
+        CK(gpfo_hvpoi_launch(st, ctx->dprog, ctx->cells, hio, hv_grid, slot_first));
+        ++launches;
+        nparts = hv_grid;
+    }
+    gpfo_argmax_final(st, ctx->dpart_val, ctx->dpart_idx, nparts, ctx->dbest_val, ctx->dbest_idx);
+    CK(cudaGetLastError());
+    ++launches;
+    CK(cudaEventRecord(ctx->ev[5], st));
+    // results
+    double hbest = 0.0;
+    long long hidx = -1;
+    if (out_values && !dev_out)
+        CK(cudaMemcpyAsync(out_values, ctx->dvalues, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&hbest, ctx->dbest_val, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&hidx, ctx->dbest_idx, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev[1], st));
+    CK(cudaStreamSynchronize(st));
+    if (best_value) *best_value = hbest;
+    if (best_index) *best_index = (int64_t)hidx;
+    float ms = 0.f;
+    if (host_in) { cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->tm.h2d_ms = ms; }
+    cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->tm.eval_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[1]); ctx->tm.d2h_ms = ms;
+    if (ctx->ngps == 1) { cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); hot_ms = ms; }
+    ctx->tm.hot_kernel_ms = hot_ms;
+    ctx->tm.launches = launches;
+    return GPFO_OK;
+}
+
+int gpfo_predict(gpfo_ctx* ctx, int gp_id, const double* X, int64_t N, int D, double* mean, double* var) {
+    if (!ctx) return GPFO_ERR_STATE;
+    cudaSetDevice(ctx->device);
+    if (gp_id < 0 || gp_id >= GPFO_MAX_GPS || !ctx->gps[gp_id].valid) return fail(ctx, GPFO_ERR_STATE, "gp not set");
+    GpHost& g = ctx->gps[gp_id];
+    if (g.D != D) return fail(ctx, GPFO_ERR_BAD_SHAPE, "point dimension does not match the model");
+    if (N < 0) return fail(ctx, GPFO_ERR_BAD_SHAPE, "N < 0");
+    if (N == 0) return GPFO_OK;
+    if (!X) return fail(ctx, GPFO_ERR_BAD_SHAPE, "null points");
+    cudaStream_t st = ctx->stream;
+    const double* dX = nullptr;
+    int rc = stage_candidates(ctx, X, N, D, &dX);
+    if (rc != GPFO_OK) return rc;
+    const int variant = effective_variant(ctx, N);
+    const int rbc = gpfo_contract_rbc(variant);
+    if (g.packed_rbc != rbc) { rc = repack(ctx, g, rbc); if (rc != GPFO_OK) return rc; }
+    const size_t need = (size_t)GPFO_MAX_SLOTS * N;
+    if (ctx->cap_mom < need) {
+        cudaFree(ctx->dmom_mean); cudaFree(ctx->dmom_var);
+        ctx->dmom_mean = ctx->dmom_var = nullptr; ctx->cap_mom = 0;
+        CK(cudaMalloc((void**)&ctx->dmom_mean, need * sizeof(double)));
+        CK(cudaMalloc((void**)&ctx->dmom_var, need * sizeof(double)));
+        ctx->cap_mom = need;
+    }
+    const int grid = gpfo_contract_grid(variant, N, ctx->num_sms);
+    rc = ensure_parts(ctx, grid);
+    if (rc != GPFO_OK) return rc;
+    EvalIO io;
+    memset(&io, 0, sizeof(io));
+    io.X = dX; io.N = N; io.mom_mean = ctx->dmom_mean; io.mom_var = ctx->dmom_var;
+    io.part_val = ctx->dpart_val; io.part_idx = ctx->dpart_idx;
+    io.write_moments = 1; io.run_program = 0;
+    CK(gpfo_contract_launch(st, variant, g.ddev, ctx->dprog, io, grid, D));
+    // [slot][N] -> N x R
+    for (int r = 0; r < g.R; ++r) {
+        const size_t off = (size_t)(g.slot0 + r) * N;
+        if (mean) CK(cudaMemcpy2DAsync(mean + r, (size_t)g.R * sizeof(double), ctx->dmom_mean + off, sizeof(double),
+                                       sizeof(double), (size_t)N, cudaMemcpyDefault, st));
+        if (var) CK(cudaMemcpy2DAsync(var + r, (size_t)g.R * sizeof(double), ctx->dmom_var + off, sizeof(double),
+                                      sizeof(double), (size_t)N, cudaMemcpyDefault, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return GPFO_OK;
+}
+
+int gpfo_timings_get(const gpfo_ctx* ctx, gpfo_timings* out) {
+    if (!ctx || !out) return GPFO_ERR_STATE;
+    *out = ctx->tm;
+    return GPFO_OK;
+}
+
+int gpfo_set_variant(gpfo_ctx* ctx, int variant) {
+    if (!ctx) return GPFO_ERR_STATE;
+    if (variant < 0 || variant > 3) return fail(ctx, GPFO_ERR_BAD_SHAPE, "variant must be 0..3");
+    ctx->variant = variant;
+    return GPFO_OK;
+}
+
+int gpfo_measure_dmma_peak(gpfo_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return GPFO_ERR_STATE;
+    cudaSetDevice(ctx->device);
+    const double v = gpfo_dmma_peak(ctx->stream, ctx->num_sms);
+    if (v < 0.0) return fail(ctx, GPFO_ERR_CUDA, "DMMA peak kernel failed");
+    *tflops = v;
+    return GPFO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,249 @@
+// Internal declarations shared by the translation units of libgpfo.so (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/gpfo.h"
+
+#define GPFO_HD __host__ __device__ __forceinline__
+
+// ------------------------------------------------------------------------------------------------
+// Packed L^-1 layout ("block stream") consumed by the contraction kernel.
+//
+// L^-1 (Mp x Mp, Mp = M rounded up to 8, zero padded) is cut into 8x8 blocks (rb = row block,
+// kp = column block).  Only blocks with rb >= kp are stored.  Rows are grouped into chunks of RBC row
+// blocks; inside chunk p the blocks are ordered [kp][rb] so that, for a fixed kp, the row blocks a CTA
+// walks through are contiguous.  One block is 64 doubles in "DMMA lane order": lane l (0..31) owns
+// {Linv[8rb + l/4][8kp + l%4], Linv[8rb + l/4][8kp + 4 + l%4]} = the A fragments of the two m8n8k4 steps
+// of that block, stored as one 16-byte pair at block_base + 2*l.
+// ------------------------------------------------------------------------------------------------
+struct PackGeom {
+    int nrb;        // number of 8-row blocks = Mp / 8
+    int rbc;        // row blocks per chunk
+    int nchunks;    // ceil(nrb / rbc)
+};
+
+GPFO_HD int pg_chunk_rows(const PackGeom& g, int p) {            // row blocks in chunk p
+    int left = g.nrb - p * g.rbc;
+    return left < g.rbc ? left : g.rbc;
+}
+// number of blocks stored before chunk p
+GPFO_HD int64_t pg_chunk_base(const PackGeom& g, int p) {
+    // full chunks q < p each hold q*rbc*rbc (off-diagonal) + rbc*(rbc+1)/2 (diagonal) blocks
+    int64_t rbc = g.rbc;
+    int64_t pp = p;
+    return rbc * rbc * (pp * (pp - 1) / 2) + pp * (rbc * (rbc + 1) / 2);
+}
+// offset (in blocks, relative to the chunk base) of the first stored block of column block kp in chunk p,
+// and the first stored row block (local index) `lo`.  nr = pg_chunk_rows(g, p).
+GPFO_HD int64_t pg_col_base(const PackGeom& g, int p, int nr, int kp, int* lo) {
+    int kd = kp - p * g.rbc;                                     // < 0: off-diagonal (dense) column block
+    if (kd < 0) { *lo = 0; return (int64_t)kp * nr; }
+    *lo = kd;
+    // sum_{q<kd} (nr - q) = kd*nr - kd*(kd-1)/2
+    return (int64_t)p * g.rbc * nr + (int64_t)kd * nr - (int64_t)kd * (kd - 1) / 2;
+}
+GPFO_HD int64_t pg_total_blocks(const PackGeom& g) {
+    int p = g.nchunks - 1;
+    int nr = pg_chunk_rows(g, p);
+    return pg_chunk_base(g, p) + (int64_t)p * g.rbc * nr + (int64_t)nr * (nr + 1) / 2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device-side description of one GP and of the acquisition program
+// ------------------------------------------------------------------------------------------------
+struct GpDev {
+    int M, Mp, D, R;
+    int kind;                   // GPFO_KERN_*
+    int slot0;
+    double variance;            // kernel variance (Kdiag)
+    const double* Xs;           // Mp x D, training inputs divided by lengthscales (rows >= M are zero)
+    const double* xn;           // Mp, squared norms of the rows of Xs
+    const double* V;            // Mp x R, L^-1 Y (rows >= M are zero)
+    const double* packed;       // block stream of L^-1
+    PackGeom geom;
+    double in_scale[GPFO_MAX_DIM], in_shift[GPFO_MAX_DIM], inv_ell[GPFO_MAX_DIM];   // per input dimension
+    double ell[GPFO_MAX_DIM];
+    double out_scale[GPFO_MAX_SLOTS], out_shift[GPFO_MAX_SLOTS];                   // per output column
+};
+
+struct ProgramDev {
+    int nops;
+    int nslots;                 // moment slots referenced
+    int has_hvpoi;
+    int32_t ops[GPFO_MAX_OPS * 4];
+    double params[GPFO_MAX_PARAMS];
+};
+
+struct EvalIO {
+    const double* X;            // N x D candidates (device)
+    int64_t N;
+    double* mom_mean;           // [slot][N] scratch (may be null when not needed)
+    double* mom_var;
+    double* values;             // N (may be null)
+    double* part_val;           // per-CTA argmax partials
+    long long* part_idx;
+    int write_moments;          // this launch stores its moments to scratch
+    int run_program;            // this launch evaluates the program in its epilogue
+};
+
+#define GPFO_STABILITY 1e-6     // gpflow settings.numerics.jitter_level (ei.py:24, poi.py:23, pof.py:23, hvpoi.py:24)
+
+// ------------------------------------------------------------------------------------------------
+// TF1 Normal.cdf / Normal.prob forms
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double gpfo_ndtr(double t) {
+    const double half_sqrt2 = 0.70710678118654757;              // 0.5 * sqrt(2) as float64
+    double w = t * half_sqrt2;
+    double z = fabs(w);
+    double y;
+    if (z < half_sqrt2) y = 1.0 + erf(w);
+    else if (w > 0.0)   y = 2.0 - erfc(z);
+    else                y = erfc(z);
+    return 0.5 * y;
+}
+__device__ __forceinline__ double gpfo_std_pdf(double z) {
+    const double half_log_2pi = 0.91893853320467267;
+    return exp(-0.5 * (z * z) - half_log_2pi);
+}
+// Normal(loc, scale).prob(x) = exp(-0.5 z^2 - (0.5 log 2pi + log scale))
+__device__ __forceinline__ double gpfo_normal_prob(double x, double loc, double scale) {
+    const double half_log_2pi = 0.91893853320467267;
+    double z = (x - loc) / scale;
+    return exp(-0.5 * (z * z) - (half_log_2pi + log(scale)));
+}
+
+// Evaluates the postfix acquisition program for one candidate.
+//   mu, va   moment slots (un-scaled predictive mean / variance, NOT clamped)
+//   hv       value of the HVPoI leaf for this candidate (only read when the program has one)
+// With GRAD: also returns d value / d mu[s] and d value / d va[s] for every slot (forward mode over the
+// tiny program; products use the product rule = TF's exclusive-product gradient).
+template <bool GRAD>
+__device__ __forceinline__ double gpfo_run_program(const ProgramDev& pr, const double* mu, const double* va,
+                                                   double hv, const double* hv_dmu, const double* hv_dva,
+                                                   double* dmu, double* dva) {
+    constexpr int STK = 8;
+    double st[STK];
+    double gm[GRAD ? STK : 1][GRAD ? GPFO_MAX_SLOTS : 1];
+    double gv[GRAD ? STK : 1][GRAD ? GPFO_MAX_SLOTS : 1];
+    int sp = 0;
+    const int ns = pr.nslots;
+    for (int i = 0; i < pr.nops; ++i) {
+        const int op = pr.ops[4 * i], a = pr.ops[4 * i + 1], b = pr.ops[4 * i + 2], c = pr.ops[4 * i + 3];
+        if (op <= GPFO_OP_LCB || op == GPFO_OP_MEAN || op == GPFO_OP_VAR) {
+            const double m = mu[a], v0 = va[a];
+            double val, d_m = 0.0, d_v = 0.0;
+            if (op == GPFO_OP_MEAN) { val = m; d_m = 1.0; }
+            else if (op == GPFO_OP_VAR) { val = v0; d_v = 1.0; }
+            else if (op == GPFO_OP_LCB) {
+                const double sig = pr.params[c];
+                const double v = fmax(v0, 0.0);
+                const double s = sqrt(v);
+                val = m - sig * s;
+                if (GRAD) { d_m = 1.0; d_v = (v0 >= 0.0) ? -sig / (2.0 * s) : 0.0; }
+            } else {
+                const double p = pr.params[c];
+                const double v = fmax(v0, GPFO_STABILITY);
+                const double s = sqrt(v);
+                const double z = (p - m) / s;
+                const double Phi = gpfo_ndtr(z);
+                const double ds_dv = (v0 >= GPFO_STABILITY) ? 1.0 / (2.0 * s) : 0.0;
+                if (op == GPFO_OP_EI) {
+                    val = (p - m) * Phi + v * gpfo_normal_prob(p, m, s);
+                    if (GRAD) { d_m = -Phi; d_v = gpfo_std_pdf(z) * ds_dv; }
+                } else {
+                    val = Phi;
+                    if (GRAD) { const double phi = gpfo_std_pdf(z); d_m = -phi / s; d_v = -(z * phi / s) * ds_dv; }
+                }
+            }
+            st[sp] = val;
+            if (GRAD) {
+                for (int s2 = 0; s2 < ns; ++s2) { gm[sp][s2] = 0.0; gv[sp][s2] = 0.0; }
+                gm[sp][a] = d_m; gv[sp][a] = d_v;
+            }
+            ++sp;
+        } else if (op == GPFO_OP_HVPOI) {
+            st[sp] = hv;
+            if (GRAD) {
+                for (int s2 = 0; s2 < ns; ++s2) { gm[sp][s2] = 0.0; gv[sp][s2] = 0.0; }
+                for (int j = 0; j < b; ++j) { gm[sp][a + j] = hv_dmu[j]; gv[sp][a + j] = hv_dva[j]; }
+            }
+            ++sp;
+        } else if (op == GPFO_OP_SUM) {
+            const int base = sp - a;
+            double acc = st[base];
+            for (int k = 1; k < a; ++k) acc += st[base + k];
+            if (GRAD) {
+                for (int k = 1; k < a; ++k)
+                    for (int s2 = 0; s2 < ns; ++s2) { gm[base][s2] += gm[base + k][s2]; gv[base][s2] += gv[base + k][s2]; }
+            }
+            st[base] = acc; sp = base + 1;
+        } else if (op == GPFO_OP_PROD) {
+            const int base = sp - a;
+            double acc = st[base];
+            for (int k = 1; k < a; ++k) acc *= st[base + k];
+            if (GRAD) {
+                for (int s2 = 0; s2 < ns; ++s2) {
+                    double tm = 0.0, tv = 0.0;
+                    for (int k = 0; k < a; ++k) {
+                        double others = 1.0;
+                        for (int q = 0; q < a; ++q) if (q != k) others *= st[base + q];
+                        tm += others * gm[base + k][s2];
+                        tv += others * gv[base + k][s2];
+                    }
+                    gm[base][s2] = tm; gv[base][s2] = tv;       // operand k == 0 is overwritten last
+                }
+            }
+            st[base] = acc; sp = base + 1;
+        } else if (op == GPFO_OP_SCALE) {
+            const double f = pr.params[c];
+            st[sp - 1] *= f;
+            if (GRAD) for (int s2 = 0; s2 < ns; ++s2) { gm[sp - 1][s2] *= f; gv[sp - 1][s2] *= f; }
+        }
+    }
+    if (GRAD) for (int s2 = 0; s2 < ns; ++s2) { dmu[s2] = gm[0][s2]; dva[s2] = gv[0][s2]; }
+    return st[0];
+}
+
+// (value, index) ordering used at every reduction level: larger value wins; ties -> lower index; NaN never wins.
+__device__ __forceinline__ bool gpfo_better(double v, long long i, double bv, long long bi) {
+    if (i < 0) return false;
+    if (bi < 0) return !(v != v);
+    return (v > bv) || (v == bv && i < bi);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launchers implemented in the other translation units
+// ------------------------------------------------------------------------------------------------
+// factor.cu  (Mf = M rounded up to 64; all matrices have leading dimension Mf)
+int gpfo_factor_device(cudaStream_t st, int M, int Mf, int D, int R, int kind, double variance, double noise,
+                       const double* dXs, const double* dxn, double* dK /*Mf x Mf work, becomes L*/,
+                       double* dLinv /*Mf x Mf*/, const double* dY /*Mf x R*/, double* dV /*Mf x R*/,
+                       int* dflag, std::string* err);
+void gpfo_pack_linv(cudaStream_t st, const double* dLinv, int ld, PackGeom g, double* dpacked);
+void gpfo_prepare_inputs(cudaStream_t st, const double* dX, int M, int Mp, int D, const double* d_ell,
+                         double* dXs, double* dxn);
+
+// contract.cu
+int gpfo_contract_rbc(int variant);
+int gpfo_contract_tile(int variant);
+int gpfo_contract_grid(int variant, int64_t N, int num_sms);
+cudaError_t gpfo_contract_launch(cudaStream_t st, int variant, const GpDev* d_gp, const ProgramDev* d_prog,
+                                 EvalIO io, int grid, int D);
+void gpfo_argmax_final(cudaStream_t st, const double* part_val, const long long* part_idx, int nparts,
+                       double* out_val, long long* out_idx);
+double gpfo_dmma_peak(cudaStream_t st, int num_sms);
+
+// hvpoi.cu
+struct CellsDev {
+    int n_ext, R;
+    int64_t C;
+    const double* pf_ext;       // n_ext x R
+    const int32_t* lb;          // C x R
+    const int32_t* ub;
+};
+int gpfo_hvpoi_grid(int64_t N, int num_sms);
+size_t gpfo_hvpoi_smem_bytes(int n_ext, int R);
+cudaError_t gpfo_hvpoi_launch(cudaStream_t st, const ProgramDev* d_prog, const CellsDev& cells, EvalIO io, int grid,
+                              int slot_first);

@@ -1,0 +1,58 @@
+"""Candidate sources for the Monte-Carlo optimiser (mirror of gpflowopt/design.py, the parts on the path)."""
+import numpy as np
+
+from .domain import ContinuousParameter
+
+
+class Design(object):
+    """N points generated in a D-dimensional domain (gpflowopt/design.py:29-81)."""
+
+    def __init__(self, size, domain):
+        self.size = size
+        self.domain = domain
+
+    @property
+    def generative_domain(self):
+        return np.sum([ContinuousParameter('d{0}'.format(i), 0, 1) for i in range(self.domain.size)])
+
+    def generate(self):
+        Xs = self.create_design()
+        assert Xs in self.generative_domain
+        assert Xs.shape == (self.size, self.domain.size)
+        X = (self.generative_domain >> self.domain).forward(Xs)
+        assert X in self.domain
+        return X
+
+    def create_design(self):
+        raise NotImplementedError
+
+
+class RandomDesign(Design):
+    """Uniform random points: the MC candidate source (gpflowopt/design.py:83-94)."""
+
+    def create_design(self):
+        return np.random.rand(self.size, self.domain.size).astype(np.float64)
+
+
+class FactorialDesign(Design):
+    """k-level grid (gpflowopt/design.py:97-116)."""
+
+    def __init__(self, levels, domain):
+        self.levels = levels
+        super(FactorialDesign, self).__init__(levels ** domain.size, domain)
+
+    @property
+    def generative_domain(self):
+        return self.domain
+
+    def create_design(self):
+        Xs = np.meshgrid(*[np.linspace(l, u, self.levels) for l, u in zip(self.domain.lower, self.domain.upper)])
+        return np.vstack([X.ravel() for X in Xs]).T
+
+
+class EmptyDesign(Design):
+    def __init__(self, domain):
+        super(EmptyDesign, self).__init__(0, domain)
+
+    def create_design(self):
+        return np.empty((0, self.domain.size))

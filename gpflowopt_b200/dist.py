@@ -1,0 +1,99 @@
+"""Candidate-row data parallelism: one process per GPU (torch.distributed), contiguous row shards, and ONE
+exchange step per evaluation -- an all-gather of a 16-byte (value, global index) pair per rank followed by the
+same lexicographic reduce (max value, then min index) on every rank.  NCCL has no MAXLOC, hence gather + reduce.
+
+Every rank factorises the GPs redundantly (deterministic kernels -> bit-identical state), so there is no
+broadcast on the setup side.  Without an initialised process group everything degenerates to a single shard.
+"""
+import numpy as np
+
+
+def _pg():
+    try:
+        import torch.distributed as td
+    except Exception:                                   # pragma: no cover
+        return None
+    return td if td.is_available() and td.is_initialized() else None
+
+
+def world():
+    td = _pg()
+    return (td.get_rank(), td.get_world_size()) if td is not None else (0, 1)
+
+
+def shard_bounds(n, rank, world_size):
+    """Contiguous block [lo, hi) of rank ``rank``: blocks of ceil(n / world_size) rows, so that
+    global index = lo + local index and the lowest-index tie-break stays trivial."""
+    per = -(-n // world_size) if n > 0 else 0
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def _device_for_collectives(td):
+    import torch
+    if td.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def broadcast_points(points):
+    """Makes all ranks score the same candidate matrix (rank 0's); identity without a process group."""
+    td = _pg()
+    if td is None or td.get_world_size() == 1:
+        return points
+    import torch
+    dev = _device_for_collectives(td)
+    shape = torch.tensor(list(points.shape), dtype=torch.int64, device=dev)
+    td.broadcast(shape, src=0)
+    n, d = int(shape[0]), int(shape[1])
+    buf = torch.from_numpy(np.ascontiguousarray(points, dtype=np.float64)).to(dev) if td.get_rank() == 0 \
+        else torch.empty((n, d), dtype=torch.float64, device=dev)
+    td.broadcast(buf, src=0)
+    return buf.cpu().numpy()
+
+
+def reduce_pairs(values, indices):
+    """Lexicographic reduce over per-rank (value, global index) pairs: max value, ties -> lowest index;
+    index < 0 marks an empty shard; NaN never wins."""
+    best_v, best_i = 0.0, -1
+    for v, i in zip(values, indices):
+        v, i = float(v), int(i)
+        if i < 0 or v != v:
+            continue
+        if best_i < 0 or v > best_v or (v == best_v and i < best_i):
+            best_v, best_i = v, i
+    return best_v, best_i
+
+
+def allgather_pair(value, index):
+    """The one exchange step: all-gather of (f64 value, i64 global index)."""
+    td = _pg()
+    if td is None or td.get_world_size() == 1:
+        return [value], [index]
+    import torch
+    dev = _device_for_collectives(td)
+    ws = td.get_world_size()
+    # one 16-byte record per rank: the int64 index travels bit-exactly inside a float64 lane
+    rec = torch.empty(2, dtype=torch.float64, device=dev)
+    rec[0] = float(value)
+    rec[1:2].view(torch.int64)[0] = int(index)
+    out = torch.empty(2 * ws, dtype=torch.float64, device=dev)
+    td.all_gather_into_tensor(out, rec) if hasattr(td, "all_gather_into_tensor") and td.get_backend() == "nccl" \
+        else td.all_gather(list(out.view(ws, 2).unbind(0)), rec)
+    out = out.view(ws, 2).cpu()
+    vals = [float(out[r, 0]) for r in range(ws)]
+    idxs = [int(out[r, 1:2].view(torch.int64)[0]) for r in range(ws)]
+    return vals, idxs
+
+
+def sharded_argmax(local_argmax, points):
+    """``local_argmax(rows) -> (best value, best local index)``; returns the global (value, index)."""
+    rank, ws = world()
+    lo, hi = shard_bounds(points.shape[0], rank, ws)
+    if hi > lo:
+        v, i = local_argmax(points[lo:hi])
+        i = i + lo if i >= 0 else -1
+    else:
+        v, i = 0.0, -1
+    vals, idxs = allgather_pair(v, i)
+    return reduce_pairs(vals, idxs)

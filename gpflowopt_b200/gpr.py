@@ -1,0 +1,106 @@
+"""Minimal GP-regression parameter holders: the attribute surface of GPflow 0.5.0 that GPflowOpt touches
+(X, Y, kern.variance, kern.lengthscales, likelihood.variance, predict_f).
+
+These classes hold numbers only.  All arithmetic (kernel matrix, Cholesky, prediction) runs on the device
+through libgpfo; hyper-parameter learning (GPflow's Model.optimize / HMC) is outside this path, so
+``optimize()`` keeps the hyper-parameters it was given.
+"""
+import numpy as np
+from scipy.optimize import OptimizeResult
+
+from . import _lib
+
+
+class _Versioned(object):
+    """Bumps ``version`` on every public attribute assignment so engines can see stale device state."""
+
+    def __setattr__(self, key, value):
+        object.__setattr__(self, key, value)
+        if not key.startswith('_') and key != 'version':
+            object.__setattr__(self, 'version', getattr(self, 'version', 0) + 1)
+
+
+class Stationary(_Versioned):
+    kind = None
+
+    def __init__(self, input_dim, variance=1.0, lengthscales=None, ARD=False):
+        self.input_dim = int(input_dim)
+        self.ARD = bool(ARD)
+        self.variance = float(variance)
+        if lengthscales is None:
+            lengthscales = np.ones(self.input_dim) if ARD else 1.0
+        self.lengthscales = lengthscales
+
+    def __setattr__(self, key, value):
+        if key == 'lengthscales':
+            value = np.atleast_1d(np.asarray(value, dtype=np.float64)).copy()
+        super(Stationary, self).__setattr__(key, value)
+
+
+class RBF(Stationary):
+    kind = _lib.KERN_RBF
+
+
+class Matern52(Stationary):
+    kind = _lib.KERN_MATERN52
+
+
+class Matern32(Stationary):
+    kind = _lib.KERN_MATERN32
+
+
+class Gaussian(_Versioned):
+    def __init__(self, variance=1.0):
+        self.variance = float(variance)
+
+
+class DataHolder(object):
+    """``.value`` / ``.shape`` view of an array, as GPflow's DataHolder offers."""
+
+    def __init__(self, array):
+        self._array = np.asarray(array, dtype=np.float64)
+
+    @property
+    def value(self):
+        return self._array.copy()
+
+    @property
+    def shape(self):
+        return self._array.shape
+
+
+class GPR(_Versioned):
+    """Gaussian process regression with a Gaussian likelihood and a zero mean function."""
+
+    def __init__(self, X, Y, kern, noise_variance=1.0, name='GPR'):
+        self.kern = kern
+        self.likelihood = Gaussian(noise_variance)
+        self.name = name
+        self.X = X
+        self.Y = Y
+
+    def __setattr__(self, key, value):
+        if key in ('X', 'Y'):
+            value = value if isinstance(value, DataHolder) else DataHolder(np.atleast_2d(value))
+            assert len(value.shape) == 2
+        super(GPR, self).__setattr__(key, value)
+
+    @property
+    def state_version(self):
+        return (self.version, self.kern.version, self.likelihood.version)
+
+    # hyper-parameter learning is not part of this path
+    def optimize(self, **kwargs):
+        return OptimizeResult(x=self.get_free_state(), fun=0.0, success=True, message="hyper-parameters kept")
+
+    def randomize(self):
+        pass
+
+    def get_free_state(self):
+        return np.hstack([[self.kern.variance], self.kern.lengthscales, [self.likelihood.variance]])
+
+    def set_state(self, x):
+        x = np.asarray(x, dtype=np.float64).ravel()
+        self.kern.variance = float(x[0])
+        self.kern.lengthscales = x[1:-1]
+        self.likelihood.variance = float(x[-1])

@@ -1,0 +1,198 @@
+"""Acquisition optimisers: mirror of gpflowopt/optim.py with the candidate scoring + argmin of
+MCOptimizer / CandidateOptimizer fused on the device when the objective is a gpflowopt_b200 acquisition.
+
+An objective handed to ``Optimizer.optimize`` may carry an ``acquisition`` attribute (see
+``bo.inverse_acquisition``).  For such objectives the Monte-Carlo stage calls ``Acquisition.argmax`` -- one
+gpfo_eval with a block argmax and no N-sized device->host copy -- and, under torch.distributed, shards the
+candidate rows over the ranks (``gpflowopt_b200.dist``).  Any other callable goes through the generic
+evaluate-then-np.argmin route of the reference.
+"""
+import contextlib
+import os
+import sys
+import warnings
+
+import numpy as np
+from scipy.optimize import OptimizeResult, minimize
+
+from . import dist
+from .design import RandomDesign
+from .objective import ObjectiveWrapper
+
+
+class Optimizer(object):
+    def __init__(self, domain, exclude_gradient=False):
+        self._domain = domain
+        self._initial = domain.value
+        self._wrapper_args = dict(exclude_gradient=exclude_gradient)
+
+    @property
+    def domain(self):
+        return self._domain
+
+    @domain.setter
+    def domain(self, dom):
+        self._domain = dom
+        self.set_initial(dom.value)
+
+    def optimize(self, objectivefx, **kwargs):
+        """Minimises ``objectivefx`` over the domain; Ctrl-C returns the last good point (optim.py:63-85)."""
+        objective = ObjectiveWrapper(objectivefx, **self._wrapper_args)
+        objective.acquisition = getattr(objectivefx, 'acquisition', None)
+        try:
+            result = self._optimize(objective, **kwargs)
+        except KeyboardInterrupt:
+            result = OptimizeResult(x=objective._previous_x, success=False,
+                                    message="Caught KeyboardInterrupt, returning last good value.")
+        result.x = np.atleast_2d(result.x)
+        result.nfev = objective.counter
+        return result
+
+    def get_initial(self):
+        return self._initial
+
+    def set_initial(self, initial):
+        initial = np.atleast_2d(initial)
+        assert initial in self.domain
+        self._initial = initial
+
+    def gradient_enabled(self):
+        return not self._wrapper_args['exclude_gradient']
+
+    @contextlib.contextmanager
+    def silent(self):
+        save_stdout = sys.stdout
+        sys.stdout = open(os.devnull, 'w')
+        try:
+            yield
+        finally:
+            sys.stdout = save_stdout
+
+
+class MCOptimizer(Optimizer):
+    """Scores ``nsamples`` uniformly random points and returns the best (gpflowopt/optim.py:131-172)."""
+
+    def __init__(self, domain, nsamples):
+        super(MCOptimizer, self).__init__(domain, exclude_gradient=True)
+        self._nsamples = nsamples
+        self.set_initial(np.empty((0, self.domain.size)))
+
+    @property
+    def domain(self):
+        return self._domain
+
+    @domain.setter
+    def domain(self, dom):
+        self._domain = dom
+
+    def _get_eval_points(self):
+        return RandomDesign(self._nsamples, self.domain).generate()
+
+    def _optimize(self, objective):
+        points = self._get_eval_points()
+        acq = getattr(objective, 'acquisition', None)
+        if acq is not None:
+            # fused route: argmin of -acq == argmax of acq with the same first-occurrence tie-break
+            points = dist.broadcast_points(points)
+            best, idx = dist.sharded_argmax(acq.argmax, points)
+            objective.counter += points.shape[0]
+            return OptimizeResult(x=points[[idx], :], success=True, fun=np.array([[-best]]),
+                                  nfev=points.shape[0], message="OK")
+        evaluations = objective(points)
+        idx_best = np.argmin(evaluations, axis=0)
+        return OptimizeResult(x=points[idx_best, :], success=True, fun=evaluations[idx_best, :],
+                              nfev=points.shape[0], message="OK")
+
+    def set_initial(self, initial):
+        initial = np.atleast_2d(initial)
+        if initial.size > 0:
+            warnings.warn("Initial points set in {0} are ignored.".format(self.__class__.__name__), UserWarning)
+            return
+        super(MCOptimizer, self).set_initial(initial)
+
+
+class CandidateOptimizer(MCOptimizer):
+    """Scores a fixed candidate matrix (gpflowopt/optim.py:175-198)."""
+
+    def __init__(self, domain, candidates):
+        super(CandidateOptimizer, self).__init__(domain, candidates.shape[0])
+        assert candidates in domain
+        self.candidates = candidates
+
+    def _get_eval_points(self):
+        return self.candidates
+
+    @property
+    def domain(self):
+        return self._domain
+
+    @domain.setter
+    def domain(self, dom):
+        t = self._domain >> dom
+        self._domain = dom
+        self.candidates = t.forward(self.candidates)
+
+
+class SciPyOptimizer(Optimizer):
+    """scipy.optimize.minimize wrapper (gpflowopt/optim.py:201-224); consumes the gradient kernel."""
+
+    def __init__(self, domain, method='L-BFGS-B', tol=None, maxiter=1000):
+        super(SciPyOptimizer, self).__init__(domain)
+        self.config = dict(tol=tol, method=method, options=dict(disp=False, maxiter=maxiter))
+
+    def _optimize(self, objective):
+        def objective1d(X):
+            return tuple(arr.ravel() for arr in objective(X))
+        return minimize(fun=objective1d, x0=self.get_initial().ravel(), jac=self.gradient_enabled(),
+                        bounds=list(zip(self.domain.lower, self.domain.upper)), **self.config)
+
+
+class StagedOptimizer(Optimizer):
+    """Pipeline of optimisers; the best point of a stage seeds the next one (gpflowopt/optim.py:227-282)."""
+
+    def __init__(self, optimizers):
+        assert all(optimizers[0].domain == opt.domain for opt in optimizers)
+        no_gradient = any(not opt.gradient_enabled() for opt in optimizers)
+        super(StagedOptimizer, self).__init__(optimizers[0].domain, exclude_gradient=no_gradient)
+        self.optimizers = optimizers
+        del self._initial
+
+    @property
+    def domain(self):
+        return self._domain
+
+    @domain.setter
+    def domain(self, domain):
+        self._domain = domain
+        for optimizer in self.optimizers:
+            optimizer.domain = domain
+
+    def _best_x(self, results):
+        ok = [r for r in results if r.success]
+        best_idx = int(np.argmin([np.ravel(r.fun)[0] for r in ok]))
+        return ok[best_idx].x, ok[best_idx].fun
+
+    def optimize(self, objectivefx):
+        results = []
+        result = None
+        for current, following in zip(self.optimizers[:-1], self.optimizers[1:]):
+            result = current.optimize(objectivefx)
+            results.append(result)
+            if not result.success:
+                result.message += " StagedOptimizer interrupted after {0}.".format(current.__class__.__name__)
+                break
+            following.set_initial(self._best_x(results)[0])
+        if result is None or result.success:
+            result = self.optimizers[-1].optimize(objectivefx)
+            results.append(result)
+        result.nfev = sum(r.nfev for r in results)
+        result.nstages = len(results)
+        if any(r.success for r in results):
+            result.x, result.fun = self._best_x(results)
+        return result
+
+    def get_initial(self):
+        return self.optimizers[0].get_initial()
+
+    def set_initial(self, initial):
+        self.optimizers[0].set_initial(initial)

@@ -1,0 +1,150 @@
+"""Pareto front and cell decomposition of the non-dominated region: the host-side producer of the int32 cell
+tables the HVPoI kernel consumes (mirror of gpflowopt/pareto.py; once per BO iteration, off the hot path).
+
+``front`` / ``bounds.lb`` / ``bounds.ub`` are ndarray subclasses that also answer ``.value`` so code written
+against the reference's DataHolders keeps working.
+"""
+import numpy as np
+
+np_int_type = np.int32          # gpflow settings.dtypes.int_type
+stability = 1e-6                # gpflow settings.numerics.jitter_level
+
+
+class _Held(np.ndarray):
+    @property
+    def value(self):
+        return np.asarray(self)
+
+
+def _held(a, dtype=None):
+    return np.asarray(a, dtype=dtype).view(_Held)
+
+
+class BoundedVolumes(object):
+    """Axis-aligned cells given by lower / upper index (or coordinate) rows."""
+
+    @classmethod
+    def empty(cls, dim, dtype):
+        z = np.zeros((0, dim), dtype=dtype)
+        return cls(z.copy(), z.copy())
+
+    def __init__(self, lb, ub):
+        lb, ub = np.atleast_2d(lb), np.atleast_2d(ub)
+        assert lb.shape == ub.shape
+        self.lb = _held(lb)
+        self.ub = _held(ub)
+
+    def append(self, lb, ub):
+        self.lb = _held(np.vstack((self.lb, lb)), self.lb.dtype)
+        self.ub = _held(np.vstack((self.ub, ub)), self.ub.dtype)
+
+    def clear(self):
+        dtype, outdim = self.lb.dtype, self.lb.shape[1]
+        self.lb = _held(np.zeros((0, outdim), dtype=dtype))
+        self.ub = _held(np.zeros((0, outdim), dtype=dtype))
+
+    def size(self):
+        return np.prod(np.asarray(self.ub) - np.asarray(self.lb), axis=1)
+
+
+def non_dominated_sort(objectives):
+    """(non-dominated rows, number of points dominating each row)  -- gpflowopt/pareto.py:78-90."""
+    Y = np.asarray(objectives)
+    n = Y.shape[0]
+    dominance = np.zeros(n, dtype=np.int64)
+    for k in range(n):                        # O(n^2 R) without the n x n x R temporary
+        no_worse = np.all(Y[k] <= Y, axis=1)
+        better = np.any(Y[k] < Y, axis=1)
+        dominance += np.logical_and(no_worse, better)
+    return Y[dominance == 0], dominance
+
+
+class Pareto(object):
+    def __init__(self, Y, threshold=0):
+        self.threshold = threshold
+        self.Y = np.asarray(Y, dtype=np.float64)
+        self.bounds = BoundedVolumes.empty(self.Y.shape[1], np_int_type)
+        self.front = _held(np.zeros((0, self.Y.shape[1])))
+        self.update()
+
+    def _update_front(self):
+        current = np.asarray(self.front)
+        pf, _ = non_dominated_sort(self.Y)
+        self.front = _held(pf[pf[:, 0].argsort(), :])         # ascending on the first objective
+        return not np.array_equal(current, np.asarray(self.front))
+
+    def update(self, Y=None, generic_strategy=False):
+        self.Y = np.asarray(Y, dtype=np.float64) if Y is not None else self.Y
+        if self._update_front():                               # cells only change with the front
+            self.bounds.clear()
+            if generic_strategy or self.Y.shape[1] != 2:
+                self.divide_conquer_nd()
+            else:
+                self.bounds_2d()
+
+    def bounds_2d(self):
+        """Two objectives: P+1 strips, strip i spans ranks [i, i+1] in objective 0 and reaches from the ideal
+        point up to the objective-1 value of the (P-i)-th point (gpflowopt/pareto.py:238-255)."""
+        front = np.asarray(self.front)
+        assert front.shape[1] == 2
+        P = front.shape[0]
+        rank_rows = np.vstack((np.zeros(2, dtype=np_int_type), np.argsort(front, axis=0) + 1,
+                               np.full(2, P + 1, dtype=np_int_type)))
+        i = np.arange(P + 1)
+        lb = np.stack((i, np.zeros(P + 1, dtype=np.int64)), axis=1)
+        ub = np.stack((i + 1, rank_rows[P + 1 - i, 1]), axis=1)
+        self.bounds.lb = _held(lb, np_int_type)
+        self.bounds.ub = _held(ub, np_int_type)
+
+    def divide_conquer_nd(self):
+        """Any number of objectives: binary space partitioning over the rank grid of the front; a cell is kept when
+        its upper corner is not dominated, dropped when its lower corner is dominated, split otherwise
+        (gpflowopt/pareto.py:173-236)."""
+        front = np.asarray(self.front)
+        P, R = front.shape
+        cols = np.arange(R)
+        lo_pt = np.min(front, axis=0) - 1
+        hi_pt = np.max(front, axis=0) + 1
+        ext = np.vstack((lo_pt, front, hi_pt))
+        rows = np.vstack((np.zeros(R, dtype=np_int_type), np.argsort(front, axis=0) + 1,
+                          np.full(R, P + 1, dtype=np_int_type)))
+        total = np.prod(hi_pt - lo_pt)
+
+        def outside_dominated_region(corner):
+            # the corner is strictly smaller than every front member in at least one objective
+            return bool(np.all(np.any(corner < front, axis=1)))
+
+        kept_lb, kept_ub = [], []
+        todo = [(np.zeros(R, dtype=np_int_type), np.full(R, P + 1, dtype=np_int_type))]
+        while todo:
+            a, b = todo.pop()
+            lb_rows, ub_rows = rows[a, cols], rows[b, cols]
+            lb, ub = ext[lb_rows, cols], ext[ub_rows, cols]
+            if outside_dominated_region(ub - stability):
+                kept_lb.append(lb_rows)
+                kept_ub.append(ub_rows)
+            elif outside_dominated_region(lb + stability):
+                width = b - a
+                if np.any(width > 1) and np.all((np.prod(ub - lb) / total) > self.threshold):
+                    k = int(np.argmax(width))
+                    first = int(np.round(width[k] / 2.0))
+                    lower_half_top = b.copy()
+                    lower_half_top[k] -= first
+                    upper_half_bottom = a.copy()
+                    upper_half_bottom[k] += width[k] - first
+                    todo.append((a.copy(), lower_half_top))
+                    todo.append((upper_half_bottom, b.copy()))
+        if kept_lb:
+            self.bounds.lb = _held(np.vstack(kept_lb), np_int_type)
+            self.bounds.ub = _held(np.vstack(kept_ub), np_int_type)
+
+    def hypervolume(self, reference):
+        """Hypervolume indicator of the dominated region (gpflowopt/pareto.py:257-282); reporting metric."""
+        front = np.asarray(self.front)
+        reference = np.asarray(reference, dtype=np.float64)
+        min_pf = np.min(front, axis=0, keepdims=True)
+        pseudo = np.vstack((min_pf, front, reference[None, :]))
+        cols = np.arange(front.shape[1])
+        ub = pseudo[np.asarray(self.bounds.ub), cols]
+        lb = pseudo[np.asarray(self.bounds.lb), cols]
+        return float(np.prod(reference[None, :] - min_pf) - np.sum(np.prod(ub - lb, axis=1)))
