@@ -142,9 +142,10 @@ int gpfo_ctx_destroy(gpfo_ctx* ctx) {
 }
 
 static int effective_variant(const gpfo_ctx* ctx, int64_t N) {
-    if (ctx->variant >= 1 && ctx->variant <= 3) return ctx->variant;
-    // automatic: 16-candidate tiles once they fill the machine, 8-candidate tiles for small batches
-    return (N >= (int64_t)16 * ctx->num_sms) ? 1 : 2;
+    if (ctx->variant >= 1) return ctx->variant;
+    // automatic (v2 kernel): the widest candidate tile that still gives every SM a tile
+    if (N >= (int64_t)32 * ctx->num_sms) return 4;
+    return (N >= (int64_t)16 * ctx->num_sms) ? 5 : 6;
 }
 
 static int repack(gpfo_ctx* ctx, GpHost& g, int rbc) {
@@ -432,7 +433,7 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
         gio.write_moments = need_mom ? 1 : 0;
         gio.run_program = (!hv && g == ctx->ngps - 1) ? 1 : 0;
         CK(cudaEventRecord(ctx->ev[6], st));
-        CK(gpfo_contract_launch(st, variant, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
+        CK(gpfo_contract_launch(st, variant, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
         CK(cudaEventRecord(ctx->ev[7], st));
         ++launches;
         if (ctx->ngps > 1) {                 // per-GP timing needs a sync only when events are reused
@@ -512,7 +513,7 @@ int gpfo_predict(gpfo_ctx* ctx, int gp_id, const double* X, int64_t N, int D, do
     io.X = dX; io.N = N; io.mom_mean = ctx->dmom_mean; io.mom_var = ctx->dmom_var;
     io.part_val = ctx->dpart_val; io.part_idx = ctx->dpart_idx;
     io.write_moments = 1; io.run_program = 0;
-    CK(gpfo_contract_launch(st, variant, g.ddev, ctx->dprog, io, grid, D));
+    CK(gpfo_contract_launch(st, variant, g.kind, g.ddev, ctx->dprog, io, grid, D));
     // [slot][N] -> N x R
     for (int r = 0; r < g.R; ++r) {
         const size_t off = (size_t)(g.slot0 + r) * N;
@@ -533,7 +534,7 @@ int gpfo_timings_get(const gpfo_ctx* ctx, gpfo_timings* out) {
 
 int gpfo_set_variant(gpfo_ctx* ctx, int variant) {
     if (!ctx) return GPFO_ERR_STATE;
-    if (variant < 0 || variant > 3) return fail(ctx, GPFO_ERR_BAD_SHAPE, "variant must be 0..3");
+    if (variant < 0 || variant > 49) return fail(ctx, GPFO_ERR_BAD_SHAPE, "variant out of range");
     ctx->variant = variant;
     return GPFO_OK;
 }

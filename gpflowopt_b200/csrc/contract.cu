@@ -15,32 +15,7 @@
 // accumulators (RBW x NB m8n8 tiles) in registers.  L^-1 arrives as a pre-packed stream of 8x8 blocks in
 // DMMA lane order (one coalesced 16-byte load per lane per block, software-pipelined one half-column ahead);
 // K(X*, X) is generated in groups of KPC column blocks into shared memory in B-fragment order.
-#include "gpfo_internal.cuh"
-
-#define KPC 8            // column blocks (of 8 training points) per generated Kx group
-#define RMAX 4           // max output columns of one GP handled by the kernel
-
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-__device__ __forceinline__ double2 ldg_stream(const double* p) {
-    double2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-
-__device__ __forceinline__ double kx_from_r2(int kind, double variance, double r2) {
-    if (kind == GPFO_KERN_RBF) return variance * exp(-r2 / 2.0);
-    const double r = sqrt(r2 + 1e-12);
-    if (kind == GPFO_KERN_MATERN52) {
-        const double s5 = 2.2360679774997898;
-        return variance * (1.0 + s5 * r + (5.0 / 3.0) * (r * r)) * exp(-s5 * r);
-    }
-    const double s3 = 1.7320508075688772;
-    return variance * (1.0 + s3 * r) * exp(-s3 * r);
-}
+#include "contract_common.cuh"
 
 template <int NW, int RBW, int NB>
 struct ContractCfg {
@@ -55,7 +30,7 @@ struct ContractCfg {
     static_assert(RBW % 2 == 0, "two halves");
 };
 
-template <int NW, int RBW, int NB>
+template <int NW, int RBW, int NB, int ABL = 0>      // ABL: profiling ablations (1 = no Kx generation, 2 = no L^-1 loads)
 __global__ void __launch_bounds__(32 * NW, 1)
 contract_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ prog, EvalIO io) {
     using C = ContractCfg<NW, RBW, NB>;
@@ -131,7 +106,10 @@ contract_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ pr
 #pragma unroll
                 for (int rr = 0; rr < HALF; ++rr) {
                     const int rbl = (H * HALF + rr) * NW + w;
-                    if (rbl >= lo && rbl < nr) buf[rr] = ldg_stream(src + (int64_t)rbl * 64);
+                    if (rbl >= lo && rbl < nr) {
+                        if (ABL & 2) buf[rr] = make_double2(1e-3 * lane, 2e-3);
+                        else buf[rr] = ldg_stream(src + (int64_t)rbl * 64);
+                    }
                 }
             };
 
@@ -142,7 +120,8 @@ contract_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ pr
                     const int ksl = (w + NW * q) / NB;                     // k-step inside the group
                     const int j = (g * KPC) * 8 + 4 * ksl + gen_jl;        // training point
                     double val = 0.0;
-                    if (j < M) {
+                    if (ABL & 1) val = 1e-3 * j;
+                    else if (j < M) {
                         const double* __restrict__ xr = Xs + (size_t)j * D;
                         double dot = 0.0;
 #pragma unroll 4
@@ -261,49 +240,7 @@ contract_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ pr
         }
 
         // ---- epilogue (warp 0): un-scale, optional moment store, acquisition program, block argmax
-        if (w == 0) {
-            double val = 0.0;
-            long long idx = -1;
-            const int64_t n = n0 + lane;
-            if (lane < T && n < io.N) {
-                double mu[GPFO_MAX_SLOTS], va[GPFO_MAX_SLOTS];
-                const double fvar = variance - tot_ss;                      // Kdiag - reduce_sum(square(A), 0)
-#pragma unroll
-                for (int ro = 0; ro < RMAX; ++ro) {
-                    if (ro < R) {
-                        const int s = gp.slot0 + ro;
-                        // build_backward / build_backward_variance (transforms.py:112-140) for a diagonal map
-                        const double m_o = (tot_mv[ro] - gp.out_shift[ro]) / gp.out_scale[ro];
-                        const double v_o = fvar / (gp.out_scale[ro] * gp.out_scale[ro]);
-                        mu[s] = m_o; va[s] = v_o;
-                        if (io.write_moments) {
-                            io.mom_mean[(size_t)s * io.N + n] = m_o;
-                            io.mom_var[(size_t)s * io.N + n] = v_o;
-                        }
-                    }
-                }
-                if (io.run_program) {
-                    for (int s = 0; s < prog->nslots; ++s) {
-                        if (s < gp.slot0 || s >= gp.slot0 + R) {
-                            mu[s] = io.mom_mean[(size_t)s * io.N + n];
-                            va[s] = io.mom_var[(size_t)s * io.N + n];
-                        }
-                    }
-                    val = gpfo_run_program<false>(*prog, mu, va, 0.0, nullptr, nullptr, nullptr, nullptr);
-                    if (io.values) io.values[n] = val;
-                    idx = n;
-                }
-            }
-            if (io.run_program) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double ov = __shfl_xor_sync(0xffffffffu, val, o);
-                    const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
-                    if (gpfo_better(ov, oi, val, idx)) { val = ov; idx = oi; }
-                }
-                if (gpfo_better(val, idx, best_v, best_i)) { best_v = val; best_i = idx; }
-            }
-        }
+        if (w == 0) gpfo_tile_epilogue<T>(gp, prog, io, n0, lane, tot_ss, tot_mv, best_v, best_i);
     }
     if (tid == 0 && io.run_program) {
         io.part_val[blockIdx.x] = best_v;
@@ -347,20 +284,32 @@ void gpfo_argmax_final(cudaStream_t st, const double* part_val, const long long*
 //   1: NW=8, RBW=16, NB=2  -> T=16 candidates/tile, 1024-row chunks   (default for large N)
 //   2: NW=8, RBW=16, NB=1  -> T=8                                     (small N: more tiles)
 //   3: NW=8, RBW=8,  NB=4  -> T=32, 512-row chunks                    (half the L2 traffic per flop)
-template <int NW, int RBW, int NB>
+template <int NW, int RBW, int NB, int ABL = 0>
 static cudaError_t launch_variant(cudaStream_t st, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io, int grid,
                                   int D) {
     using C = ContractCfg<NW, RBW, NB>;
     const size_t smem = ((size_t)D * C::T + C::T + 2 * C::GROUP_SLOTS + (size_t)NW * C::T * (1 + RMAX)) * sizeof(double);
-    auto kern = contract_kernel<NW, RBW, NB>;
+    auto kern = contract_kernel<NW, RBW, NB, ABL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, C::THREADS, smem, st>>>(d_gp, d_prog, io);
     return cudaGetLastError();
 }
 
-int gpfo_contract_rbc(int variant) { return variant == 3 ? 64 : 128; }
-int gpfo_contract_tile(int variant) { return variant == 3 ? 32 : (variant == 2 ? 8 : 16); }
+// variant table.  1-3 (+ablations 1x/3x): v1 register-prefetch kernel above; 4-6 (+ablations 4x): v2 cp.async kernel
+// (contract2.cu).  Ablation results are meaningless numerically.
+struct VarInfo { int gen, rbc, tile; };
+static VarInfo var_info(int v) {
+    if (v == 4 || v == 9 || (v >= 40 && v <= 49)) return {2, 64, 32};
+    if (v == 7 || v == 8) return {2, 128, 16};
+    if (v == 5) return {2, 64, 16};
+    if (v == 6) return {2, 64, 8};
+    if (v == 3 || (v >= 30 && v <= 39)) return {1, 64, 32};
+    if (v == 2) return {1, 128, 8};
+    return {1, 128, 16};
+}
+int gpfo_contract_rbc(int variant) { return var_info(variant).rbc; }
+int gpfo_contract_tile(int variant) { return var_info(variant).tile; }
 
 int gpfo_contract_grid(int variant, int64_t N, int num_sms) {
     const int T = gpfo_contract_tile(variant);
@@ -368,11 +317,21 @@ int gpfo_contract_grid(int variant, int64_t N, int num_sms) {
     return (int)(ntiles < num_sms ? (ntiles > 0 ? ntiles : 1) : num_sms);
 }
 
-cudaError_t gpfo_contract_launch(cudaStream_t st, int variant, const GpDev* d_gp, const ProgramDev* d_prog,
+cudaError_t gpfo_contract2_launch(cudaStream_t st, int variant, int kind, const GpDev* d_gp, const ProgramDev* d_prog,
+                                  EvalIO io, int grid, int D);
+
+cudaError_t gpfo_contract_launch(cudaStream_t st, int variant, int kind, const GpDev* d_gp, const ProgramDev* d_prog,
                                  EvalIO io, int grid, int D) {
+    if (var_info(variant).gen == 2) return gpfo_contract2_launch(st, variant, kind, d_gp, d_prog, io, grid, D);
     switch (variant) {
         case 2: return launch_variant<8, 16, 1>(st, d_gp, d_prog, io, grid, D);
         case 3: return launch_variant<8, 8, 4>(st, d_gp, d_prog, io, grid, D);
+        case 11: return launch_variant<8, 16, 2, 1>(st, d_gp, d_prog, io, grid, D);
+        case 12: return launch_variant<8, 16, 2, 2>(st, d_gp, d_prog, io, grid, D);
+        case 13: return launch_variant<8, 16, 2, 3>(st, d_gp, d_prog, io, grid, D);
+        case 31: return launch_variant<8, 8, 4, 1>(st, d_gp, d_prog, io, grid, D);
+        case 32: return launch_variant<8, 8, 4, 2>(st, d_gp, d_prog, io, grid, D);
+        case 33: return launch_variant<8, 8, 4, 3>(st, d_gp, d_prog, io, grid, D);
         default: return launch_variant<8, 16, 2>(st, d_gp, d_prog, io, grid, D);
     }
 }

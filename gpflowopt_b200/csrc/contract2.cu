@@ -1,0 +1,382 @@
+// Contraction kernel v2 (the default hot kernel): same math and work decomposition as contract.cu, re-plumbed
+// after the first ncu capture (profiles/r01_contract_v1_summary.md):
+//   * L^-1 blocks travel global -> shared with cp.async (LDGSTS) into a per-warp ring, S column blocks deep.
+//     Every lane copies and later reads back exactly its own 16 bytes, so the ring is a private asynchronous
+//     FIFO: no registers are held by loads in flight, no cross-lane synchronisation is needed, and
+//     (S-1) * RBW * 512 B per warp are in flight (vs. one half column in v1, which left 23% long-scoreboard stalls).
+//   * K(X*, X) generation is branch-free (covariance family is a template parameter; sqrt and exp are inlined
+//     Newton / polynomial sequences without special-case paths) and processes GEN_ITERS elements per thread in
+//     lock step, so the FP64 pipe sees independent chains; half of the warps of every scheduler generate the
+//     next group BEFORE their DMMA work and the other half AFTER it, so generation overlaps tensor work.
+//   * 16 warps x <=128 registers (4 warps per scheduler) instead of 8 x 255.
+#include <type_traits>
+#include "contract_common.cuh"
+
+template <int NW, int RBW, int NB, int S>
+struct Contract2Cfg {
+    static constexpr int THREADS = 32 * NW;
+    static constexpr int RBC = NW * RBW;
+    static constexpr int T = 8 * NB;
+    static constexpr int GROUP_SLOTS = KPC * 2 * NB * 32;
+    static constexpr int GEN_ITERS = GROUP_SLOTS / THREADS;
+    static constexpr int RING_DOUBLES_PER_WARP = S * RBW * 64;
+    static_assert(NW % NB == 0, "per-thread candidate must be fixed");
+    static_assert(GROUP_SLOTS % THREADS == 0, "gen loop must tile");
+};
+
+__device__ __forceinline__ void cp_async16(unsigned smem_dst, const void* gmem_src) {     // smem_dst: shared-window address
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// sqrt(x) for normal positive x without the IEEE slow path: MUFU.RSQ64H seed, one cubically convergent step on
+// 1/sqrt, one correction step on sqrt.  Error < 1 ulp on the range used here (x = r^2 + 1e-12).
+__device__ __forceinline__ double fast_sqrt_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y * y, 1.0);
+    y = fma(y * e, fma(e, 0.375, 0.5), y);
+    double s = x * y;
+    const double d = fma(-s, s, x);
+    return fma(d, 0.5 * y, s);
+}
+
+// exp(x) for x <= 0 without special-case paths: clamp at -708 (result ~1e-308 instead of a denormal / 0),
+// n = round(x / ln 2), r = x - n ln 2 in two pieces, degree-13 Taylor polynomial on |r| <= ln2/2 (truncation
+// 4e-18), scaling by 2^n through the exponent field.
+__device__ __forceinline__ double fast_exp_neg(double x) {
+    x = fmax(x, -708.0);
+    const double magic = 6755399441055744.0;                 // 1.5 * 2^52
+    const double t = fma(x, 1.4426950408889634, magic);
+    const double n = t - magic;
+    double r = fma(n, -6.93147180559945286e-01, x);
+    r = fma(n, -2.31904681384629956e-17, r);
+    double p = 1.6059043836821613e-10;                       // 1/13!
+    p = fma(p, r, 2.0876756987868100e-09);                   // 1/12!
+    p = fma(p, r, 2.5052108385441720e-08);                   // 1/11!
+    p = fma(p, r, 2.7557319223985893e-07);                   // 1/10!
+    p = fma(p, r, 2.7557319223985888e-06);                   // 1/9!
+    p = fma(p, r, 2.4801587301587302e-05);                   // 1/8!
+    p = fma(p, r, 1.9841269841269841e-04);                   // 1/7!
+    p = fma(p, r, 1.3888888888888889e-03);                   // 1/6!
+    p = fma(p, r, 8.3333333333333332e-03);                   // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);                   // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);                   // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int ni = __double2loint(t);                        // low word of t holds n (two's complement)
+    return __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
+}
+
+template <int KIND>
+__device__ __forceinline__ double kx_branchless(double variance, double r2) {
+    if (KIND == GPFO_KERN_RBF) return variance * fast_exp_neg(-0.5 * r2);      // r2 >= -tiny: fmin keeps x <= 0
+    const double r = fast_sqrt_pos(r2 + 1e-12);
+    if (KIND == GPFO_KERN_MATERN52) {
+        const double s5 = 2.2360679774997898;
+        return variance * (1.0 + s5 * r + (5.0 / 3.0) * (r * r)) * fast_exp_neg(-s5 * r);
+    }
+    const double s3 = 1.7320508075688772;
+    return variance * (1.0 + s3 * r) * fast_exp_neg(-s3 * r);
+}
+
+template <int NW, int RBW, int NB, int S, int KIND, int ABL>
+__global__ void __launch_bounds__(32 * NW, 1)
+contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ prog, EvalIO io) {
+    using C = Contract2Cfg<NW, RBW, NB, S>;
+    constexpr int T = C::T;
+    extern __shared__ __align__(16) double smem[];
+    const int D = gpp->D;
+    double* ring = smem;                                             // [NW][S][RBW][64]
+    double* kx = ring + (size_t)NW * C::RING_DOUBLES_PER_WARP;       // [2][GROUP_SLOTS]
+    double* red = kx + 2 * C::GROUP_SLOTS;                           // [NW][T][1+RMAX]
+    double* xc = red + (size_t)NW * T * (1 + RMAX);                  // [D][T]
+    double* x2 = xc + (size_t)D * T;                                 // [T]
+    double* tot = x2 + T;                                            // [T][1+RMAX] running colsum(A^2), A^T V
+    double* sbest = tot + T * (1 + RMAX);                            // [2] best value, best index (as bits)
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+
+    const GpDev& gp = *gpp;
+    const int M = gp.M, R = gp.R;
+    const double variance = gp.variance;
+    const double* __restrict__ Xs = gp.Xs;
+    const double* __restrict__ xn = gp.xn;
+    const double* __restrict__ Vv = gp.V;
+    const PackGeom geom = gp.geom;
+    double* myring = ring + (size_t)w * C::RING_DOUBLES_PER_WARP + 2 * lane;
+    const unsigned myring_s = (unsigned)__cvta_generic_to_shared(myring);     // same location, shared-window address
+
+    const int gen_nb = w % NB;
+    const int gen_n = 8 * gen_nb + (lane >> 2);
+    const int gen_jl = lane & 3;
+    const bool gen_first = ((w >> 2) & 1) == 0;          // warps w, w+4, w+8, w+12 share a scheduler: 2 + 2
+
+    if (tid == 0) { sbest[0] = 0.0; reinterpret_cast<long long*>(sbest)[1] = -1; }
+
+    const int64_t ntiles = (io.N + T - 1) / T;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t n0 = tile * T;
+        __syncthreads();
+        if (tid < T * (1 + RMAX)) tot[tid] = 0.0;
+        for (int e = tid; e < T * D; e += C::THREADS) {
+            const int n = e / D, d = e - n * D;
+            double x = 0.0;
+            if (n0 + n < io.N) x = io.X[(size_t)(n0 + n) * D + d];
+            const double xt = __dadd_rn(__dmul_rn(x, gp.in_scale[d]), gp.in_shift[d]);
+            xc[d * T + n] = xt / gp.ell[d];
+        }
+        __syncthreads();
+        if (tid < T) {
+            double s = 0.0;
+            for (int d = 0; d < D; ++d) s += xc[d * T + tid] * xc[d * T + tid];
+            x2[tid] = s;
+        }
+        __syncthreads();
+
+        for (int p = 0; p < geom.nchunks; ++p) {
+            const int nr = pg_chunk_rows(geom, p);
+            const int kd0 = p * geom.rbc;                 // first diagonal column block of this chunk
+            const int kp_end = kd0 + nr;
+            const double* __restrict__ cbase = gp.packed + pg_chunk_base(geom, p) * 64 + 2 * lane;
+
+            double acc[RBW][NB][2];
+#pragma unroll
+            for (int r = 0; r < RBW; ++r)
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) { acc[r][nb][0] = 0.0; acc[r][nb][1] = 0.0; }
+
+            // ---- L^-1 stream state of this warp: running source pointer (block (kp_issue, row block w)), ring cursors.
+            // Block (kp, r) lives at P(kp) + r*NW*64 doubles; P advances by nr blocks per dense column block and by
+            // (nr - kd - 1) per diagonal one (pg_col_base in closed form, without 64-bit multiplies in the loop).
+            const double* __restrict__ src_issue = cbase + (int64_t)w * 64;
+            int kp_issue = 0, wr_stage = 0, rd_stage = 0;
+            // asynchronous copy of this warp's blocks of column block kp_issue into ring stage wr_stage (one commit group)
+            auto issue = [&]() {
+                if (!(ABL & 2) && kp_issue < kp_end) {
+                    const int kd = kp_issue - kd0;
+                    const int lo = kd > 0 ? kd : 0;
+                    const unsigned dst = myring_s + wr_stage * 8;
+#pragma unroll
+                    for (int r = 0; r < RBW; ++r) {
+                        const int rbl = r * NW + w;
+                        if (rbl >= lo && rbl < nr) cp_async16(dst + r * 512, src_issue + r * (NW * 64));
+                    }
+                    src_issue += (kd < 0 ? nr : nr - kd - 1) * 64;
+                }
+                cp_async_commit();
+                ++kp_issue;
+                wr_stage = (wr_stage == (S - 1) * RBW * 64) ? 0 : wr_stage + RBW * 64;
+            };
+
+            auto gen_group = [&](int g, double* __restrict__ dst) {
+                double dot[C::GEN_ITERS];
+                int jj[C::GEN_ITERS];
+#pragma unroll
+                for (int q = 0; q < C::GEN_ITERS; ++q) {
+                    const int ksl = (w + NW * q) / NB;
+                    const int j = (g * KPC) * 8 + 4 * ksl + gen_jl;
+                    jj[q] = j < M ? j : M - 1;            // clamp: keeps the loads in range, result masked below
+                    dot[q] = 0.0;
+                }
+                if (!(ABL & 1)) {
+                    for (int d = 0; d < D; ++d) {
+                        const double c = xc[d * T + gen_n];
+#pragma unroll
+                        for (int q = 0; q < C::GEN_ITERS; ++q) dot[q] = fma(__ldg(Xs + (size_t)jj[q] * D + d), c, dot[q]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < C::GEN_ITERS; ++q) {
+                    const int ksl = (w + NW * q) / NB;
+                    const int j = (g * KPC) * 8 + 4 * ksl + gen_jl;
+                    double val;
+                    if (ABL & 1) val = 1e-3 * j;
+                    else {
+                        const double r2 = (-2.0 * dot[q] + __ldg(xn + jj[q])) + x2[gen_n];    // square_dist, expanded form
+                        val = kx_branchless<KIND>(variance, KIND == GPFO_KERN_RBF ? fmax(r2, 0.0) : r2);
+                    }
+                    dst[(ksl * NB + gen_nb) * 32 + lane] = j < M ? val : 0.0;
+                }
+            };
+
+            // one column block: B fragments from the Kx group buffer, A fragments from the ring, RBW*2*NB DMMAs.
+            // FULL = every row block of this warp is active (dense column block of a full chunk): no predicates.
+            auto mma_kp = [&](const double* __restrict__ kbk, int lo, auto full_tag) {
+                constexpr bool FULL = decltype(full_tag)::value;
+                issue();
+                double bf[2][NB];
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) bf[h][nb] = kbk[(h * NB + nb) * 32];
+                cp_async_wait<S - 1>();               // this thread's copies for the current column block have landed
+                const double* stage = myring + rd_stage;
+#pragma unroll
+                for (int r = 0; r < RBW; ++r) {
+                    const int rbl = r * NW + w;
+                    if (FULL || (rbl >= lo && rbl < nr)) {
+                        double2 a;
+                        if (ABL & 2) a = make_double2(1e-3 * lane, 2e-3);
+                        else a = *reinterpret_cast<const double2*>(stage + r * 64);
+#pragma unroll
+                        for (int nb = 0; nb < NB; ++nb) dmma884(acc[r][nb][0], acc[r][nb][1], a.x, bf[0][nb]);
+#pragma unroll
+                        for (int nb = 0; nb < NB; ++nb) dmma884(acc[r][nb][0], acc[r][nb][1], a.y, bf[1][nb]);
+                    }
+                }
+                rd_stage = (rd_stage == (S - 1) * RBW * 64) ? 0 : rd_stage + RBW * 64;
+            };
+            auto mma_group = [&](int g) {
+                const double* __restrict__ kb = kx + (g & 1) * C::GROUP_SLOTS + lane;
+                const int k0 = g * KPC;
+                const int k1 = (k0 + KPC < kp_end) ? k0 + KPC : kp_end;
+                if (nr == C::RBC && k1 <= kd0) {       // whole group in the dense part of a full chunk
+#pragma unroll 1
+                    for (int kp = k0; kp < k1; ++kp) mma_kp(kb + (kp - k0) * (2 * NB * 32), 0, std::true_type());
+                } else {
+#pragma unroll 1
+                    for (int kp = k0; kp < k1; ++kp)
+                        mma_kp(kb + (kp - k0) * (2 * NB * 32), kp > kd0 ? kp - kd0 : 0, std::false_type());
+                }
+            };
+
+            const int ngroups = (kp_end + KPC - 1) / KPC;
+            gen_group(0, kx);
+#pragma unroll
+            for (int s = 0; s < S - 1; ++s) issue();
+            __syncthreads();
+            for (int g = 0; g < ngroups; ++g) {
+                const bool more = g + 1 < ngroups;
+                double* nxt = kx + ((g + 1) & 1) * C::GROUP_SLOTS;
+                if (gen_first) {
+                    if (more) gen_group(g + 1, nxt);
+                    mma_group(g);
+                } else {
+                    mma_group(g);
+                    if (more) gen_group(g + 1, nxt);
+                }
+                __syncthreads();
+            }
+            cp_async_wait<0>();
+
+            // ---- chunk reduction (fixed order -> deterministic)
+            {
+                double ss[NB][2];
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) { ss[nb][0] = 0.0; ss[nb][1] = 0.0; }
+#pragma unroll
+                for (int r = 0; r < RBW; ++r)
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) {
+                        ss[nb][0] += acc[r][nb][0] * acc[r][nb][0];
+                        ss[nb][1] += acc[r][nb][1] * acc[r][nb][1];
+                    }
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        double v = ss[nb][c];
+                        v += __shfl_xor_sync(0xffffffffu, v, 4);
+                        v += __shfl_xor_sync(0xffffffffu, v, 8);
+                        v += __shfl_xor_sync(0xffffffffu, v, 16);
+                        if (lane < 4) red[(w * T + nb * 8 + 2 * lane + c) * (1 + RMAX)] = v;
+                    }
+                for (int ro = 0; ro < R; ++ro) {
+                    double mv[NB][2];
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) { mv[nb][0] = 0.0; mv[nb][1] = 0.0; }
+#pragma unroll
+                    for (int r = 0; r < RBW; ++r) {
+                        const int rbl = r * NW + w;
+                        double v = 0.0;
+                        if (rbl < nr) v = __ldg(Vv + (size_t)(8 * (kd0 + rbl) + (lane >> 2)) * R + ro);
+#pragma unroll
+                        for (int nb = 0; nb < NB; ++nb) {
+                            mv[nb][0] += acc[r][nb][0] * v;
+                            mv[nb][1] += acc[r][nb][1] * v;
+                        }
+                    }
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            double v = mv[nb][c];
+                            v += __shfl_xor_sync(0xffffffffu, v, 4);
+                            v += __shfl_xor_sync(0xffffffffu, v, 8);
+                            v += __shfl_xor_sync(0xffffffffu, v, 16);
+                            if (lane < 4) red[(w * T + nb * 8 + 2 * lane + c) * (1 + RMAX) + 1 + ro] = v;
+                        }
+                }
+            }
+            __syncthreads();
+            if (tid < T * (1 + RMAX)) {                  // thread (n, k): fixed warp order -> deterministic
+                const int n = tid / (1 + RMAX), k = tid - n * (1 + RMAX);
+                if (k <= R) {
+                    double a = tot[tid];
+                    for (int ww = 0; ww < NW; ++ww) a += red[(ww * T + n) * (1 + RMAX) + k];
+                    tot[tid] = a;
+                }
+            }
+            __syncthreads();
+        }
+        if (w == 0) {
+            double tot_mv[RMAX];
+            const int ln = lane < T ? lane : 0;
+#pragma unroll
+            for (int ro = 0; ro < RMAX; ++ro) tot_mv[ro] = tot[ln * (1 + RMAX) + 1 + ro];
+            double best_v = sbest[0];
+            long long best_i = reinterpret_cast<long long*>(sbest)[1];
+            gpfo_tile_epilogue<T>(gp, prog, io, n0, lane, tot[ln * (1 + RMAX)], tot_mv, best_v, best_i);
+            if (lane == 0) { sbest[0] = best_v; reinterpret_cast<long long*>(sbest)[1] = best_i; }
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && io.run_program) {
+        io.part_val[blockIdx.x] = sbest[0];
+        io.part_idx[blockIdx.x] = reinterpret_cast<long long*>(sbest)[1];
+    }
+}
+
+template <int NW, int RBW, int NB, int S, int KIND, int ABL>
+static cudaError_t launch2_kind(cudaStream_t st, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io, int grid, int D) {
+    using C = Contract2Cfg<NW, RBW, NB, S>;
+    const size_t smem = ((size_t)NW * C::RING_DOUBLES_PER_WARP + 2 * C::GROUP_SLOTS + (size_t)NW * C::T * (1 + RMAX) +
+                         (size_t)D * C::T + C::T + C::T * (1 + RMAX) + 2) * sizeof(double);
+    auto kern = contract2_kernel<NW, RBW, NB, S, KIND, ABL>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, C::THREADS, smem, st>>>(d_gp, d_prog, io);
+    return cudaGetLastError();
+}
+
+template <int NW, int RBW, int NB, int S, int ABL = 0>
+static cudaError_t launch2(cudaStream_t st, int kind, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io, int grid,
+                           int D) {
+    switch (kind) {
+        case GPFO_KERN_RBF: return launch2_kind<NW, RBW, NB, S, GPFO_KERN_RBF, ABL>(st, d_gp, d_prog, io, grid, D);
+        case GPFO_KERN_MATERN52: return launch2_kind<NW, RBW, NB, S, GPFO_KERN_MATERN52, ABL>(st, d_gp, d_prog, io, grid, D);
+        default: return launch2_kind<NW, RBW, NB, S, GPFO_KERN_MATERN32, ABL>(st, d_gp, d_prog, io, grid, D);
+    }
+}
+
+// v2 variants (all use 64-row-block = 512-row chunks):
+//   4: 16 warps, RBW=4, NB=4 (T=32), 4-stage ring     5: 16 warps, RBW=4, NB=2 (T=16), 4-stage ring
+//   6: 16 warps, RBW=4, NB=1 (T=8)                    41/42/43: ablations of 4 (no gen / no loads / neither)
+//   7: 16 warps, RBW=8, NB=2 (T=16), 1024-row chunks, 3-stage ring      8: same, 2-stage ring      9: as 4, 6-stage ring
+cudaError_t gpfo_contract2_launch(cudaStream_t st, int variant, int kind, const GpDev* d_gp, const ProgramDev* d_prog,
+                                  EvalIO io, int grid, int D) {
+    switch (variant) {
+        case 5: return launch2<16, 4, 2, 4>(st, kind, d_gp, d_prog, io, grid, D);
+        case 7: return launch2<16, 8, 2, 3>(st, kind, d_gp, d_prog, io, grid, D);
+        case 8: return launch2<16, 8, 2, 2>(st, kind, d_gp, d_prog, io, grid, D);
+        case 9: return launch2<16, 4, 4, 6>(st, kind, d_gp, d_prog, io, grid, D);
+        case 6: return launch2<16, 4, 1, 4>(st, kind, d_gp, d_prog, io, grid, D);
+        case 41: return launch2<16, 4, 4, 4, 1>(st, kind, d_gp, d_prog, io, grid, D);
+        case 42: return launch2<16, 4, 4, 4, 2>(st, kind, d_gp, d_prog, io, grid, D);
+        case 43: return launch2<16, 4, 4, 4, 3>(st, kind, d_gp, d_prog, io, grid, D);
+        default: return launch2<16, 4, 4, 4>(st, kind, d_gp, d_prog, io, grid, D);
+    }
+}

@@ -229,7 +229,7 @@ void gpfo_prepare_inputs(cudaStream_t st, const double* dX, int M, int Mp, int D
 int gpfo_contract_rbc(int variant);
 int gpfo_contract_tile(int variant);
 int gpfo_contract_grid(int variant, int64_t N, int num_sms);
-cudaError_t gpfo_contract_launch(cudaStream_t st, int variant, const GpDev* d_gp, const ProgramDev* d_prog,
+cudaError_t gpfo_contract_launch(cudaStream_t st, int variant, int kind, const GpDev* d_gp, const ProgramDev* d_prog,
                                  EvalIO io, int grid, int D);
 void gpfo_argmax_final(cudaStream_t st, const double* part_val, const long long* part_idx, int nparts,
                        double* out_val, long long* out_idx);

@@ -143,8 +143,11 @@ class SciPyOptimizer(Optimizer):
     def _optimize(self, objective):
         def objective1d(X):
             return tuple(arr.ravel() for arr in objective(X))
+        config = dict(self.config)
+        if not config['options'].get('disp'):          # recent SciPy warns about an explicit disp=False
+            config['options'] = {k: v for k, v in config['options'].items() if k != 'disp'}
         return minimize(fun=objective1d, x0=self.get_initial().ravel(), jac=self.gradient_enabled(),
-                        bounds=list(zip(self.domain.lower, self.domain.upper)), **self.config)
+                        bounds=list(zip(self.domain.lower, self.domain.upper)), **config)
 
 
 class StagedOptimizer(Optimizer):

@@ -1,0 +1,183 @@
+"""-m gpu: the drop-in Python surface (Acquisition.evaluate / set_data / enable_scaling / + / *, MCOptimizer,
+CandidateOptimizer) against oracle objects built from the same numbers.  Mirrors the reference's
+testing/unit/test_acquisition.py and test_implementations.py."""
+import numpy as np
+import pytest
+
+import gpflowopt_b200 as gpfo
+from gpflowopt_b200 import synthetic
+from gpflowopt_b200.acquisition import (AcquisitionProduct, AcquisitionSum, ExpectedImprovement,
+                                        HVProbabilityOfImprovement, LowerConfidenceBound, MCMCAcquistion,
+                                        ProbabilityOfFeasibility, ProbabilityOfImprovement)
+from gpflowopt_b200.design import FactorialDesign, RandomDesign
+from gpflowopt_b200.domain import ContinuousParameter
+from gpflowopt_b200.optim import CandidateOptimizer, MCOptimizer
+from oracle import acq as oacq, gp as ogp, pareto as opareto
+from helpers import assert_parity, near_tie, oracle_gp
+
+pytestmark = pytest.mark.gpu
+
+DOMAIN = np.sum([ContinuousParameter("x{0}".format(i), -1, 1) for i in range(1, 3)])
+
+
+def parabola2d(X):
+    return np.atleast_2d(np.sum(X ** 2, axis=1)).T
+
+
+def plane(X):
+    return X[:, [0]] - 0.5
+
+
+def _design(n=16, seed=3):
+    return -1 + 2 * np.random.RandomState(seed).rand(n, 2)
+
+
+def _gpr(X, Y, kern=gpfo.RBF, ell=(0.6, 0.9), var=1.3, noise=1e-3):
+    return gpfo.GPR(X, Y, kern(2, variance=var, lengthscales=np.array(ell), ARD=True), noise_variance=noise)
+
+
+def _ogp(X, Y, kind=ogp.RBF, ell=(0.6, 0.9), var=1.3, noise=1e-3, scaled=False):
+    h = dict(lengthscales=np.array(ell), variance=var, noise_variance=noise)
+    if scaled:
+        return oracle_gp(X, Y, kind, h, lower=DOMAIN.lower, upper=DOMAIN.upper, normalize=True)
+    return oracle_gp(X, Y, kind, h)
+
+
+def test_shapes_and_types():                               # reference test_implementations.py:19-33
+    X = _design()
+    acqs = [ExpectedImprovement(_gpr(X, parabola2d(X))), ProbabilityOfImprovement(_gpr(X, parabola2d(X))),
+            ProbabilityOfFeasibility(_gpr(X, parabola2d(X))), LowerConfidenceBound(_gpr(X, parabola2d(X))),
+            HVProbabilityOfImprovement([_gpr(X, parabola2d(X)), _gpr(X, plane(X))])]
+    Xc = RandomDesign(10, DOMAIN).generate()
+    for a in acqs:
+        p = a.evaluate(Xc)
+        assert isinstance(p, np.ndarray) and p.shape == (10, 1) and p.dtype == np.float64
+
+
+def test_ei_poi_pof_lcb_against_oracle_with_scaling():
+    X = _design(20)
+    Y = parabola2d(X)
+    Xc = RandomDesign(300, DOMAIN).generate()
+    for cls, kind in ((ExpectedImprovement, 'ei'), (ProbabilityOfImprovement, 'poi')):
+        a = cls(_gpr(X, Y, gpfo.Matern52))
+        a.enable_scaling(DOMAIN)                            # domain -> unit cube, Y normalised (bo.py:98-100)
+        g = _ogp(X, Y, ogp.MATERN52, scaled=True)
+        fmin = oacq.fmin_of(g, X)
+        got = a.evaluate(Xc)
+        assert_parity(a.fmin, fmin, what="fmin")
+        assert_parity(got, oacq.Leaf(kind, g, fmin[0]).value(Xc), what=kind)
+    pof = ProbabilityOfFeasibility(_gpr(X, plane(X)), threshold=0.1)
+    g = _ogp(X, plane(X))
+    assert_parity(pof.evaluate(Xc), oacq.Leaf('pof', g, 0.1).value(Xc), what="pof")
+    np.testing.assert_array_equal(pof.feasible_data_index(), oacq.pof_feasible(g, X, 0.1, 0.5))
+    lcb = LowerConfidenceBound(_gpr(X, Y), 3.2)
+    g = _ogp(X, Y)
+    assert_parity(lcb.evaluate(Xc), oacq.Leaf('lcb', g, 3.2).value(Xc), what="lcb")
+    lcb.sigma = np.array(0.0)                               # reference test_implementations.py:162-168
+    np.testing.assert_allclose(lcb.evaluate(Xc), lcb.models[0].predict_f(Xc)[0], rtol=1e-7)
+
+
+def test_validity_properties():                             # reference test_implementations.py:64-74, 130-136
+    X = _design(25, seed=11)
+    ei = ExpectedImprovement(_gpr(X, parabola2d(X)))
+    rs = np.random.RandomState(0)
+    Xcenter = rs.rand(20, 2) * 0.25 - 0.125
+    Xr = rs.rand(100, 2) * 2 - 1
+    Xborder = np.vstack((Xr[np.abs(Xr[:, 0]) > 0.8], Xr[np.abs(Xr[:, 1]) > 0.8]))
+    assert np.min(ei.evaluate(Xcenter)) > np.max(ei.evaluate(Xborder))
+    assert np.all(ei.feasible_data_index())
+    pof = ProbabilityOfFeasibility(_gpr(X, plane(X)))
+    X1, X2 = rs.rand(10, 2) / 4, rs.rand(10, 2) / 4 + 0.75
+    assert np.all(pof.evaluate(X1) > 0.85) and np.all(pof.evaluate(X2) < 0.15)
+
+
+def test_constrained_ei_tree_and_lazy_setup():
+    """EI * PoF: constraints are set up first, fmin is taken over the model-feasible points only
+    (reference test_acquisition.py:259-280, acquisition.py:334-347, ei.py:63-68)."""
+    X = _design(24, seed=5)
+    Yo, Yc = parabola2d(X), -parabola2d(X) + 0.5
+    ei, pof = ExpectedImprovement(_gpr(X, Yo)), ProbabilityOfFeasibility(_gpr(X, Yc))
+    joint = ei * pof
+    assert isinstance(joint, AcquisitionProduct)
+    np.testing.assert_array_equal(joint.objective_indices(), [0])
+    np.testing.assert_array_equal(joint.constraint_indices(), [1])
+    go, gc = _ogp(X, Yo), _ogp(X, Yc)
+    feas = oacq.pof_feasible(gc, X)
+    assert 0 < feas.sum() < len(feas)
+    fmin = oacq.fmin_of(go, X[feas])
+    Xc = RandomDesign(500, DOMAIN).generate()
+    got = joint.evaluate(Xc)
+    assert_parity(ei.fmin, fmin, what="constrained fmin")
+    assert ei.fmin > np.min(Yo)
+    ref = oacq.Agg('prod', [oacq.Leaf('ei', go, fmin[0]), oacq.Leaf('pof', gc, 0.0)]).value(Xc)
+    assert_parity(got, ref, what="EI*PoF")
+    bv, bi = joint.argmax(Xc)
+    assert bi == int(np.argmax(ref)) or near_tie(ref, bi, int(np.argmax(ref)))
+    # set_data slices Y column-wise over the operands and re-arms the lazy setup (acquisition.py:145-169, 328-332)
+    Xn = np.vstack((X, [[0.0, 0.0]]))
+    Yn = np.hstack((parabola2d(Xn), -parabola2d(Xn) + 0.5))
+    assert joint.set_data(Xn, Yn) == 2 and joint._needs_setup
+    got2 = joint.evaluate(Xc)
+    assert not joint._needs_setup
+    go2, gc2 = _ogp(Xn, Yn[:, [0]]), _ogp(Xn, Yn[:, [1]])
+    fmin2 = oacq.fmin_of(go2, Xn[oacq.pof_feasible(gc2, Xn)])
+    ref2 = oacq.Agg('prod', [oacq.Leaf('ei', go2, fmin2[0]), oacq.Leaf('pof', gc2, 0.0)]).value(Xc)
+    assert_parity(got2, ref2, what="EI*PoF after set_data")
+
+
+def test_aggregation_algebra_and_flattening():             # reference test_acquisition.py:170-191, 297-333
+    X = _design()
+    Y = parabola2d(X)
+    a = [ExpectedImprovement(_gpr(X, Y)) for _ in range(4)]
+    s = a[0] + a[1] + a[2]
+    assert isinstance(s, AcquisitionSum) and s.operands == [a[0], a[1], a[2]]
+    Xc = FactorialDesign(4, DOMAIN).generate()
+    single = ExpectedImprovement(_gpr(X, Y)).evaluate(Xc)
+    np.testing.assert_allclose(s.evaluate(Xc), 3 * single, rtol=1e-12)
+    b = [ExpectedImprovement(_gpr(X, Y)) for _ in range(2)]
+    pr = b[0] * b[1]
+    np.testing.assert_allclose(pr.evaluate(Xc), single ** 2, rtol=1e-12)
+    c = [ExpectedImprovement(_gpr(X, Y)) for _ in range(3)]
+    nested = c[0] * (ProbabilityOfFeasibility(_gpr(X, plane(X))) + c[1])
+    np.testing.assert_array_equal(nested.objective_indices(), [0, 2])
+    np.testing.assert_array_equal(nested.constraint_indices(), [1])
+    assert nested.evaluate(Xc).shape == (16, 1)
+    mc = MCMCAcquistion(c[2], 3)
+    np.testing.assert_allclose(mc.evaluate(Xc), single, rtol=1e-12)     # identical hyper-parameters -> the mean is EI
+
+
+def test_hvpoi_class_against_oracle():
+    X = -1 + 2 * np.random.RandomState(2).rand(30, 2)
+    t = 1 / np.sqrt(2)
+    Y = np.hstack((1 - np.exp(-((X[:, [0]] - t) ** 2 + (X[:, [1]] - t) ** 2)),
+                   1 - np.exp(-((X[:, [0]] + t) ** 2 + (X[:, [1]] + t) ** 2))))        # vlmop2 (testing/utility.py:29-36)
+    hv = HVProbabilityOfImprovement([_gpr(X, Y[:, [0]], gpfo.Matern32), _gpr(X, Y[:, [1]], gpfo.Matern32)])
+    Xc = RandomDesign(400, DOMAIN).generate()
+    got = hv.evaluate(Xc)
+    gs = [_ogp(X, Y[:, [j]], ogp.MATERN32) for j in range(2)]
+    F = np.hstack([g.predict(X)[0] for g in gs])
+    p = opareto.Pareto(np.zeros((1, 2)))
+    p.update(F)
+    np.testing.assert_array_equal(np.asarray(hv.pareto.bounds.lb), p.lb)
+    ref = oacq.HVPoI(gs, p.front, p.lb, p.ub).value(Xc)
+    assert_parity(got, ref, what="HVPoI class")
+
+
+def test_mc_and_candidate_optimizer_fused_equals_generic():
+    """The fused device argmax must select what np.argmin over -evaluate() selects (optim.py:155-164)."""
+    X = _design(20, seed=8)
+    ei = ExpectedImprovement(_gpr(X, parabola2d(X)))
+
+    def inverse_acquisition(x):
+        return -ei.evaluate(np.atleast_2d(x))
+    cand = RandomDesign(3000, DOMAIN).generate()
+    generic = CandidateOptimizer(DOMAIN, cand).optimize(inverse_acquisition)
+    inverse_acquisition.acquisition = ei
+    fused = CandidateOptimizer(DOMAIN, cand).optimize(inverse_acquisition)
+    assert fused.success and fused.nfev == 3000 and fused.x.shape == (1, 2)
+    np.testing.assert_array_equal(fused.x, generic.x)
+    np.testing.assert_array_equal(np.ravel(fused.fun), np.ravel(generic.fun))
+    np.random.seed(5)
+    r = MCOptimizer(DOMAIN, 2000).optimize(inverse_acquisition)
+    assert r.success and r.x in DOMAIN and r.nfev == 2000
+    assert np.allclose(-ei.evaluate(r.x), r.fun)

@@ -1,0 +1,248 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, called through the C-ABI, against the CPU oracle on the same
+seeded inputs.  Tolerance (written here, from BASELINE.json north_star "rel. 1e-9 (float64)"): scale-relative 1e-9,
+see helpers.RTOL; argmax index identical except on near-ties within that tolerance."""
+import numpy as np
+import pytest
+
+from gpflowopt_b200 import _lib, synthetic
+from oracle import acq as oacq, gp as ogp, pareto as opareto
+from helpers import RTOL, assert_parity, near_tie, oracle_gp, upload_oracle_gp
+
+pytestmark = pytest.mark.gpu
+
+KINDS = {"rbf": ogp.RBF, "matern52": ogp.MATERN52, "matern32": ogp.MATERN32}
+
+
+def _model(M, D, kind, noise=1e-2, scaled=False, seed=1234, R=1):
+    X, Y = synthetic.training_set(M, D, seed=seed, constraint=(R == 2))
+    h = synthetic.hypers(D, noise)
+    if scaled:                     # domain [-5, 10]^D with input scaling and output normalisation
+        lo, up = np.full(D, -5.0), np.full(D, 10.0)
+        return oracle_gp(lo + X * (up - lo), 3.0 * Y + 2.0, KINDS[kind], h, lower=lo, upper=up, normalize=True), lo, up
+    return oracle_gp(X, Y, KINDS[kind], h), np.zeros(D), np.ones(D)
+
+
+def _cands(N, D, lo, up, seed=4321):
+    return lo + synthetic.candidates(N, D, seed=seed) * (up - lo)
+
+
+@pytest.mark.parametrize("M", [1, 7, 64, 65, 200, 513])
+def test_factor_matches_lapack(ctx, M):
+    g, _, _ = _model(M, 3, "matern52")
+    upload_oracle_gp(ctx, 0, g)
+    L, Linv, V = ctx.gp_get_factor(0, M, 1)
+    Lo, Vo = g.factor()
+    assert_parity(L, Lo, tol=1e-12, what="L")
+    assert_parity(V, Vo, tol=1e-11, what="V")
+    assert np.max(np.abs(Linv @ Lo - np.eye(M))) < 1e-10
+    assert np.all(np.triu(Linv, 1) == 0.0) and np.all(np.triu(L, 1) == 0.0)
+
+
+def test_not_positive_definite_raises(ctx):
+    X = np.zeros((8, 2))                                   # 8 identical points, no noise: singular K
+    with pytest.raises(_lib.NotPositiveDefiniteError):
+        ctx.gp_set(0, X, np.zeros((8, 1)), _lib.KERN_RBF, [1.0, 1.0], 1.0, 0.0)
+
+
+@pytest.mark.parametrize("kind", ["rbf", "matern52", "matern32"])
+@pytest.mark.parametrize("M,D,scaled", [(20, 2, False), (100, 3, True), (515, 8, False), (1100, 16, True)])
+def test_predict_parity(ctx, kind, M, D, scaled):
+    g, lo, up = _model(M, D, kind, scaled=scaled)
+    upload_oracle_gp(ctx, 0, g)
+    for N in (1, 9, 1000):
+        Xc = _cands(N, D, lo, up)
+        mean, var = ctx.predict(0, Xc, 1)
+        mo, vo = g.predict(Xc)
+        assert_parity(mean, mo, what="mean M=%d N=%d" % (M, N))
+        prior = g.variance / np.diag(g.output_transform.A)[0] ** 2
+        assert_parity(var, vo, scale=prior, what="var M=%d N=%d" % (M, N))
+
+
+def test_multi_output_gp(ctx):
+    """One GP with two output columns (shared covariance): mean per column, variance tiled (GPflow gpr.py)."""
+    g, lo, up = _model(150, 4, "matern52", R=2)
+    upload_oracle_gp(ctx, 0, g)
+    Xc = _cands(333, 4, lo, up)
+    mean, var = ctx.predict(0, Xc, 2)
+    mo, vo = g.predict(Xc)
+    assert_parity(mean, mo, what="mean")
+    assert_parity(var, vo, scale=g.variance, what="var")
+
+
+@pytest.mark.parametrize("variant", [4, 5, 6, 1, 2, 3])
+@pytest.mark.parametrize("leaf,param", [("ei", None), ("poi", None), ("pof", 0.15), ("lcb", 2.0)])
+def test_leaf_acquisitions(ctx, variant, leaf, param):
+    g, lo, up = _model(300, 5, "matern52", scaled=True)
+    upload_oracle_gp(ctx, 0, g)
+    if param is None:
+        param = float(np.min(g.predict(g.input_transform.backward(g.Xs))[0]))     # fmin over the training inputs
+    op = {"ei": _lib.OP_EI, "poi": _lib.OP_POI, "pof": _lib.OP_POF, "lcb": _lib.OP_LCB}[leaf]
+    ctx.program_set([[op, 0, 0, 0]], [param])
+    ctx.set_variant(variant)
+    try:
+        for N in (1, 31, 33, 2000):
+            Xc = _cands(N, 5, lo, up)
+            vals, _, bv, bi = ctx.eval(Xc)
+            ref = oacq.Leaf(leaf, g, param).value(Xc)
+            assert_parity(vals, ref, what="%s N=%d variant %d" % (leaf, N, variant))
+            assert bv == vals[bi, 0] and bi == int(np.argmax(vals))           # fused argmax == argmax of its own scores
+            assert bi == int(np.argmax(ref)) or near_tie(ref, bi, int(np.argmax(ref)))
+    finally:
+        ctx.set_variant(0)
+
+
+def test_sum_product_scale_programs(ctx):
+    """EI x PoF (constrained BO), nested EI * (PoF + EI), Sum, and the MCMC mean (SUM then SCALE 1/n)."""
+    D, N = 3, 777
+    g1, lo, up = _model(120, D, "matern52")
+    g2, _, _ = _model(90, D, "rbf", seed=77)
+    g3, _, _ = _model(60, D, "matern32", seed=99, noise=1e-3)
+    for i, g in enumerate((g1, g2, g3)):
+        upload_oracle_gp(ctx, i, g, slot0=i)
+    ctx.gp_count_set(3)
+    Xc = _cands(N, D, lo, up)
+    f1, f3 = -0.4, 0.2
+    ei1, pof2, ei3 = oacq.Leaf('ei', g1, f1), oacq.Leaf('pof', g2, 0.0), oacq.Leaf('ei', g3, f3)
+    cases = [
+        ([[_lib.OP_EI, 0, 0, 0], [_lib.OP_POF, 1, 0, 1], [_lib.OP_PROD, 2, 0, 0]], [f1, 0.0],
+         oacq.Agg('prod', [ei1, pof2])),
+        ([[_lib.OP_EI, 0, 0, 0], [_lib.OP_POF, 1, 0, 1], [_lib.OP_EI, 2, 0, 2], [_lib.OP_SUM, 2, 0, 0],
+          [_lib.OP_PROD, 2, 0, 0]], [f1, 0.0, f3], oacq.Agg('prod', [ei1, oacq.Agg('sum', [pof2, ei3])])),
+        ([[_lib.OP_EI, 0, 0, 0], [_lib.OP_POF, 1, 0, 1], [_lib.OP_EI, 2, 0, 2], [_lib.OP_SUM, 3, 0, 0]],
+         [f1, 0.0, f3], oacq.Agg('sum', [ei1, pof2, ei3])),
+        ([[_lib.OP_EI, 0, 0, 0], [_lib.OP_EI, 2, 0, 1], [_lib.OP_SUM, 2, 0, 0], [_lib.OP_SCALE, 0, 0, 2]],
+         [f1, f3, 0.5], oacq.Agg('sum', [ei1, ei3], scale=0.5)),
+    ]
+    try:
+        for ops, params, node in cases:
+            ctx.program_set(ops, params)
+            vals, _, bv, bi = ctx.eval(Xc)
+            ref = node.value(Xc)
+            assert_parity(vals, ref, what=str(ops))
+            assert bi == int(np.argmax(ref)) or near_tie(ref, bi, int(np.argmax(ref)))
+    finally:
+        ctx.gp_count_set(1)
+
+
+def test_argmax_first_occurrence_and_edges(ctx):
+    g, lo, up = _model(64, 2, "rbf")
+    upload_oracle_gp(ctx, 0, g)
+    ctx.program_set([[_lib.OP_EI, 0, 0, 0]], [-0.3])
+    Xc = _cands(5000, 2, lo, up)
+    vals, _, _, bi = ctx.eval(Xc)
+    Xd = Xc.copy()
+    Xd[4000] = Xd[bi]                      # exact duplicates of the winner, before and after it
+    Xd[10] = Xd[bi]
+    _, _, bv2, bi2 = ctx.eval(Xd)
+    assert bi2 == min(10, bi) and bv2 == vals[bi, 0]
+    # N = 0: nothing is touched, index -1
+    v0, _, _, b0 = ctx.eval(np.empty((0, 2)))
+    assert v0.shape == (0, 1) and b0 == -1
+    # determinism / sharding property: one call == two halves, bit for bit
+    a, _, _, _ = ctx.eval(Xc[:2500])
+    b, _, _, _ = ctx.eval(Xc[2500:])
+    assert np.array_equal(np.vstack((a, b)), vals)
+    # row independence: a permutation of the candidates permutes the scores
+    perm = np.random.RandomState(0).permutation(5000)
+    vp, _, _, _ = ctx.eval(Xc[perm])
+    assert np.array_equal(vp, vals[perm])
+
+
+def test_api_errors(ctx):
+    g, lo, up = _model(30, 2, "rbf")
+    upload_oracle_gp(ctx, 0, g)
+    ctx.program_set([[_lib.OP_EI, 0, 0, 0]], [0.0])
+    with pytest.raises(_lib.GpfoError):                    # wrong candidate dimension
+        ctx.eval(np.zeros((4, 3)))
+    with pytest.raises(_lib.GpfoError):                    # program that leaves two values on the stack
+        ctx.program_set([[_lib.OP_EI, 0, 0, 0], [_lib.OP_EI, 0, 0, 0]], [0.0])
+    with pytest.raises(_lib.GpfoError):                    # slot no GP produces
+        ctx.program_set([[_lib.OP_EI, 5, 0, 0]], [0.0])
+        ctx.eval(np.zeros((4, 2)))
+    ctx.program_set([[_lib.OP_EI, 0, 0, 0]], [0.0])
+    with pytest.raises(_lib.GpfoError):                    # unsupported covariance family
+        ctx.gp_set(1, g.Xs, g.Ys, 7, [1.0, 1.0], 1.0, 0.1, slot0=1)
+
+
+@pytest.mark.parametrize("R", [2, 3])
+def test_hvpoi_parity(ctx, R):
+    """HVPoI over the Pareto cell decomposition (hvpoi.py:98-140): R GPs, front of the predicted means."""
+    D, M, N = 4, 80, 1500
+    X = synthetic.candidates(M, D, seed=5)
+    F = synthetic.dtlz2_objectives(X, R)
+    h = synthetic.hypers(D, 1e-3)
+    gps = [oracle_gp(X, F[:, [j]], ogp.MATERN52, h) for j in range(R)]
+    for j, g in enumerate(gps):
+        upload_oracle_gp(ctx, j, g, slot0=j)
+    ctx.gp_count_set(R)
+    try:
+        Fm = np.hstack([g.predict(X)[0] for g in gps])
+        p = opareto.Pareto(np.zeros((1, R)))
+        p.update(Fm)
+        hv = oacq.HVPoI(gps, p.front, p.lb, p.ub)
+        ctx.cells_set(hv.pf_ext(), p.lb, p.ub)
+        ctx.program_set([[_lib.OP_HVPOI, 0, R, 0]], [])
+        Xc = synthetic.candidates(N, D)
+        vals, _, bv, bi = ctx.eval(Xc)
+        ref = hv.value(Xc)
+        assert p.lb.shape[0] > 10 and np.max(ref) > 0
+        assert_parity(vals, ref, what="HVPoI R=%d cells=%d" % (R, p.lb.shape[0]))
+        assert bi == int(np.argmax(ref)) or near_tie(ref, bi, int(np.argmax(ref)))
+        # HVPoI x PoF (constrained multi-objective) through the same program machinery
+        ctx.program_set([[_lib.OP_HVPOI, 0, R, 0], [_lib.OP_POF, 0, 0, 0], [_lib.OP_PROD, 2, 0, 0]], [0.8])
+        vals2, _, _, _ = ctx.eval(Xc)
+        ref2 = ref * oacq.Leaf('pof', gps[0], 0.8).value(Xc)
+        assert_parity(vals2, ref2, what="HVPoI*PoF")
+    finally:
+        ctx.gp_count_set(1)
+
+
+def test_hvpoi_reference_fixture(ctx):
+    """reference testing/unit/test_implementations.py:184-187 + testing/data/vlmop.npz, tolerance decimal=2 as there."""
+    import os
+    from helpers import GOLDEN, fit_mle
+    d = np.load(os.path.join(GOLDEN, "vlmop.npz"))
+    gps = [oracle_gp(d['X'], d['Y'][:, [r]], ogp.MATERN32, fit_mle(d['X'], d['Y'][:, [r]], ogp.MATERN32)) for r in range(2)]
+    for j, g in enumerate(gps):
+        upload_oracle_gp(ctx, j, g, slot0=j)
+    ctx.gp_count_set(2)
+    try:
+        means = np.hstack([ctx.predict(j, d['X'], 1)[0] for j in range(2)])
+        p = opareto.Pareto(np.zeros((1, 2)))
+        p.update(means)
+        hv = oacq.HVPoI(gps, p.front, p.lb, p.ub)
+        ctx.cells_set(hv.pf_ext(), p.lb, p.ub)
+        ctx.program_set([[_lib.OP_HVPOI, 0, 2, 0]], [])
+        vals, _, _, _ = ctx.eval(d['candidates'])
+        np.testing.assert_almost_equal(vals, d['scores'], decimal=2)
+    finally:
+        ctx.gp_count_set(1)
+
+
+def test_headline_shape_subset_and_properties(ctx):
+    """BASELINE configs[1] at full M (2048, D=8, Matern52): oracle parity on a 20 000-row subset, plus
+    size-independent properties on a larger batch (argmax == argmax of the returned scores, halves == whole)."""
+    g, lo, up = _model(2048, 8, "matern52")
+    upload_oracle_gp(ctx, 0, g)
+    fmin = float(np.min(g.predict(g.Xs)[0]))
+    ctx.program_set([[_lib.OP_EI, 0, 0, 0]], [fmin])
+    N = 200000
+    Xc = synthetic.candidates(N, 8)
+    vals, _, bv, bi = ctx.eval(Xc)
+    sub = np.random.RandomState(9).choice(N, 20000, replace=False)
+    sub[0] = bi
+    ref = oacq.Leaf('ei', g, fmin).value(Xc[sub])
+    assert_parity(vals[sub], ref, what="EI M=2048 subset")
+    assert bi == int(np.argmax(vals)) and bv == vals[bi, 0]
+    assert int(np.argmax(ref)) == 0 or near_tie(ref, 0, int(np.argmax(ref)))
+    a, _, _, _ = ctx.eval(Xc[:N // 2 + 7])
+    b, _, _, _ = ctx.eval(Xc[N // 2 + 7:])
+    assert np.array_equal(np.vstack((a, b)), vals)
+    # the stress conditioning of SURVEY 8d (noise 1e-6, cond ~ 4e7) stays inside the same tolerance
+    g2, _, _ = _model(1024, 8, "rbf", noise=1e-6)
+    upload_oracle_gp(ctx, 0, g2)
+    Xs = synthetic.candidates(3000, 8, seed=8)
+    mean, var = ctx.predict(0, Xs, 1)
+    mo, vo = g2.predict(Xs)
+    assert_parity(mean, mo, tol=1e-8, what="mean, cond 4e7")      # documented: conditioning-limited (both sides)
+    assert_parity(var, vo, scale=g2.variance, tol=1e-8, what="var, cond 4e7")

@@ -1,0 +1,141 @@
+"""Host-side mirror of the reference interface (no GPU): domains, transforms, designs, optimisers on plain Python
+objectives, program construction, sharding logic.  Modelled on testing/unit/test_optimizers.py, test_domain.py,
+test_transforms.py and test_acquisition.py of the reference."""
+import warnings
+
+import numpy as np
+import pytest
+
+import gpflowopt_b200 as gpfo
+from gpflowopt_b200 import dist, _lib
+from gpflowopt_b200.design import EmptyDesign, FactorialDesign, RandomDesign
+from gpflowopt_b200.domain import ContinuousParameter, UnitCube
+from gpflowopt_b200.engine import ProgramBuilder
+from gpflowopt_b200.optim import CandidateOptimizer, MCOptimizer, SciPyOptimizer, StagedOptimizer
+from gpflowopt_b200.transforms import LinearTransform
+
+
+def parabola2d(X):
+    return np.atleast_2d(np.sum(X ** 2, axis=1)).T, 2 * X
+
+
+class KeyboardRaiser(object):
+    def __init__(self, iters_to_raise, f):
+        self.iters_to_raise, self.f, self.count = iters_to_raise, f, 0
+
+    def __call__(self, X):
+        if self.count >= self.iters_to_raise:
+            raise KeyboardInterrupt
+        val = self.f(X)
+        self.count += X.shape[0]
+        return val
+
+
+def _domain():
+    return ContinuousParameter("x1", -1.0, 1.0) + ContinuousParameter("x2", -1.0, 1.0)
+
+
+def test_domain_transform_and_contains():
+    d = _domain()
+    t = d >> UnitCube(2)
+    np.testing.assert_allclose(np.diag(t.A), [0.5, 0.5])
+    np.testing.assert_allclose(t.b, [0.5, 0.5])
+    assert np.array([[1.0, -1.0]]) in d and np.array([[1.1, 0.0]]) not in d and np.zeros((1, 3)) not in d
+    assert d == _domain() and d != UnitCube(2)
+    x = np.random.RandomState(0).rand(10, 2) * 2 - 1
+    np.testing.assert_allclose(t.backward(t.forward(x)), x)
+    np.testing.assert_allclose((~t).forward(t.forward(x)), x)
+
+
+def test_linear_transform_backward_variance():       # reference test_transforms.py:82-99
+    t = ~LinearTransform([2.0, 1.0], [1.2, 0.7])
+    B = np.random.RandomState(1).rand(10, 2)
+    np.testing.assert_allclose(t.backward_variance(B), B * np.array([4, 1]))
+    t1, t2 = LinearTransform([2.0, 1.0], [1.2, 0.7]), LinearTransform([1.0, 1.0], [0, 0])
+    t1.assign(t2)
+    np.testing.assert_allclose(t1.A, t2.A)
+    assert not LinearTransform(np.array([[1.0, 0.2], [0.0, 1.0]]), [0, 0]).is_diagonal()
+
+
+def test_designs():
+    d = _domain()
+    X = RandomDesign(200, d).generate()
+    assert X.shape == (200, 2) and X in d
+    F = FactorialDesign(4, d).generate()
+    assert F.shape == (16, 2) and F in d
+    assert EmptyDesign(d).generate().shape == (0, 2)
+
+
+def test_candidate_optimizer_finds_planted_optimum():        # reference test_optimizers.py:94-105
+    d = _domain()
+    opt = CandidateOptimizer(d, FactorialDesign(4, d).generate())
+    assert opt.get_initial().shape == (0, 2) and not opt.gradient_enabled()
+    opt.candidates = np.vstack((opt.candidates, np.zeros((1, 2))))
+    result = opt.optimize(parabola2d)
+    assert result.success and np.allclose(result.x, 0) and np.allclose(result.fun, 0) and result.nfev == 17
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        opt.set_initial([1, 1])
+        assert len(w) == 1 and issubclass(w[-1].category, UserWarning)
+    opt2 = CandidateOptimizer(d, FactorialDesign(4, d).generate())
+    opt2.domain = UnitCube(2)
+    np.testing.assert_allclose(opt2.candidates, FactorialDesign(4, UnitCube(2)).generate())
+
+
+def test_mc_optimizer_first_occurrence_and_interrupt():
+    d = _domain()
+    opt = MCOptimizer(d, 200)
+    r = opt.optimize(parabola2d)
+    assert r.success and r.nfev == 200 and r.x.shape == (1, 2) and 0 < r.fun < 2
+    r = opt.optimize(KeyboardRaiser(0, parabola2d))
+    assert not r.success
+
+
+def test_scipy_and_staged_optimizers():                        # reference test_optimizers.py:108-190
+    d = _domain()
+    opt = SciPyOptimizer(d, maxiter=10)
+    assert opt.config == {'tol': None, 'method': 'L-BFGS-B', 'options': {'maxiter': 10, 'disp': False}}
+    opt.set_initial([-1, -1])
+    r = opt.optimize(parabola2d)
+    assert r.success and r.nit <= 10 and r.nfev <= 20 and np.allclose(r.x, 0) and np.allclose(r.fun, 0)
+    r = opt.optimize(KeyboardRaiser(2, parabola2d))
+    assert not r.success and not np.allclose(r.x, 0)
+    staged = StagedOptimizer([MCOptimizer(d, 5), MCOptimizer(d, 5), SciPyOptimizer(d, maxiter=10)])
+    assert staged.gradient_enabled() is False
+    r = staged.optimize(parabola2d)
+    assert r.success and r.nstages == 3 and np.allclose(r.x, 0, atol=1e-3)
+    r = staged.optimize(KeyboardRaiser(0, parabola2d))
+    assert not r.success and r.nstages == 1 and r.nfev == 0
+
+
+def test_shard_bounds_and_pair_reduce():
+    for n in (0, 1, 7, 8, 9, 1000):
+        for ws in (1, 2, 3, 8):
+            cover = []
+            for r in range(ws):
+                lo, hi = dist.shard_bounds(n, r, ws)
+                assert 0 <= lo <= hi <= n
+                cover.extend(range(lo, hi))
+            assert cover == list(range(n))
+    # max value wins; ties -> lowest global index; empty shards (-1) and NaN never win
+    assert dist.reduce_pairs([1.0, 2.0, 2.0, 0.5], [3, 40, 12, 7]) == (2.0, 12)
+    assert dist.reduce_pairs([0.0, -3.0], [-1, 5]) == (-3.0, 5)
+    assert dist.reduce_pairs([float('nan'), -1.0], [0, 9]) == (-1.0, 9)
+    assert dist.reduce_pairs([0.0], [-1]) == (0.0, -1)
+
+
+class _FakeModel(object):
+    class _Y(object):
+        shape = (5, 1)
+    Y = _Y()
+
+
+def test_program_builder_postfix():
+    m1, m2 = _FakeModel(), _FakeModel()
+    b = ProgramBuilder({id(m1): 0, id(m2): 1})
+    n1 = b.ei(m1, np.array([0.25]))
+    n2 = b.pof(m2, 0.0)
+    b.reduce('prod', [n1, n2])
+    b.scale(None, 0.5)
+    assert b.ops == [(_lib.OP_EI, 0, 0, 0), (_lib.OP_POF, 1, 0, 1), (_lib.OP_PROD, 2, 0, 0), (_lib.OP_SCALE, 0, 0, 2)]
+    assert b.params == [0.25, 0.0, 0.5]

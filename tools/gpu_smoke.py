@@ -37,7 +37,7 @@ def main():
             mo, vo = g.predict(Xc)
             fmin = float(np.min(g.predict(X)[0]))
             ctx.program_set([[_lib.OP_EI, 0, 0, 0]], [fmin])
-            for variant in (1, 2, 3):
+            for variant in (4, 5, 6, 7, 8, 9):
                 ctx.set_variant(variant)
                 vals, _, bv, bi = ctx.eval(Xc)
                 ref = oacq.Leaf('ei', g, fmin).value(Xc)
@@ -47,11 +47,11 @@ def main():
             ctx.set_variant(0)
     # timing at the headline shape
     M, D = 2048, 8
-    for N in (200000,):
+    for N in (296000,):
         Xc = synthetic.candidates(N, D)
-        for variant in (1, 3, 2):
+        for variant in (4, 9, 5, 7, 8, 6, 41, 42, 43):
             ctx.set_variant(variant)
-            for rep in range(3):
+            for rep in range(2):
                 ctx.eval(Xc, want_values=False)
                 t = ctx.timings()
                 print("M=%d N=%d variant %d: eval_ms %.2f hot %.2f h2d %.2f -> %.3e cand/s, %.2f TF/s" % (
