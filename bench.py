@@ -43,7 +43,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super(ClockSampler, self).__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.max_mhz, self._stop = index, [], set(), None, threading.Event()
+        self.index, self.samples, self.reasons, self.max_mhz, self._halt = index, [], set(), None, threading.Event()
 
     def run(self):
         try:
@@ -53,18 +53,18 @@ class ClockSampler(threading.Thread):
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
             names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
                      "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
-            while not self._stop.is_set():
+            while not self._halt.is_set():
                 self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
                 mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
                 for k, bit in names.items():
                     if mask & bit:
                         self.reasons.add(k)
-                self._stop.wait(0.1)
+                self._halt.wait(0.1)
         except Exception as e:                         # pragma: no cover
             self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
 
     def finish(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}

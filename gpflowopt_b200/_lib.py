@@ -16,7 +16,8 @@ MAX_GPS, MAX_SLOTS, MAX_OPS, MAX_PARAMS, MAX_DIM = 16, 16, 64, 64, 64
 # every symbol include/gpfo.h declares
 EXPORTS = ["gpfo_version", "gpfo_ctx_create", "gpfo_ctx_destroy", "gpfo_last_error", "gpfo_status_string",
            "gpfo_gp_set", "gpfo_gp_count_set", "gpfo_gp_get_factor", "gpfo_program_set", "gpfo_cells_set",
-           "gpfo_eval", "gpfo_predict", "gpfo_timings_get", "gpfo_set_variant", "gpfo_measure_dmma_peak"]
+           "gpfo_eval", "gpfo_predict", "gpfo_timings_get", "gpfo_set_variant", "gpfo_measure_dmma_peak",
+           "gpfo_measure_fp64_pipes"]
 
 
 class Timings(ctypes.Structure):
@@ -69,6 +70,8 @@ def load():
     lib.gpfo_timings_get.argtypes = [vp, ctypes.POINTER(Timings)]
     lib.gpfo_set_variant.argtypes = [vp, ctypes.c_int]
     lib.gpfo_measure_dmma_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
+    lib.gpfo_measure_fp64_pipes.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
+                                            ctypes.POINTER(ctypes.c_double)]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is ctypes.c_int and name not in ("gpfo_version",):
@@ -199,6 +202,11 @@ class Context(object):
 
     def set_variant(self, v):
         self._check(self._lib.gpfo_set_variant(self._h, int(v)))
+
+    def measure_fp64_pipes(self, mode):
+        a, b = ctypes.c_double(0.0), ctypes.c_double(0.0)
+        self._check(self._lib.gpfo_measure_fp64_pipes(self._h, int(mode), ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
 
     def measure_dmma_peak(self):
         v = ctypes.c_double(0.0)

@@ -548,4 +548,14 @@ int gpfo_measure_dmma_peak(gpfo_ctx* ctx, double* tflops) {
     return GPFO_OK;
 }
 
+int gpfo_measure_fp64_pipes(gpfo_ctx* ctx, int mode, double* dmma_tflops, double* dfma_tflops) {
+    if (!ctx || !dmma_tflops || !dfma_tflops) return GPFO_ERR_STATE;
+    if (mode < 0 || mode > 2) return fail(ctx, GPFO_ERR_BAD_SHAPE, "mode must be 0, 1 or 2");
+    cudaSetDevice(ctx->device);
+    double out[2] = {0.0, 0.0};
+    if (gpfo_fp64_pipes(ctx->stream, ctx->num_sms, mode, out) != 0) return fail(ctx, GPFO_ERR_CUDA, "pipe benchmark failed");
+    *dmma_tflops = out[0]; *dfma_tflops = out[1];
+    return GPFO_OK;
+}
+
 }  // extern "C"

@@ -337,16 +337,31 @@ cudaError_t gpfo_contract_launch(cudaStream_t st, int variant, int kind, const G
 }
 
 // ------------------------------------------------------------------------------------------------
-// FP64 DMMA issue peak: register-only mma.sync m8n8k4 loop, 8 warps/CTA, 16 independent accumulators/warp
+// FP64 pipe microbenchmarks (register-only loops; 16 warps per SM):
+//   mode 0: every warp issues mma.sync m8n8k4 (DMMA.8x8x4)          -> the roofline denominator
+//   mode 1: every warp issues DFMA                                   -> FP64 vector rate
+//   mode 2: two warps of every scheduler issue DMMA, the other two DFMA, concurrently
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink) {
+__global__ void __launch_bounds__(256) fp64_pipe_kernel(int iters, int mode, double* sink) {
     double c[16][2];
 #pragma unroll
     for (int i = 0; i < 16; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
     const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
-    for (int it = 0; it < iters; ++it) {
+    const int w = threadIdx.x >> 5;
+    const bool use_dmma = mode == 0 || (mode == 2 && ((w >> 2) & 1) == 0);
+    if (use_dmma) {
+        for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) dmma884(c[i][0], c[i][1], a, b);
+            for (int i = 0; i < 16; ++i) dmma884(c[i][0], c[i][1], a, b);
+        }
+    } else {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                c[i][0] = fma(c[i][0], a, b);
+                c[i][1] = fma(c[i][1], b, a);
+            }
+        }
     }
     double s = 0.0;
 #pragma unroll
@@ -354,26 +369,36 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
     if (s == 123.456) sink[0] = s;
 }
 
-double gpfo_dmma_peak(cudaStream_t st, int num_sms) {
+// out[0] = DMMA TFLOP/s, out[1] = DFMA TFLOP/s for the given mode (best of 5)
+int gpfo_fp64_pipes(cudaStream_t st, int num_sms, int mode, double* out) {
     double* sink = nullptr;
-    if (cudaMalloc((void**)&sink, sizeof(double)) != cudaSuccess) return -1.0;
+    if (cudaMalloc((void**)&sink, sizeof(double)) != cudaSuccess) return -1;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int iters = 20000, ctas = num_sms * 2;
-    dmma_peak_kernel<<<ctas, 256, 0, st>>>(200, sink);            // warm-up
-    double best = 0.0;
+    fp64_pipe_kernel<<<ctas, 256, 0, st>>>(200, mode, sink);
+    double best_ms = 1e30;
     for (int rep = 0; rep < 5; ++rep) {
         cudaEventRecord(e0, st);
-        dmma_peak_kernel<<<ctas, 256, 0, st>>>(iters, sink);
+        fp64_pipe_kernel<<<ctas, 256, 0, st>>>(iters, mode, sink);
         cudaEventRecord(e1, st);
-        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best_ms = -1.0; break; }
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
-        const double flops = (double)ctas * 8 /*warps*/ * 16.0 * iters * 512.0;
-        const double tf = flops / (ms * 1e-3) / 1e12;
-        if (tf > best) best = tf;
+        if (ms < best_ms) best_ms = ms;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(sink);
-    return best;
+    if (best_ms <= 0.0) return -1;
+    const double warps = (double)ctas * 8;
+    const double dmma_warps = mode == 0 ? warps : (mode == 2 ? warps / 2 : 0.0);
+    const double dfma_warps = warps - dmma_warps;
+    out[0] = dmma_warps * 16.0 * iters * 512.0 / (best_ms * 1e-3) / 1e12;
+    out[1] = dfma_warps * 32.0 * iters * 64.0 / (best_ms * 1e-3) / 1e12;      // 32 DFMA x 32 lanes x 2 flop
+    return 0;
+}
+
+double gpfo_dmma_peak(cudaStream_t st, int num_sms) {
+    double out[2];
+    return gpfo_fp64_pipes(st, num_sms, 0, out) == 0 ? out[0] : -1.0;
 }

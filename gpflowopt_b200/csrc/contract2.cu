@@ -365,14 +365,14 @@ static cudaError_t launch2(cudaStream_t st, int kind, const GpDev* d_gp, const P
 // v2 variants (all use 64-row-block = 512-row chunks):
 //   4: 16 warps, RBW=4, NB=4 (T=32), 4-stage ring     5: 16 warps, RBW=4, NB=2 (T=16), 4-stage ring
 //   6: 16 warps, RBW=4, NB=1 (T=8)                    41/42/43: ablations of 4 (no gen / no loads / neither)
-//   7: 16 warps, RBW=8, NB=2 (T=16), 1024-row chunks, 3-stage ring      8: same, 2-stage ring      9: as 4, 6-stage ring
+//   7: 16 warps, RBW=8, NB=2 (T=16), 1024-row chunks, 3-stage ring      8: same, 2-stage ring      9: as 4, 5-stage ring
 cudaError_t gpfo_contract2_launch(cudaStream_t st, int variant, int kind, const GpDev* d_gp, const ProgramDev* d_prog,
                                   EvalIO io, int grid, int D) {
     switch (variant) {
         case 5: return launch2<16, 4, 2, 4>(st, kind, d_gp, d_prog, io, grid, D);
         case 7: return launch2<16, 8, 2, 3>(st, kind, d_gp, d_prog, io, grid, D);
         case 8: return launch2<16, 8, 2, 2>(st, kind, d_gp, d_prog, io, grid, D);
-        case 9: return launch2<16, 4, 4, 6>(st, kind, d_gp, d_prog, io, grid, D);
+        case 9: return launch2<16, 4, 4, 5>(st, kind, d_gp, d_prog, io, grid, D);
         case 6: return launch2<16, 4, 1, 4>(st, kind, d_gp, d_prog, io, grid, D);
         case 41: return launch2<16, 4, 4, 4, 1>(st, kind, d_gp, d_prog, io, grid, D);
         case 42: return launch2<16, 4, 4, 4, 2>(st, kind, d_gp, d_prog, io, grid, D);

@@ -234,6 +234,7 @@ cudaError_t gpfo_contract_launch(cudaStream_t st, int variant, int kind, const G
 void gpfo_argmax_final(cudaStream_t st, const double* part_val, const long long* part_idx, int nparts,
                        double* out_val, long long* out_idx);
 double gpfo_dmma_peak(cudaStream_t st, int num_sms);
+int gpfo_fp64_pipes(cudaStream_t st, int num_sms, int mode, double* out);
 
 // hvpoi.cu
 struct CellsDev {

@@ -90,6 +90,9 @@ class Engine(object):
         self._program_key = None
         self._cells_key = None
 
+    def __deepcopy__(self, memo):
+        return None                      # device state is never copied; a copy gets (or adopts) its own engine
+
     def close(self):
         if self.ctx is not None:
             self.ctx.close()

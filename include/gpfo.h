@@ -147,6 +147,10 @@ int gpfo_set_variant(gpfo_ctx* ctx, int variant);
 /* Measures this device's FP64 DMMA issue peak with a register-only mma.sync m8n8k4 loop; TFLOP/s. */
 int gpfo_measure_dmma_peak(gpfo_ctx* ctx, double* tflops);
 
+/* FP64 pipe microbenchmarks (register-only loops, 16 warps/SM): mode 0 = DMMA only, 1 = DFMA only,
+   2 = half of the warps of every scheduler DMMA and half DFMA concurrently.  TFLOP/s of each instruction class. */
+int gpfo_measure_fp64_pipes(gpfo_ctx* ctx, int mode, double* dmma_tflops, double* dfma_tflops);
+
 #ifdef __cplusplus
 }
 #endif
