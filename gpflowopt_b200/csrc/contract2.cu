@@ -31,56 +31,53 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// sqrt(x) for normal positive x without the IEEE slow path: MUFU.RSQ64H seed, one cubically convergent step on
-// 1/sqrt, one correction step on sqrt.  Error < 1 ulp on the range used here (x = r^2 + 1e-12).
+// The FP64 ALU and the DMMA unit share one issue pipe on B200 (profiles/r01_fp64_pipes.log: 37.0 TF/s DMMA alone,
+// 24.4 DFMA alone, 26.6 + 6.7 together), so every FP64 instruction spent on K(X*, X) is taken from the contraction.
+// The helpers below are therefore op-count-minimal and branch-free.
+
+// sqrt(x) for normal positive x: MUFU.RSQ64H seed (2^-22), one cubically convergent step on 1/sqrt (-> 2^-66),
+// then x * y.  About 1 ulp; no IEEE slow path.  6 FP64 ops.
 __device__ __forceinline__ double fast_sqrt_pos(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double e = fma(-x, y * y, 1.0);
     y = fma(y * e, fma(e, 0.375, 0.5), y);
-    double s = x * y;
-    const double d = fma(-s, s, x);
-    return fma(d, 0.5 * y, s);
+    return x * y;
 }
 
-// exp(x) for x <= 0 without special-case paths: clamp at -708 (result ~1e-308 instead of a denormal / 0),
-// n = round(x / ln 2), r = x - n ln 2 in two pieces, degree-13 Taylor polynomial on |r| <= ln2/2 (truncation
-// 4e-18), scaling by 2^n through the exponent field.
-__device__ __forceinline__ double fast_exp_neg(double x) {
+// exp(x) for x <= 0: clamp at -708 (~1e-308 instead of a denormal / 0); k = round(32 x / ln 2), x = k ln2/32 + r
+// with |r| <= ln2/64; exp(x) = 2^(k>>5) * 2^((k&31)/32) * P6(r), P6 = degree-6 Taylor (truncation 3.5e-18 relative);
+// the 32-entry table of 2^(i/32) lives in shared memory.  12 FP64 ops.
+__device__ __forceinline__ double fast_exp_neg(double x, const double* __restrict__ tab32) {
     x = fmax(x, -708.0);
     const double magic = 6755399441055744.0;                 // 1.5 * 2^52
-    const double t = fma(x, 1.4426950408889634, magic);
-    const double n = t - magic;
-    double r = fma(n, -6.93147180559945286e-01, x);
-    r = fma(n, -2.31904681384629956e-17, r);
-    double p = 1.6059043836821613e-10;                       // 1/13!
-    p = fma(p, r, 2.0876756987868100e-09);                   // 1/12!
-    p = fma(p, r, 2.5052108385441720e-08);                   // 1/11!
-    p = fma(p, r, 2.7557319223985893e-07);                   // 1/10!
-    p = fma(p, r, 2.7557319223985888e-06);                   // 1/9!
-    p = fma(p, r, 2.4801587301587302e-05);                   // 1/8!
-    p = fma(p, r, 1.9841269841269841e-04);                   // 1/7!
-    p = fma(p, r, 1.3888888888888889e-03);                   // 1/6!
-    p = fma(p, r, 8.3333333333333332e-03);                   // 1/5!
-    p = fma(p, r, 4.1666666666666664e-02);                   // 1/4!
-    p = fma(p, r, 1.6666666666666666e-01);                   // 1/3!
+    const double t = fma(x, 46.166241308446828, magic);      // 32 / ln 2
+    const double kf = t - magic;
+    double r = fma(kf, -2.1660849392498290e-02, x);          // ln2/32 (head)
+    r = fma(kf, -7.2470213052434896e-19, r);                 // ln2/32 (tail)
+    double p = 1.3888888888888889e-03;                       // 1/6!
+    p = fma(p, r, 8.3333333333333332e-03);
+    p = fma(p, r, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    const int ni = __double2loint(t);                        // low word of t holds n (two's complement)
-    return __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
+    const int k = __double2loint(t);                         // low word of t holds k (two's complement)
+    p *= tab32[k & 31];
+    return __hiloint2double(__double2hiint(p) + ((k >> 5) << 20), __double2loint(p));
 }
 
 template <int KIND>
-__device__ __forceinline__ double kx_branchless(double variance, double r2) {
-    if (KIND == GPFO_KERN_RBF) return variance * fast_exp_neg(-0.5 * r2);      // r2 >= -tiny: fmin keeps x <= 0
-    const double r = fast_sqrt_pos(r2 + 1e-12);
+__device__ __forceinline__ double kx_branchless(double variance, double r2, const double* __restrict__ tab32) {
+    if (KIND == GPFO_KERN_RBF) return variance * fast_exp_neg(-0.5 * fmax(r2, 0.0), tab32);
+    const double x = r2 + 1e-12;                             // euclid_dist: sqrt(r2 + 1e-12); square(r) == x to 1 ulp
+    const double r = fast_sqrt_pos(x);
     if (KIND == GPFO_KERN_MATERN52) {
         const double s5 = 2.2360679774997898;
-        return variance * (1.0 + s5 * r + (5.0 / 3.0) * (r * r)) * fast_exp_neg(-s5 * r);
+        return (variance * fma(5.0 / 3.0, x, fma(s5, r, 1.0))) * fast_exp_neg(-s5 * r, tab32);
     }
     const double s3 = 1.7320508075688772;
-    return variance * (1.0 + s3 * r) * fast_exp_neg(-s3 * r);
+    return (variance * fma(s3, r, 1.0)) * fast_exp_neg(-s3 * r, tab32);
 }
 
 template <int NW, int RBW, int NB, int S, int KIND, int ABL>
@@ -97,6 +94,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     double* x2 = xc + (size_t)D * T;                                 // [T]
     double* tot = x2 + T;                                            // [T][1+RMAX] running colsum(A^2), A^T V
     double* sbest = tot + T * (1 + RMAX);                            // [2] best value, best index (as bits)
+    double* tab32 = sbest + 2;                                       // [32] 2^(i/32)
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
     const GpDev& gp = *gpp;
@@ -115,6 +113,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     const bool gen_first = ((w >> 2) & 1) == 0;          // warps w, w+4, w+8, w+12 share a scheduler: 2 + 2
 
     if (tid == 0) { sbest[0] = 0.0; reinterpret_cast<long long*>(sbest)[1] = -1; }
+    if (tid < 32) tab32[tid] = exp2(tid * (1.0 / 32.0));
 
     const int64_t ntiles = (io.N + T - 1) / T;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -196,7 +195,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                     if (ABL & 1) val = 1e-3 * j;
                     else {
                         const double r2 = (-2.0 * dot[q] + __ldg(xn + jj[q])) + x2[gen_n];    // square_dist, expanded form
-                        val = kx_branchless<KIND>(variance, KIND == GPFO_KERN_RBF ? fmax(r2, 0.0) : r2);
+                        val = kx_branchless<KIND>(variance, r2, tab32);
                     }
                     dst[(ksl * NB + gen_nb) * 32 + lane] = j < M ? val : 0.0;
                 }
@@ -344,7 +343,7 @@ template <int NW, int RBW, int NB, int S, int KIND, int ABL>
 static cudaError_t launch2_kind(cudaStream_t st, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io, int grid, int D) {
     using C = Contract2Cfg<NW, RBW, NB, S>;
     const size_t smem = ((size_t)NW * C::RING_DOUBLES_PER_WARP + 2 * C::GROUP_SLOTS + (size_t)NW * C::T * (1 + RMAX) +
-                         (size_t)D * C::T + C::T + C::T * (1 + RMAX) + 2) * sizeof(double);
+                         (size_t)D * C::T + C::T + C::T * (1 + RMAX) + 2 + 32) * sizeof(double);
     auto kern = contract2_kernel<NW, RBW, NB, S, KIND, ABL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -10,7 +10,7 @@ def training_set(M, D, seed=1234, constraint=False):
     rs = np.random.RandomState(seed)
     X = rs.rand(M, D)
     y = np.sin(3.0 * X.sum(axis=1)) + 0.1 * rs.randn(M)
-    y = (y - y.mean()) / y.std()
+    y = (y - y.mean()) / (y.std() if y.std() > 0 else 1.0) + (1.0 if M == 1 else 0.0)
     Y = y.reshape(-1, 1)
     if constraint:
         yc = X[:, 0] - 0.5 + 0.05 * rs.randn(M)
