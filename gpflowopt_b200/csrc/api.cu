@@ -12,8 +12,10 @@ struct GpHost {
     int M = 0, Mp = 0, Mf = 0, D = 0, R = 0, kind = 0, slot0 = 0;
     double *dX = nullptr, *dell = nullptr, *dXs = nullptr, *dxn = nullptr, *dY = nullptr, *dV = nullptr;
     double *dL = nullptr, *dLinv = nullptr, *dpacked = nullptr;
+    double *dalpha = nullptr, *dpacked_kinv = nullptr;      // gradient pass state, built lazily
+    bool kinv_ready = false;
     int packed_rbc = 0;
-    size_t cap_mf = 0, cap_d = 0, cap_r = 0, cap_packed = 0;
+    size_t cap_mf = 0, cap_d = 0, cap_r = 0, cap_packed = 0, cap_alpha = 0, cap_kinv = 0;
     GpDev hdev;
     GpDev* ddev = nullptr;
 };
@@ -37,6 +39,8 @@ struct gpfo_ctx {
     double* dXc = nullptr; size_t cap_xc = 0;
     double* dvalues = nullptr; size_t cap_values = 0;
     double *dmom_mean = nullptr, *dmom_var = nullptr; size_t cap_mom = 0;
+    double *dcmu = nullptr, *dcva = nullptr; size_t cap_coef = 0;
+    double* dgrads = nullptr; size_t cap_grads = 0;
     double* dpart_val = nullptr; long long* dpart_idx = nullptr; int cap_parts = 0;
     double* dbest_val = nullptr; long long* dbest_idx = nullptr;
     int* dflag = nullptr;
@@ -123,6 +127,7 @@ int gpfo_ctx_create(int device, gpfo_ctx** out) {
 static void free_gp(GpHost& g) {
     cudaFree(g.dX); cudaFree(g.dell); cudaFree(g.dXs); cudaFree(g.dxn); cudaFree(g.dY); cudaFree(g.dV);
     cudaFree(g.dL); cudaFree(g.dLinv); cudaFree(g.dpacked); cudaFree(g.ddev);
+    cudaFree(g.dalpha); cudaFree(g.dpacked_kinv);
     g = GpHost();
 }
 
@@ -133,6 +138,7 @@ int gpfo_ctx_destroy(gpfo_ctx* ctx) {
     for (int i = 0; i < GPFO_MAX_GPS; ++i) free_gp(ctx->gps[i]);
     cudaFree(ctx->dprog); cudaFree(ctx->dpf); cudaFree(ctx->dlb); cudaFree(ctx->dub);
     cudaFree(ctx->dXc); cudaFree(ctx->dvalues); cudaFree(ctx->dmom_mean); cudaFree(ctx->dmom_var);
+    cudaFree(ctx->dcmu); cudaFree(ctx->dcva); cudaFree(ctx->dgrads);
     cudaFree(ctx->dpart_val); cudaFree(ctx->dpart_idx); cudaFree(ctx->dbest_val); cudaFree(ctx->dbest_idx);
     cudaFree(ctx->dflag);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
@@ -153,6 +159,7 @@ static int repack(gpfo_ctx* ctx, GpHost& g, int rbc) {
     geom.nrb = g.Mp / 8;
     geom.rbc = rbc;
     geom.nchunks = (geom.nrb + rbc - 1) / rbc;
+    geom.dense = 0;
     const size_t need = (size_t)pg_total_blocks(geom) * 64;
     CK(ensure(&g.dpacked, &g.cap_packed, need));
     gpfo_pack_linv(ctx->stream, g.dLinv, g.Mf, geom, g.dpacked);
@@ -162,6 +169,33 @@ static int repack(gpfo_ctx* ctx, GpHost& g, int rbc) {
     g.hdev.packed = g.dpacked;
     CK(cudaMemcpyAsync(g.ddev, &g.hdev, sizeof(GpDev), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return GPFO_OK;
+}
+
+// Gradient-pass state of one GP: alpha = L^-T V and the dense block stream of K^-1 = L^-T L^-1 (built on first use).
+static int ensure_kinv(gpfo_ctx* ctx, GpHost& g) {
+    if (g.kinv_ready) return GPFO_OK;
+    cudaStream_t st = ctx->stream;
+    PackGeom geom;
+    geom.nrb = g.Mp / 8;
+    geom.rbc = gpfo_contract_grad_rbc();
+    geom.nchunks = (geom.nrb + geom.rbc - 1) / geom.rbc;
+    geom.dense = 1;
+    CK(ensure(&g.dalpha, &g.cap_alpha, (size_t)g.Mf * g.R));
+    CK(ensure(&g.dpacked_kinv, &g.cap_kinv, (size_t)pg_total_blocks(geom) * 64));
+    double* dKinv = nullptr;
+    CK(cudaMalloc((void**)&dKinv, (size_t)g.Mf * g.Mf * sizeof(double)));
+    gpfo_kinv_alpha(st, g.dLinv, g.Mf, g.dV, g.R, dKinv, g.dalpha);
+    gpfo_pack_linv(st, dKinv, g.Mf, geom, g.dpacked_kinv);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(dKinv);
+    if (e != cudaSuccess) return fail(ctx, GPFO_ERR_CUDA, std::string("ensure_kinv: ") + cudaGetErrorString(e));
+    g.hdev.alpha = g.dalpha;
+    g.hdev.packed_kinv = g.dpacked_kinv;
+    g.hdev.geom_kinv = geom;
+    CK(cudaMemcpy(g.ddev, &g.hdev, sizeof(GpDev), cudaMemcpyHostToDevice));
+    g.kinv_ready = true;
     return GPFO_OK;
 }
 
@@ -198,6 +232,7 @@ int gpfo_gp_set(gpfo_ctx* ctx, int gp_id, int64_t M64, int D, int R, const doubl
         g.cap_mf = Mf; g.cap_d = D; g.cap_r = R;
     }
     g.valid = false;
+    g.kinv_ready = false;
     g.M = M; g.Mp = Mp; g.Mf = Mf; g.D = D; g.R = R; g.kind = kernel_kind; g.slot0 = slot0;
     memset(&g.hdev, 0, sizeof(GpDev));
     double ell[GPFO_MAX_DIM];
@@ -378,7 +413,10 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     for (int s = 0; s < ctx->hprog.nslots; ++s)
         if (!have[s]) return fail(ctx, GPFO_ERR_STATE, "program references a moment slot no GP produces");
     if (ctx->hprog.has_hvpoi && !ctx->cells_set) return fail(ctx, GPFO_ERR_STATE, "HVPoI program without gpfo_cells_set");
-    if (out_grads) return fail(ctx, GPFO_ERR_UNSUPPORTED, "gradient kernel not available in this build");
+    const bool want_grad = out_grads != nullptr;
+    if (want_grad && ctx->hprog.has_hvpoi &&
+        gpfo_hvpoi_smem_bytes_grad(ctx->cells.n_ext, ctx->cells.R) > 227 * 1024)
+        return fail(ctx, GPFO_ERR_UNSUPPORTED, "Pareto front too large for the gradient HVPoI kernel");
     if (N == 0) {
         if (best_index) *best_index = -1;
         if (best_value) *best_value = 0.0;
@@ -399,7 +437,9 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
         if (ctx->gps[g].packed_rbc != rbc) { rc = repack(ctx, ctx->gps[g], rbc); if (rc != GPFO_OK) return rc; }
 
     const bool hv = ctx->hprog.has_hvpoi != 0;
-    const bool need_mom = hv || ctx->ngps > 1;
+    const bool need_mom = hv || ctx->ngps > 1 || want_grad;
+    if (want_grad)
+        for (int g = 0; g < ctx->ngps; ++g) { rc = ensure_kinv(ctx, ctx->gps[g]); if (rc != GPFO_OK) return rc; }
     EvalIO io;
     memset(&io, 0, sizeof(io));
     io.X = dX; io.N = N;
@@ -419,9 +459,26 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
         if (dev_out) io.values = out_values;
         else { CK(ensure(&ctx->dvalues, &ctx->cap_values, (size_t)N)); io.values = ctx->dvalues; }
     }
+    const bool dev_grads = want_grad && is_device_ptr(out_grads);
+    if (want_grad) {
+        const size_t need = (size_t)GPFO_MAX_SLOTS * N;
+        if (ctx->cap_coef < need) {
+            cudaFree(ctx->dcmu); cudaFree(ctx->dcva);
+            ctx->dcmu = ctx->dcva = nullptr; ctx->cap_coef = 0;
+            CK(cudaMalloc((void**)&ctx->dcmu, need * sizeof(double)));
+            CK(cudaMalloc((void**)&ctx->dcva, need * sizeof(double)));
+            ctx->cap_coef = need;
+        }
+        io.cmu = ctx->dcmu; io.cva = ctx->dcva;
+        if (dev_grads) io.grads = out_grads;
+        else { CK(ensure(&ctx->dgrads, &ctx->cap_grads, (size_t)N * D)); io.grads = ctx->dgrads; }
+    }
     const int grid = gpfo_contract_grid(variant, N, ctx->num_sms);
     const int hv_grid = gpfo_hvpoi_grid(N, ctx->num_sms);
-    rc = ensure_parts(ctx, grid > hv_grid ? grid : hv_grid);
+    const int pg_grid = gpfo_program_grad_grid(N, ctx->num_sms);
+    int max_parts = grid > hv_grid ? grid : hv_grid;
+    if (pg_grid > max_parts) max_parts = pg_grid;
+    rc = ensure_parts(ctx, max_parts);
     if (rc != GPFO_OK) return rc;
     io.part_val = ctx->dpart_val; io.part_idx = ctx->dpart_idx;
 
@@ -431,7 +488,7 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     for (int g = 0; g < ctx->ngps; ++g) {
         EvalIO gio = io;
         gio.write_moments = need_mom ? 1 : 0;
-        gio.run_program = (!hv && g == ctx->ngps - 1) ? 1 : 0;
+        gio.run_program = (!hv && !want_grad && g == ctx->ngps - 1) ? 1 : 0;
         CK(cudaEventRecord(ctx->ev[6], st));
         CK(gpfo_contract_launch(st, variant, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
         CK(cudaEventRecord(ctx->ev[7], st));
@@ -452,9 +509,23 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
                 if (ctx->hprog.ops[4 * i + 2] != ctx->cells.R)
                     return fail(ctx, GPFO_ERR_BAD_SHAPE, "HVPoI objective count does not match the cell tables");
             }
-        CK(gpfo_hvpoi_launch(st, ctx->dprog, ctx->cells, hio, hv_grid, slot_first));
+        CK(gpfo_hvpoi_launch(st, ctx->dprog, ctx->cells, hio, hv_grid, slot_first, want_grad ? 1 : 0));
         ++launches;
         nparts = hv_grid;
+    } else if (want_grad) {
+        CK(gpfo_program_grad_launch(st, ctx->dprog, io, pg_grid));
+        ++launches;
+        nparts = pg_grid;
+    }
+    if (want_grad) {
+        // chain rule through each GP: W = K^-1 Kx on DMMA, then the (1+D)-wide reduction over the training points
+        const int ggrid = gpfo_contract_grad_grid(N, ctx->num_sms);
+        for (int g = 0; g < ctx->ngps; ++g) {
+            EvalIO gio = io;
+            gio.grad_accumulate = g > 0 ? 1 : 0;
+            CK(gpfo_contract_grad_launch(st, ctx->gps[g].kind, ctx->gps[g].ddev, gio, ggrid, D));
+            ++launches;
+        }
     }
     gpfo_argmax_final(st, ctx->dpart_val, ctx->dpart_idx, nparts, ctx->dbest_val, ctx->dbest_idx);
     CK(cudaGetLastError());
@@ -465,6 +536,8 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     long long hidx = -1;
     if (out_values && !dev_out)
         CK(cudaMemcpyAsync(out_values, ctx->dvalues, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (want_grad && !dev_grads)
+        CK(cudaMemcpyAsync(out_grads, ctx->dgrads, (size_t)N * D * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&hbest, ctx->dbest_val, sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&hidx, ctx->dbest_idx, sizeof(long long), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev[1], st));

@@ -80,6 +80,23 @@ __device__ __forceinline__ double kx_branchless(double variance, double r2, cons
     return (variance * fma(s3, r, 1.0)) * fast_exp_neg(-s3 * r, tab32);
 }
 
+// d k / d r^2 for the gradient pass: RBF -k/2; Matern52 -(5/6) s2 (1 + sqrt5 r) e^{-sqrt5 r};
+// Matern32 -(3/2) s2 e^{-sqrt3 r}, with r = sqrt(r^2 + 1e-12) as in euclid_dist.
+template <int KIND>
+__device__ __forceinline__ double dk_dr2_branchless(double variance, double r2, const double* __restrict__ tab32) {
+    if (KIND == GPFO_KERN_RBF) return (-0.5 * variance) * fast_exp_neg(-0.5 * fmax(r2, 0.0), tab32);
+    const double r = fast_sqrt_pos(r2 + 1e-12);
+    if (KIND == GPFO_KERN_MATERN52) {
+        const double s5 = 2.2360679774997898;
+        return ((-5.0 / 6.0) * variance * fma(s5, r, 1.0)) * fast_exp_neg(-s5 * r, tab32);
+    }
+    const double s3 = 1.7320508075688772;
+    return (-1.5 * variance) * fast_exp_neg(-s3 * r, tab32);
+}
+
+// ABL bit 0/1: profiling ablations.  ABL bit 2 (value 4) = GRADIENT PASS: the stream is the dense block stream of
+// K^-1, the accumulators hold W = K^-1 Kx, and the chunk epilogue forms u = (c_mu . alpha_i + c_var w_in) dk_in/dr^2
+// and reduces u [1, Xs_i] over the training points; the tile epilogue writes d acq / d Xcand.
 template <int NW, int RBW, int NB, int S, int KIND, int ABL>
 __global__ void __launch_bounds__(32 * NW, 1)
 contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ prog, EvalIO io) {
@@ -95,6 +112,11 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     double* tot = x2 + T;                                            // [T][1+RMAX] running colsum(A^2), A^T V
     double* sbest = tot + T * (1 + RMAX);                            // [2] best value, best index (as bits)
     double* tab32 = sbest + 2;                                       // [32] 2^(i/32)
+    constexpr bool GRADM = (ABL & 4) != 0;
+    double* gcm = tab32 + 32;                                        // [T][RMAX]  (d acq/d mean_ro) / out_scale_ro
+    double* gcv = gcm + T * RMAX;                                    // [T]        -2 sum_ro (d acq/d var_ro) / out_scale_ro^2
+    double* gsum = gcv + T;                                          // [T][1+D]   sum_i u_in [1, Xs_i]
+    static_assert(!GRADM || S >= NB, "the u buffer of the gradient pass reuses the ring");
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
     const GpDev& gp = *gpp;
@@ -103,7 +125,8 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     const double* __restrict__ Xs = gp.Xs;
     const double* __restrict__ xn = gp.xn;
     const double* __restrict__ Vv = gp.V;
-    const PackGeom geom = gp.geom;
+    const PackGeom geom = GRADM ? gp.geom_kinv : gp.geom;
+    const double* __restrict__ packed = GRADM ? gp.packed_kinv : gp.packed;
     double* myring = ring + (size_t)w * C::RING_DOUBLES_PER_WARP + 2 * lane;
     const unsigned myring_s = (unsigned)__cvta_generic_to_shared(myring);     // same location, shared-window address
 
@@ -120,6 +143,24 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
         const int64_t n0 = tile * T;
         __syncthreads();
         if (tid < T * (1 + RMAX)) tot[tid] = 0.0;
+        if (GRADM) {
+            for (int e = tid; e < T * (1 + D); e += C::THREADS) gsum[e] = 0.0;
+            if (tid < T) {
+                const int64_t n = n0 + tid;
+                double cv = 0.0;
+#pragma unroll
+                for (int ro = 0; ro < RMAX; ++ro) {
+                    double cm = 0.0;
+                    if (ro < R && n < io.N) {
+                        const size_t o = (size_t)(gp.slot0 + ro) * io.N + n;
+                        cm = io.cmu[o] / gp.out_scale[ro];
+                        cv += -2.0 * io.cva[o] / (gp.out_scale[ro] * gp.out_scale[ro]);
+                    }
+                    gcm[tid * RMAX + ro] = cm;
+                }
+                gcv[tid] = cv;
+            }
+        }
         for (int e = tid; e < T * D; e += C::THREADS) {
             const int n = e / D, d = e - n * D;
             double x = 0.0;
@@ -137,9 +178,10 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
 
         for (int p = 0; p < geom.nchunks; ++p) {
             const int nr = pg_chunk_rows(geom, p);
-            const int kd0 = p * geom.rbc;                 // first diagonal column block of this chunk
-            const int kp_end = kd0 + nr;
-            const double* __restrict__ cbase = gp.packed + pg_chunk_base(geom, p) * 64 + 2 * lane;
+            const int row0 = p * geom.rbc;                // first row block of this chunk
+            const int kp_end = GRADM ? geom.nrb : row0 + nr;
+            const int kd0 = GRADM ? kp_end : row0;        // first diagonal column block (none in the dense stream)
+            const double* __restrict__ cbase = packed + pg_chunk_base(geom, p) * 64 + 2 * lane;
 
             double acc[RBW][NB][2];
 #pragma unroll
@@ -261,6 +303,44 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             }
             cp_async_wait<0>();
 
+            if (GRADM) {
+                // ---- gradient pass: u_in = (sum_ro c_mu[n][ro] alpha[i][ro] + c_var[n] w_in) * dk_in/dr^2 into the (drained) ring
+                __syncthreads();                          // every warp is done reading its ring
+                double* ubuf = ring;                      // [8 * RBC][T]
+#pragma unroll
+                for (int r = 0; r < RBW; ++r) {
+                    const int rbl = r * NW + w;
+                    const int il = 8 * rbl + (lane >> 2);
+                    const int gi = 8 * (row0 + rbl) + (lane >> 2);
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const int n = 8 * nb + 2 * (lane & 3) + c;
+                            double u = 0.0;
+                            if (rbl < nr) {
+                                double dot = 0.0;
+                                for (int d = 0; d < D; ++d) dot = fma(__ldg(Xs + (size_t)gi * D + d), xc[d * T + n], dot);
+                                const double r2 = (-2.0 * dot + __ldg(xn + gi)) + x2[n];
+                                double coef = gcv[n] * acc[r][nb][c];
+                                for (int ro = 0; ro < R; ++ro) coef = fma(gcm[n * RMAX + ro], __ldg(gp.alpha + (size_t)gi * R + ro), coef);
+                                u = coef * dk_dr2_branchless<KIND>(variance, r2, tab32);
+                            }
+                            ubuf[il * T + n] = u;
+                        }
+                }
+                __syncthreads();
+                for (int e = tid; e < T * (1 + D); e += C::THREADS) {     // thread (n, dd): fixed row order
+                    const int n = e / (1 + D), dd = e - n * (1 + D);
+                    double a = gsum[e];
+                    if (dd == 0) for (int il = 0; il < 8 * nr; ++il) a += ubuf[il * T + n];
+                    else for (int il = 0; il < 8 * nr; ++il)
+                        a = fma(ubuf[il * T + n], __ldg(Xs + (size_t)(8 * row0 + il) * D + dd - 1), a);
+                    gsum[e] = a;
+                }
+                __syncthreads();
+                continue;
+            }
             // ---- chunk reduction (fixed order -> deterministic)
             {
                 double ss[NB][2];
@@ -291,7 +371,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                     for (int r = 0; r < RBW; ++r) {
                         const int rbl = r * NW + w;
                         double v = 0.0;
-                        if (rbl < nr) v = __ldg(Vv + (size_t)(8 * (kd0 + rbl) + (lane >> 2)) * R + ro);
+                        if (rbl < nr) v = __ldg(Vv + (size_t)(8 * (row0 + rbl) + (lane >> 2)) * R + ro);
 #pragma unroll
                         for (int nb = 0; nb < NB; ++nb) {
                             mv[nb][0] += acc[r][nb][0] * v;
@@ -321,6 +401,19 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             }
             __syncthreads();
         }
+        if (GRADM) {
+            // d acq / d x_d = 2 a_d / l_d * (xs_d * sum_i u_i - sum_i u_i Xs_id)       (d r^2 / d x_d = 2 (xs_d - Xs_id) a_d / l_d)
+            for (int e = tid; e < T * D; e += C::THREADS) {
+                const int n = e / D, d = e - n * D;
+                if (n0 + n < io.N) {
+                    const double g = 2.0 * gp.in_scale[d] / gp.ell[d] *
+                                     (xc[d * T + n] * gsum[n * (1 + D)] - gsum[n * (1 + D) + 1 + d]);
+                    double* dst = io.grads + (size_t)(n0 + n) * D + d;
+                    *dst = io.grad_accumulate ? *dst + g : g;
+                }
+            }
+            continue;
+        }
         if (w == 0) {
             double tot_mv[RMAX];
             const int ln = lane < T ? lane : 0;
@@ -343,7 +436,8 @@ template <int NW, int RBW, int NB, int S, int KIND, int ABL>
 static cudaError_t launch2_kind(cudaStream_t st, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io, int grid, int D) {
     using C = Contract2Cfg<NW, RBW, NB, S>;
     const size_t smem = ((size_t)NW * C::RING_DOUBLES_PER_WARP + 2 * C::GROUP_SLOTS + (size_t)NW * C::T * (1 + RMAX) +
-                         (size_t)D * C::T + C::T + C::T * (1 + RMAX) + 2 + 32) * sizeof(double);
+                         (size_t)D * C::T + C::T + C::T * (1 + RMAX) + 2 + 32 +
+                         ((ABL & 4) ? C::T * RMAX + C::T + C::T * (1 + (size_t)D) : 0)) * sizeof(double);
     auto kern = contract2_kernel<NW, RBW, NB, S, KIND, ABL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -378,4 +472,14 @@ cudaError_t gpfo_contract2_launch(cudaStream_t st, int variant, int kind, const 
         case 43: return launch2<16, 4, 4, 4, 3>(st, kind, d_gp, d_prog, io, grid, D);
         default: return launch2<16, 4, 4, 4>(st, kind, d_gp, d_prog, io, grid, D);
     }
+}
+
+// gradient pass launcher (dense K^-1 stream; T = 32 candidates per tile, 512-row chunks)
+cudaError_t gpfo_contract_grad_launch(cudaStream_t st, int kind, const GpDev* d_gp, EvalIO io, int grid, int D) {
+    return launch2<16, 4, 4, 4, 4>(st, kind, d_gp, nullptr, io, grid, D);
+}
+int gpfo_contract_grad_rbc() { return 64; }
+int gpfo_contract_grad_grid(int64_t N, int num_sms) {
+    const int64_t ntiles = (N + 31) / 32;
+    return (int)(ntiles < num_sms ? (ntiles > 0 ? ntiles : 1) : num_sms);
 }

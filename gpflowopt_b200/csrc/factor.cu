@@ -250,7 +250,7 @@ __global__ void linv_times_y_kernel(const double* __restrict__ Linv, int ld, con
 __global__ void pack_linv_kernel(const double* __restrict__ Linv, int ld, PackGeom g, int p, int nr,
                                  int64_t chunk_base, double* __restrict__ packed) {
     // grid.x enumerates (kp, rb_local) pairs of chunk p densely over [0, kp_end) x [0, nr); inactive pairs exit
-    const int kp_end = p * g.rbc + nr;
+    const int kp_end = g.dense ? g.nrb : p * g.rbc + nr;
     const int64_t pair = blockIdx.x;
     const int kp = (int)(pair / nr), rbl = (int)(pair % nr);
     if (kp >= kp_end) return;
@@ -267,7 +267,7 @@ __global__ void pack_linv_kernel(const double* __restrict__ Linv, int ld, PackGe
 void gpfo_pack_linv(cudaStream_t st, const double* dLinv, int ld, PackGeom g, double* dpacked) {
     for (int p = 0; p < g.nchunks; ++p) {
         const int nr = pg_chunk_rows(g, p);
-        const int kp_end = p * g.rbc + nr;
+        const int kp_end = g.dense ? g.nrb : p * g.rbc + nr;
         const int64_t pairs = (int64_t)kp_end * nr;
         pack_linv_kernel<<<(unsigned)pairs, 64, 0, st>>>(dLinv, ld, g, p, nr, pg_chunk_base(g, p), dpacked);
     }
@@ -328,4 +328,62 @@ int gpfo_factor_device(cudaStream_t st, int M, int Mf, int D, int R, int kind, d
     ce = cudaGetLastError();
     if (ce != cudaSuccess) { *err = std::string("factor: ") + cudaGetErrorString(ce); return GPFO_ERR_CUDA; }
     return GPFO_OK;
+}
+
+// Kinv[i][j] = sum_t Linv[t][i] * Linv[t][j]  (t >= max(i, j)); 64x64 tile per CTA, 256 threads, 4x4 outputs each.
+__global__ void __launch_bounds__(256) ata_kernel(const double* __restrict__ A, int ld, double* __restrict__ C) {
+    __shared__ double As[32][FB + 1];
+    __shared__ double Bs[32][FB + 1];
+    const int ti = blockIdx.y, tj = blockIdx.x;
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    const int t0 = (ti > tj ? ti : tj) * FB;              // rows above the larger tile index are zero in both
+    for (int t = t0; t < ld; t += 32) {
+        for (int e = tid; e < 32 * FB; e += 256) {
+            const int r = e / FB, c = e % FB;
+            As[r][c] = A[(size_t)(t + r) * ld + ti * FB + c];
+            Bs[r][c] = A[(size_t)(t + r) * ld + tj * FB + c];
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) av[a] = As[k][ty + 16 * a];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bv[b] = Bs[k][tx + 16 * b];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] += av[a] * bv[b];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) C[(size_t)(ti * FB + ty + 16 * a) * ld + tj * FB + tx + 16 * b] = acc[a][b];
+}
+
+// alpha[i][r] = sum_{t >= i} Linv[t][i] V[t][r]   (one warp per column i)
+__global__ void linvT_times_v_kernel(const double* __restrict__ Linv, int ld, const double* __restrict__ V, int R,
+                                     double* __restrict__ alpha) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+    if (i >= ld) return;
+    for (int r = 0; r < R; ++r) {
+        double s = 0.0;
+        for (int t = i + lane; t < ld; t += 32) s += Linv[(size_t)t * ld + i] * V[(size_t)t * R + r];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) alpha[(size_t)i * R + r] = s;
+    }
+}
+
+void gpfo_kinv_alpha(cudaStream_t st, const double* dLinv, int Mf, const double* dV, int R, double* dKinv, double* dalpha) {
+    const int nb = Mf / FB;
+    ata_kernel<<<dim3(nb, nb), 256, 0, st>>>(dLinv, Mf, dKinv);
+    linvT_times_v_kernel<<<(Mf + 3) / 4, 128, 0, st>>>(dLinv, Mf, dV, R, dalpha);
 }

@@ -22,6 +22,7 @@ struct PackGeom {
     int nrb;        // number of 8-row blocks = Mp / 8
     int rbc;        // row blocks per chunk
     int nchunks;    // ceil(nrb / rbc)
+    int dense;      // 0: lower block-triangular (L^-1); 1: every block stored (K^-1, gradient pass)
 };
 
 GPFO_HD int pg_chunk_rows(const PackGeom& g, int p) {            // row blocks in chunk p
@@ -33,18 +34,20 @@ GPFO_HD int64_t pg_chunk_base(const PackGeom& g, int p) {
     // full chunks q < p each hold q*rbc*rbc (off-diagonal) + rbc*(rbc+1)/2 (diagonal) blocks
     int64_t rbc = g.rbc;
     int64_t pp = p;
+    if (g.dense) return pp * rbc * g.nrb;
     return rbc * rbc * (pp * (pp - 1) / 2) + pp * (rbc * (rbc + 1) / 2);
 }
 // offset (in blocks, relative to the chunk base) of the first stored block of column block kp in chunk p,
 // and the first stored row block (local index) `lo`.  nr = pg_chunk_rows(g, p).
 GPFO_HD int64_t pg_col_base(const PackGeom& g, int p, int nr, int kp, int* lo) {
     int kd = kp - p * g.rbc;                                     // < 0: off-diagonal (dense) column block
-    if (kd < 0) { *lo = 0; return (int64_t)kp * nr; }
+    if (kd < 0 || g.dense) { *lo = 0; return (int64_t)kp * nr; }
     *lo = kd;
     // sum_{q<kd} (nr - q) = kd*nr - kd*(kd-1)/2
     return (int64_t)p * g.rbc * nr + (int64_t)kd * nr - (int64_t)kd * (kd - 1) / 2;
 }
 GPFO_HD int64_t pg_total_blocks(const PackGeom& g) {
+    if (g.dense) return (int64_t)g.nrb * g.nrb;
     int p = g.nchunks - 1;
     int nr = pg_chunk_rows(g, p);
     return pg_chunk_base(g, p) + (int64_t)p * g.rbc * nr + (int64_t)nr * (nr + 1) / 2;
@@ -63,6 +66,9 @@ struct GpDev {
     const double* V;            // Mp x R, L^-1 Y (rows >= M are zero)
     const double* packed;       // block stream of L^-1
     PackGeom geom;
+    const double* alpha;        // Mp x R, K^-1 Y = L^-T V            (gradient pass only)
+    const double* packed_kinv;  // dense block stream of K^-1         (gradient pass only)
+    PackGeom geom_kinv;
     double in_scale[GPFO_MAX_DIM], in_shift[GPFO_MAX_DIM], inv_ell[GPFO_MAX_DIM];   // per input dimension
     double ell[GPFO_MAX_DIM];
     double out_scale[GPFO_MAX_SLOTS], out_shift[GPFO_MAX_SLOTS];                   // per output column
@@ -86,6 +92,11 @@ struct EvalIO {
     long long* part_idx;
     int write_moments;          // this launch stores its moments to scratch
     int run_program;            // this launch evaluates the program in its epilogue
+    // gradient pass
+    double* cmu;                // [slot][N] d acq / d mean_slot   (written by the program-gradient kernel)
+    double* cva;                // [slot][N] d acq / d var_slot
+    double* grads;              // N x D  d acq / d Xcand
+    int grad_accumulate;        // 0: this GP's launch overwrites grads, 1: adds to it
 };
 
 #define GPFO_STABILITY 1e-6     // gpflow settings.numerics.jitter_level (ei.py:24, poi.py:23, pof.py:23, hvpoi.py:24)
@@ -222,6 +233,8 @@ int gpfo_factor_device(cudaStream_t st, int M, int Mf, int D, int R, int kind, d
                        double* dLinv /*Mf x Mf*/, const double* dY /*Mf x R*/, double* dV /*Mf x R*/,
                        int* dflag, std::string* err);
 void gpfo_pack_linv(cudaStream_t st, const double* dLinv, int ld, PackGeom g, double* dpacked);
+// Kinv = Linv^T Linv (Mf x Mf, full symmetric) and alpha = Linv^T V, for the gradient pass
+void gpfo_kinv_alpha(cudaStream_t st, const double* dLinv, int Mf, const double* dV, int R, double* dKinv, double* dalpha);
 void gpfo_prepare_inputs(cudaStream_t st, const double* dX, int M, int Mp, int D, const double* d_ell,
                          double* dXs, double* dxn);
 
@@ -247,4 +260,12 @@ struct CellsDev {
 int gpfo_hvpoi_grid(int64_t N, int num_sms);
 size_t gpfo_hvpoi_smem_bytes(int n_ext, int R);
 cudaError_t gpfo_hvpoi_launch(cudaStream_t st, const ProgramDev* d_prog, const CellsDev& cells, EvalIO io, int grid,
-                              int slot_first);
+                              int slot_first, int with_grad);
+size_t gpfo_hvpoi_smem_bytes_grad(int n_ext, int R);
+
+// grad.cu
+cudaError_t gpfo_program_grad_launch(cudaStream_t st, const ProgramDev* d_prog, EvalIO io, int grid);
+int gpfo_program_grad_grid(int64_t N, int num_sms);
+cudaError_t gpfo_contract_grad_launch(cudaStream_t st, int kind, const GpDev* d_gp, EvalIO io, int grid, int D);
+int gpfo_contract_grad_grid(int64_t N, int num_sms);
+int gpfo_contract_grad_rbc();

@@ -11,16 +11,21 @@
 #define HV_THREADS 256
 #define HV_RMAX 8          // objectives
 
-template <int R>
+// GRAD: also d(Hv PoI)/d mean_j and /d var_j per candidate (closed form of SURVEY Appendix A item 10), fed through the
+// forward-mode program evaluation; writes the per-slot coefficients the contraction kernel's gradient mode consumes.
+template <int R, bool GRAD>
 __global__ void __launch_bounds__(HV_THREADS)
 hvpoi_kernel(const ProgramDev* __restrict__ prog, CellsDev cells, EvalIO io, int slot_first) {
     extern __shared__ double sm[];
     const int n_ext = cells.n_ext;
+    constexpr int NQ = GRAD ? 2 + 3 * R : 2;           // per-candidate sums: PoI, Hv [, dPoI/dmu_j, dPoI/dsd_j, dHv/dmu_j]
     double* pf = sm;                                   // [n_ext][R]
     double* phi = pf + (size_t)n_ext * R;              // [HV_TC][n_ext][R]
     double* cmu = phi + (size_t)HV_TC * n_ext * R;     // [HV_TC][R]
     double* csd = cmu + HV_TC * R;                     // [HV_TC][R]
-    double* red = csd + HV_TC * R;                     // [HV_THREADS/32][HV_TC][2]
+    double* red = csd + HV_TC * R;                     // [HV_THREADS/32][HV_TC][NQ]
+    double* pdf = red + (HV_THREADS / 32) * HV_TC * NQ;            // GRAD: [HV_TC][n_ext][R] phi(z)
+    double* zpdf = pdf + (GRAD ? (size_t)HV_TC * n_ext * R : 0);   // GRAD: [HV_TC][n_ext][R] z phi(z)
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
     for (int e = tid; e < n_ext * R; e += HV_THREADS) pf[e] = cells.pf_ext[e];
@@ -47,12 +52,21 @@ hvpoi_kernel(const ProgramDev* __restrict__ prog, CellsDev cells, EvalIO io, int
         // Phi[t][i][j] = Normal(mu_tj, sd_tj).cdf(pf_ext[i][j])                           (hvpoi.py:112-113)
         for (int e = tid; e < HV_TC * n_ext * R; e += HV_THREADS) {
             const int t = e / (n_ext * R), ij = e % (n_ext * R), j = ij % R;
-            phi[e] = gpfo_ndtr((pf[ij] - cmu[t * R + j]) / csd[t * R + j]);
+            const double z = (pf[ij] - cmu[t * R + j]) / csd[t * R + j];
+            phi[e] = gpfo_ndtr(z);
+            if (GRAD) {                                // terms with infinite z vanish
+                const bool fin = isfinite(z);
+                const double pz = fin ? gpfo_std_pdf(z) : 0.0;
+                pdf[e] = pz;
+                zpdf[e] = fin ? z * pz : 0.0;
+            }
         }
         __syncthreads();
-        double poi[HV_TC], hv[HV_TC];
+        double q[HV_TC][NQ];
 #pragma unroll
-        for (int t = 0; t < HV_TC; ++t) { poi[t] = 0.0; hv[t] = 0.0; }
+        for (int t = 0; t < HV_TC; ++t)
+#pragma unroll
+            for (int k = 0; k < NQ; ++k) q[t][k] = 0.0;
         for (int64_t c = tid; c < cells.C; c += HV_THREADS) {
             int ub[R], lb[R];
             double ubp[R], lbp[R];
@@ -68,45 +82,79 @@ hvpoi_kernel(const ProgramDev* __restrict__ prog, CellsDev cells, EvalIO io, int
                 const double* ph = phi + (size_t)t * n_ext * R;
                 double pr = 1.0, ext = 1.0;
                 bool valid = true;
+                double dP[R], ex[R];
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
-                    pr *= (ph[ub[j]] - ph[lb[j]]);                                         // hvpoi.py:116-120
+                    dP[j] = ph[ub[j]] - ph[lb[j]];
+                    pr *= dP[j];                                                           // hvpoi.py:116-120
                     const double m = cmu[t * R + j];
                     valid = valid && (ubp[j] > m);                                         // hvpoi.py:130-131
-                    ext *= (ubp[j] - fmax(lbp[j], m));                                     // hvpoi.py:133-136
+                    ex[j] = ubp[j] - fmax(lbp[j], m);
+                    ext *= ex[j];                                                          // hvpoi.py:133-136
                 }
-                poi[t] += pr;
-                hv[t] += valid ? ext : 0.0;
+                q[t][0] += pr;
+                q[t][1] += valid ? ext : 0.0;
+                if (GRAD) {
+                    const double* pd = pdf + (size_t)t * n_ext * R;
+                    const double* zp = zpdf + (size_t)t * n_ext * R;
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        double oP = 1.0, oE = 1.0;                                         // exclusive products
+#pragma unroll
+                        for (int k = 0; k < R; ++k) if (k != j) { oP *= dP[k]; oE *= ex[k]; }
+                        const double isd = 1.0 / csd[t * R + j];
+                        q[t][2 + j] += oP * (-(pd[ub[j]] - pd[lb[j]]) * isd);              // d PoI / d mu_j
+                        q[t][2 + R + j] += oP * (-(zp[ub[j]] - zp[lb[j]]) * isd);          // d PoI / d sd_j
+                        // tf.maximum(lb, mu): the gradient reaches mu only where lb < mu; the indicator carries none
+                        q[t][2 + 2 * R + j] += (valid && lbp[j] < cmu[t * R + j]) ? -oE : 0.0;   // d Hv / d mu_j
+                    }
+                }
             }
         }
         // deterministic block reduction: shuffle tree inside the warp, fixed warp order across warps
 #pragma unroll
-        for (int t = 0; t < HV_TC; ++t) {
-            double a = poi[t], b = hv[t];
+        for (int t = 0; t < HV_TC; ++t)
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                a += __shfl_xor_sync(0xffffffffu, a, o);
-                b += __shfl_xor_sync(0xffffffffu, b, o);
+            for (int k = 0; k < NQ; ++k) {
+                double a = q[t][k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                if (lane == 0) red[(w * HV_TC + t) * NQ + k] = a;
             }
-            if (lane == 0) { red[(w * HV_TC + t) * 2] = a; red[(w * HV_TC + t) * 2 + 1] = b; }
-        }
         __syncthreads();
         if (w == 0) {
             double val = 0.0;
             long long idx = -1;
             const int64_t n = n0 + lane;
             if (lane < HV_TC && n < io.N) {
-                double a = 0.0, b = 0.0;
-                for (int ww = 0; ww < HV_THREADS / 32; ++ww) {
-                    a += red[(ww * HV_TC + lane) * 2];
-                    b += red[(ww * HV_TC + lane) * 2 + 1];
+                double tq[NQ];
+#pragma unroll
+                for (int k = 0; k < NQ; ++k) {
+                    double a = 0.0;
+                    for (int ww = 0; ww < HV_THREADS / 32; ++ww) a += red[(ww * HV_TC + lane) * NQ + k];
+                    tq[k] = a;
                 }
-                const double leaf = b * a;                                                 // Hv * PoI, hvpoi.py:140
+                const double leaf = tq[1] * tq[0];                                         // Hv * PoI, hvpoi.py:140
                 double mu[GPFO_MAX_SLOTS], va[GPFO_MAX_SLOTS];
                 for (int s = 0; s < prog->nslots; ++s) {
                     mu[s] = io.mom_mean[(size_t)s * io.N + n];
                     va[s] = io.mom_var[(size_t)s * io.N + n];
                 }
+                if (GRAD) {
+                    double hdm[R], hdv[R], dmu[GPFO_MAX_SLOTS], dva[GPFO_MAX_SLOTS];
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        hdm[j] = tq[0] * tq[2 + 2 * R + j] + tq[1] * tq[2 + j];           // PoI dHv + Hv dPoI
+                        const double v0 = va[slot_first + j];
+                        const double ds_dv = (v0 >= GPFO_STABILITY) ? 1.0 / (2.0 * csd[lane * R + j]) : 0.0;
+                        hdv[j] = tq[1] * tq[2 + R + j] * ds_dv;
+                    }
+                    val = gpfo_run_program<true>(*prog, mu, va, leaf, hdm, hdv, dmu, dva);
+                    for (int s = 0; s < prog->nslots; ++s) {
+                        io.cmu[(size_t)s * io.N + n] = dmu[s];
+                        io.cva[(size_t)s * io.N + n] = dva[s];
+                    }
+                } else
                 val = gpfo_run_program<false>(*prog, mu, va, leaf, nullptr, nullptr, nullptr, nullptr);
                 if (io.values) io.values[n] = val;
                 idx = n;
@@ -126,12 +174,16 @@ hvpoi_kernel(const ProgramDev* __restrict__ prog, CellsDev cells, EvalIO io, int
     }
 }
 
-template <int R>
+static size_t hv_smem(int n_ext, int R, bool grad) {
+    const int nq = grad ? 2 + 3 * R : 2;
+    return ((size_t)n_ext * R * (1 + HV_TC * (grad ? 3 : 1)) + 2 * HV_TC * R + (HV_THREADS / 32) * HV_TC * nq) * sizeof(double);
+}
+
+template <int R, bool GRAD>
 static cudaError_t launch_hv(cudaStream_t st, const ProgramDev* d_prog, const CellsDev& cells, EvalIO io, int grid,
                              int slot_first) {
-    const size_t smem = ((size_t)cells.n_ext * R * (1 + HV_TC) + 2 * HV_TC * R + (HV_THREADS / 32) * HV_TC * 2) *
-                       sizeof(double);
-    auto kern = hvpoi_kernel<R>;
+    const size_t smem = hv_smem(cells.n_ext, R, GRAD);
+    auto kern = hvpoi_kernel<R, GRAD>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, HV_THREADS, smem, st>>>(d_prog, cells, io, slot_first);
@@ -144,18 +196,24 @@ int gpfo_hvpoi_grid(int64_t N, int num_sms) {
     return (int)(ntiles < cap ? (ntiles > 0 ? ntiles : 1) : cap);
 }
 
-size_t gpfo_hvpoi_smem_bytes(int n_ext, int R) {
-    return ((size_t)n_ext * R * (1 + HV_TC) + 2 * HV_TC * R + (HV_THREADS / 32) * HV_TC * 2) * sizeof(double);
+size_t gpfo_hvpoi_smem_bytes(int n_ext, int R) { return hv_smem(n_ext, R, false); }
+size_t gpfo_hvpoi_smem_bytes_grad(int n_ext, int R) { return hv_smem(n_ext, R, true); }
+
+template <int R>
+static cudaError_t launch_hv_r(cudaStream_t st, const ProgramDev* d_prog, const CellsDev& cells, EvalIO io, int grid,
+                               int slot_first, int with_grad) {
+    return with_grad ? launch_hv<R, true>(st, d_prog, cells, io, grid, slot_first)
+                     : launch_hv<R, false>(st, d_prog, cells, io, grid, slot_first);
 }
 
 cudaError_t gpfo_hvpoi_launch(cudaStream_t st, const ProgramDev* d_prog, const CellsDev& cells, EvalIO io, int grid,
-                              int slot_first) {
+                              int slot_first, int with_grad) {
     switch (cells.R) {
-        case 2: return launch_hv<2>(st, d_prog, cells, io, grid, slot_first);
-        case 3: return launch_hv<3>(st, d_prog, cells, io, grid, slot_first);
-        case 4: return launch_hv<4>(st, d_prog, cells, io, grid, slot_first);
-        case 5: return launch_hv<5>(st, d_prog, cells, io, grid, slot_first);
-        case 6: return launch_hv<6>(st, d_prog, cells, io, grid, slot_first);
+        case 2: return launch_hv_r<2>(st, d_prog, cells, io, grid, slot_first, with_grad);
+        case 3: return launch_hv_r<3>(st, d_prog, cells, io, grid, slot_first, with_grad);
+        case 4: return launch_hv_r<4>(st, d_prog, cells, io, grid, slot_first, with_grad);
+        case 5: return launch_hv_r<5>(st, d_prog, cells, io, grid, slot_first, with_grad);
+        case 6: return launch_hv_r<6>(st, d_prog, cells, io, grid, slot_first, with_grad);
         default: return cudaErrorInvalidValue;
     }
 }

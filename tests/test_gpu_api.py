@@ -181,3 +181,30 @@ def test_mc_and_candidate_optimizer_fused_equals_generic():
     r = MCOptimizer(DOMAIN, 2000).optimize(inverse_acquisition)
     assert r.success and r.x in DOMAIN and r.nfev == 2000
     assert np.allclose(-ei.evaluate(r.x), r.fun)
+
+
+def test_evaluate_with_gradients_contract_and_scipy_polish():
+    """reference test_implementations.py:19-33 (shapes, evaluate == ewg[0]) and the Staged MC -> L-BFGS-B pipeline of
+    the notebooks (optim.py:201-282) fed by the device gradient."""
+    from gpflowopt_b200.optim import SciPyOptimizer, StagedOptimizer
+    X = _design(20, seed=8)
+    ei = ExpectedImprovement(_gpr(X, parabola2d(X), gpfo.Matern52))
+    ei.enable_scaling(DOMAIN)
+    Xc = RandomDesign(10, DOMAIN).generate()
+    p = ei.evaluate(Xc)
+    q = ei.evaluate_with_gradients(Xc)
+    assert isinstance(q, tuple) and len(q) == 2 and q[0].shape == (10, 1) and q[1].shape == (10, 2)
+    np.testing.assert_array_equal(p, q[0])
+    g = _ogp(X, parabola2d(X), ogp.MATERN52, scaled=True)
+    rv, rg = oacq.Leaf('ei', g, oacq.fmin_of(g, X)[0]).value_and_grad(Xc)
+    assert_parity(q[1], rg, what="EI gradient through the API")
+
+    def inverse_acquisition(x):
+        return tuple(-r for r in ei.evaluate_with_gradients(np.atleast_2d(x)))
+    inverse_acquisition.acquisition = ei
+    np.random.seed(3)
+    staged = StagedOptimizer([MCOptimizer(DOMAIN, 2000), SciPyOptimizer(DOMAIN)])
+    r = staged.optimize(inverse_acquisition)
+    assert r.success and r.nstages == 2 and r.x in DOMAIN
+    mc_best = -np.max(ei.evaluate(RandomDesign(2000, DOMAIN).generate()))
+    assert np.ravel(r.fun)[0] <= mc_best + 1e-12 or np.ravel(r.fun)[0] < 0

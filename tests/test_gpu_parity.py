@@ -246,3 +246,98 @@ def test_headline_shape_subset_and_properties(ctx):
     mo, vo = g2.predict(Xs)
     assert_parity(mean, mo, tol=1e-8, what="mean, cond 4e7")      # documented: conditioning-limited (both sides)
     assert_parity(var, vo, scale=g2.variance, tol=1e-8, what="var, cond 4e7")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# gradients: d acq / d Xcand against the oracle's closed form (itself checked against torch autograd of
+# the reference's op graph in tests/test_oracle_gp.py).  Same scale-relative 1e-9 tolerance, scale = max |grad|.
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["rbf", "matern52", "matern32"])
+@pytest.mark.parametrize("leaf,param", [("ei", -0.5), ("poi", -0.5), ("pof", 0.15), ("lcb", 2.0)])
+def test_leaf_gradients(ctx, kind, leaf, param):
+    g, lo, up = _model(260, 5, kind, scaled=True)
+    upload_oracle_gp(ctx, 0, g)
+    if leaf in ("ei", "poi"):
+        param = float(np.min(g.predict(g.input_transform.backward(g.Xs))[0])) + 0.1
+    op = {"ei": _lib.OP_EI, "poi": _lib.OP_POI, "pof": _lib.OP_POF, "lcb": _lib.OP_LCB}[leaf]
+    ctx.program_set([[op, 0, 0, 0]], [param])
+    for N in (1, 33, 700):
+        Xc = _cands(N, 5, lo, up)
+        vals, grads, bv, bi = ctx.eval(Xc, want_grads=True)
+        rv, rg = oacq.Leaf(leaf, g, param).value_and_grad(Xc)
+        assert_parity(vals, rv, what="%s value (grad call) N=%d" % (leaf, N))
+        assert_parity(grads, rg, what="%s grad N=%d" % (leaf, N))
+        assert grads.shape == (N, 5)
+        v_only, _, _, _ = ctx.eval(Xc)
+        np.testing.assert_array_equal(v_only, vals)     # reference test_implementations.py:33: evaluate == ewg[0]
+        assert bi == int(np.argmax(vals))
+
+
+def test_product_sum_gradients_multi_gp(ctx):
+    D, N = 3, 500
+    g1, lo, up = _model(120, D, "matern52", scaled=True)
+    g2, _, _ = _model(90, D, "rbf", seed=77, scaled=True)
+    for i, g in enumerate((g1, g2)):
+        upload_oracle_gp(ctx, i, g, slot0=i)
+    ctx.gp_count_set(2)
+    try:
+        Xc = _cands(N, D, lo, up)
+        f1 = float(np.min(g1.predict(g1.input_transform.backward(g1.Xs))[0]))
+        ei1, pof2, lcb2 = oacq.Leaf('ei', g1, f1), oacq.Leaf('pof', g2, 2.5), oacq.Leaf('lcb', g2, 1.5)
+        cases = [
+            ([[_lib.OP_EI, 0, 0, 0], [_lib.OP_POF, 1, 0, 1], [_lib.OP_PROD, 2, 0, 0]], [f1, 2.5], oacq.Agg('prod', [ei1, pof2])),
+            ([[_lib.OP_EI, 0, 0, 0], [_lib.OP_POF, 1, 0, 1], [_lib.OP_LCB, 1, 0, 2], [_lib.OP_SUM, 2, 0, 0],
+              [_lib.OP_PROD, 2, 0, 0], [_lib.OP_SCALE, 0, 0, 3]], [f1, 2.5, 1.5, 0.25],
+             oacq.Agg('prod', [ei1, oacq.Agg('sum', [pof2, lcb2])], scale=0.25)),
+        ]
+        for ops, params, node in cases:
+            ctx.program_set(ops, params)
+            vals, grads, _, _ = ctx.eval(Xc, want_grads=True)
+            rv, rg = node.value_and_grad(Xc)
+            assert_parity(vals, rv, what="value " + str(ops))
+            assert_parity(grads, rg, what="grad " + str(ops))
+    finally:
+        ctx.gp_count_set(1)
+
+
+@pytest.mark.parametrize("R", [2, 3])
+def test_hvpoi_gradients(ctx, R):
+    D, M, N = 4, 70, 400
+    X = synthetic.candidates(M, D, seed=5)
+    F = synthetic.dtlz2_objectives(X, R)
+    h = synthetic.hypers(D, 1e-3)
+    gps = [oracle_gp(X, F[:, [j]], ogp.MATERN52, h) for j in range(R)]
+    for j, g in enumerate(gps):
+        upload_oracle_gp(ctx, j, g, slot0=j)
+    ctx.gp_count_set(R)
+    try:
+        p = opareto.Pareto(np.zeros((1, R)))
+        p.update(np.hstack([g.predict(X)[0] for g in gps]))
+        hv = oacq.HVPoI(gps, p.front, p.lb, p.ub)
+        ctx.cells_set(hv.pf_ext(), p.lb, p.ub)
+        ctx.program_set([[_lib.OP_HVPOI, 0, R, 0]], [])
+        Xc = synthetic.candidates(N, D)
+        vals, grads, _, _ = ctx.eval(Xc, want_grads=True)
+        rv, rg = hv.value_and_grad(Xc)
+        assert_parity(vals, rv, what="HVPoI value R=%d" % R)
+        assert_parity(grads, rg, what="HVPoI grad R=%d" % R)
+    finally:
+        ctx.gp_count_set(1)
+
+
+def test_gradient_large_m_and_finite_difference(ctx):
+    """M = 1100 (three 512-row chunks incl. a partial one) and an independent central finite-difference check."""
+    g, lo, up = _model(1100, 8, "matern52")
+    upload_oracle_gp(ctx, 0, g)
+    fmin = float(np.min(g.predict(g.Xs)[0]))
+    ctx.program_set([[_lib.OP_EI, 0, 0, 0]], [fmin])
+    Xc = _cands(300, 8, lo, up)
+    vals, grads, _, _ = ctx.eval(Xc, want_grads=True)
+    rv, rg = oacq.Leaf('ei', g, fmin).value_and_grad(Xc)
+    assert_parity(grads, rg, what="EI grad M=1100")
+    eps = 1e-6
+    for d in (0, 7):
+        e = np.zeros(8)
+        e[d] = eps
+        fd = (ctx.eval(Xc + e)[0] - ctx.eval(Xc - e)[0])[:, 0] / (2 * eps)
+        assert np.max(np.abs(fd - grads[:, d])) <= 1e-5 * np.max(np.abs(grads))
