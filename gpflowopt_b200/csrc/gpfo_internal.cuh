@@ -122,7 +122,8 @@ __device__ __forceinline__ double gpfo_std_pdf(double z) {
 __device__ __forceinline__ double gpfo_normal_prob(double x, double loc, double scale) {
     const double half_log_2pi = 0.91893853320467267;
     double z = (x - loc) / scale;
-    return exp(-0.5 * (z * z) - (half_log_2pi + log(scale)));
+    // explicit roundings (no FMA contraction): the same bits in every kernel this is inlined into, and TF's op order
+    return exp(__dsub_rn(__dmul_rn(-0.5, __dmul_rn(z, z)), __dadd_rn(half_log_2pi, log(scale))));
 }
 
 // Evaluates the postfix acquisition program for one candidate.
@@ -151,7 +152,7 @@ __device__ __forceinline__ double gpfo_run_program(const ProgramDev& pr, const d
                 const double sig = pr.params[c];
                 const double v = fmax(v0, 0.0);
                 const double s = sqrt(v);
-                val = m - sig * s;
+                val = __dsub_rn(m, __dmul_rn(sig, s));
                 if (GRAD) { d_m = 1.0; d_v = (v0 >= 0.0) ? -sig / (2.0 * s) : 0.0; }
             } else {
                 const double p = pr.params[c];
@@ -161,7 +162,7 @@ __device__ __forceinline__ double gpfo_run_program(const ProgramDev& pr, const d
                 const double Phi = gpfo_ndtr(z);
                 const double ds_dv = (v0 >= GPFO_STABILITY) ? 1.0 / (2.0 * s) : 0.0;
                 if (op == GPFO_OP_EI) {
-                    val = (p - m) * Phi + v * gpfo_normal_prob(p, m, s);
+                    val = __dadd_rn(__dmul_rn(p - m, Phi), __dmul_rn(v, gpfo_normal_prob(p, m, s)));
                     if (GRAD) { d_m = -Phi; d_v = gpfo_std_pdf(z) * ds_dv; }
                 } else {
                     val = Phi;

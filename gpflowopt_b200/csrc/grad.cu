@@ -19,7 +19,10 @@ __global__ void __launch_bounds__(PG_THREADS) program_grad_kernel(const ProgramD
             mu[s] = io.mom_mean[(size_t)s * io.N + n];
             va[s] = io.mom_var[(size_t)s * io.N + n];
         }
-        const double val = gpfo_run_program<true>(*prog, mu, va, 0.0, nullptr, nullptr, dmu, dva);
+        // the VALUE comes from the same instantiation the plain evaluate path uses, so evaluate(X) == evaluate_with_gradients(X)[0]
+        // bit for bit (reference testing/unit/test_implementations.py:33); the forward-mode pass supplies the partials only
+        const double val = gpfo_run_program<false>(*prog, mu, va, 0.0, nullptr, nullptr, nullptr, nullptr);
+        gpfo_run_program<true>(*prog, mu, va, 0.0, nullptr, nullptr, dmu, dva);
         for (int s = 0; s < ns; ++s) {
             io.cmu[(size_t)s * io.N + n] = dmu[s];
             io.cva[(size_t)s * io.N + n] = dva[s];

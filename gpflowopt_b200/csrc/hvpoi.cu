@@ -149,7 +149,8 @@ hvpoi_kernel(const ProgramDev* __restrict__ prog, CellsDev cells, EvalIO io, int
                         const double ds_dv = (v0 >= GPFO_STABILITY) ? 1.0 / (2.0 * csd[lane * R + j]) : 0.0;
                         hdv[j] = tq[1] * tq[2 + R + j] * ds_dv;
                     }
-                    val = gpfo_run_program<true>(*prog, mu, va, leaf, hdm, hdv, dmu, dva);
+                    val = gpfo_run_program<false>(*prog, mu, va, leaf, nullptr, nullptr, nullptr, nullptr);   // same code as evaluate
+                    gpfo_run_program<true>(*prog, mu, va, leaf, hdm, hdv, dmu, dva);
                     for (int s = 0; s < prog->nslots; ++s) {
                         io.cmu[(size_t)s * io.N + n] = dmu[s];
                         io.cva[(size_t)s * io.N + n] = dva[s];
