@@ -70,9 +70,25 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def cpu_oracle_throughput(n_sample, threads_note=True):
+def host_threads():
+    """Threads the CPU arm really uses: all host cores (torchrun exports OMP_NUM_THREADS=1, so the BLAS pool is
+    re-sized at run time through threadpoolctl)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:                                 # pragma: no cover
+        n = os.cpu_count() or 1
+    return max(1, n)
+
+
+def cpu_oracle_throughput(n_sample):
     """Times the CPU oracle (op-for-op NumPy/SciPy restatement; OpenBLAS threads = all host cores) on a bounded
     sample of the same workload; candidates in chunks of 4096 rows (what the literal reference graph can hold)."""
+    from threadpoolctl import threadpool_limits
+    with threadpool_limits(limits=host_threads()):
+        return _cpu_oracle_throughput(n_sample)
+
+
+def _cpu_oracle_throughput(n_sample):
     from gpflowopt_b200 import synthetic
     from oracle import acq as oacq, gp as ogp
     X, Y = synthetic.training_set(M, D)
@@ -93,7 +109,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count()
+    cores = host_threads()
     n_sample = 20000
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_oracle_throughput(4096)
@@ -247,7 +263,7 @@ def main():
         if not args.no_cpu_baseline:
             n_cpu = 100000
             v_cpu, dt = cpu_oracle_throughput(n_cpu)
-            out["cpu_baseline"] = {"value": v_cpu, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            out["cpu_baseline"] = {"value": v_cpu, "unit": UNIT, "cores": host_threads(), "kind": "port",
                                    "sample": "%d candidates (%.1f s) in 4096-row chunks, Cholesky hoisted, "
                                              "NumPy/SciPy + OpenBLAS on all host cores" % (n_cpu, dt)}
         print(json.dumps(out))

@@ -4,7 +4,8 @@ Only the data-parallel hot path of GPflowOpt lives here: s
 EI / PoI / PoF / LCB, their sums and products and HVPoI, on hand-written FP64 CUDA kernels for sm_100a
 (libgpfo.so, C-ABI in include/gpfo.h).  There is no CPU fallback.
 """
-from . import acquisition, design, domain, optim, pareto, scaling, transforms
+from . import acquisition, bo, design, domain, optim, pareto, scaling, transforms
+from .bo import BayesianOptimizer
 from ._lib import GpfoError, NotPositiveDefiniteError
 from .engine import get_device, set_device
 from .gpr import GPR, RBF, Matern32, Matern52
