@@ -14,6 +14,9 @@ struct GpHost {
     double *dL = nullptr, *dLinv = nullptr, *dpacked = nullptr;
     double *dalpha = nullptr, *dpacked_kinv = nullptr;      // gradient pass state, built lazily
     bool kinv_ready = false;
+    double* dpacked_c[2] = {nullptr, nullptr};              // cluster layout (contract3), built lazily
+    size_t cap_packed_c[2] = {0, 0};
+    bool cluster_ready = false;
     int packed_rbc = 0;
     size_t cap_mf = 0, cap_d = 0, cap_r = 0, cap_packed = 0, cap_alpha = 0, cap_kinv = 0;
     GpDev hdev;
@@ -41,6 +44,7 @@ struct gpfo_ctx {
     double *dmom_mean = nullptr, *dmom_var = nullptr; size_t cap_mom = 0;
     double *dcmu = nullptr, *dcva = nullptr; size_t cap_coef = 0;
     double* dgrads = nullptr; size_t cap_grads = 0;
+    double* dkx_scratch = nullptr; size_t cap_kx_scratch = 0;
     double* dpart_val = nullptr; long long* dpart_idx = nullptr; int cap_parts = 0;
     double* dbest_val = nullptr; long long* dbest_idx = nullptr;
     int* dflag = nullptr;
@@ -127,7 +131,7 @@ int gpfo_ctx_create(int device, gpfo_ctx** out) {
 static void free_gp(GpHost& g) {
     cudaFree(g.dX); cudaFree(g.dell); cudaFree(g.dXs); cudaFree(g.dxn); cudaFree(g.dY); cudaFree(g.dV);
     cudaFree(g.dL); cudaFree(g.dLinv); cudaFree(g.dpacked); cudaFree(g.ddev);
-    cudaFree(g.dalpha); cudaFree(g.dpacked_kinv);
+    cudaFree(g.dalpha); cudaFree(g.dpacked_kinv); cudaFree(g.dpacked_c[0]); cudaFree(g.dpacked_c[1]);
     g = GpHost();
 }
 
@@ -138,7 +142,7 @@ int gpfo_ctx_destroy(gpfo_ctx* ctx) {
     for (int i = 0; i < GPFO_MAX_GPS; ++i) free_gp(ctx->gps[i]);
     cudaFree(ctx->dprog); cudaFree(ctx->dpf); cudaFree(ctx->dlb); cudaFree(ctx->dub);
     cudaFree(ctx->dXc); cudaFree(ctx->dvalues); cudaFree(ctx->dmom_mean); cudaFree(ctx->dmom_var);
-    cudaFree(ctx->dcmu); cudaFree(ctx->dcva); cudaFree(ctx->dgrads);
+    cudaFree(ctx->dcmu); cudaFree(ctx->dcva); cudaFree(ctx->dgrads); cudaFree(ctx->dkx_scratch);
     cudaFree(ctx->dpart_val); cudaFree(ctx->dpart_idx); cudaFree(ctx->dbest_val); cudaFree(ctx->dbest_idx);
     cudaFree(ctx->dflag);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
@@ -169,6 +173,25 @@ static int repack(gpfo_ctx* ctx, GpHost& g, int rbc) {
     g.hdev.packed = g.dpacked;
     CK(cudaMemcpyAsync(g.ddev, &g.hdev, sizeof(GpDev), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return GPFO_OK;
+}
+
+// Cluster-layout block streams of L^-1 for the 2-CTA kernel (variant 10), built on first use.
+static int ensure_cluster_pack(gpfo_ctx* ctx, GpHost& g) {
+    if (g.cluster_ready) return GPFO_OK;
+    ClusterGeom cgm;
+    long long total[2];
+    gpfo_cluster_geom(g.Mp / 8, gpfo_contract3_rbc(), &cgm, total);
+    if (cgm.nchunks > GPFO_MAX_CCHUNKS) return fail(ctx, GPFO_ERR_UNSUPPORTED, "M too large for the cluster layout");
+    for (int c = 0; c < 2; ++c) CK(ensure(&g.dpacked_c[c], &g.cap_packed_c[c], (size_t)(total[c] > 0 ? total[c] : 1) * 64));
+    gpfo_pack_linv_cluster(ctx->stream, g.dLinv, g.Mf, cgm, g.dpacked_c[0], g.dpacked_c[1]);
+    CK(cudaGetLastError());
+    g.hdev.packed_c[0] = g.dpacked_c[0];
+    g.hdev.packed_c[1] = g.dpacked_c[1];
+    g.hdev.cgeom = cgm;
+    CK(cudaMemcpyAsync(g.ddev, &g.hdev, sizeof(GpDev), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    g.cluster_ready = true;
     return GPFO_OK;
 }
 
@@ -233,6 +256,7 @@ int gpfo_gp_set(gpfo_ctx* ctx, int gp_id, int64_t M64, int D, int R, const doubl
     }
     g.valid = false;
     g.kinv_ready = false;
+    g.cluster_ready = false;
     g.M = M; g.Mp = Mp; g.Mf = Mf; g.D = D; g.R = R; g.kind = kernel_kind; g.slot0 = slot0;
     memset(&g.hdev, 0, sizeof(GpDev));
     double ell[GPFO_MAX_DIM];
@@ -432,9 +456,13 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     const bool host_in = (dX != Xcand);
 
     const int variant = effective_variant(ctx, N);
+    const bool use_cluster = variant == 10;
     const int rbc = gpfo_contract_rbc(variant);
-    for (int g = 0; g < ctx->ngps; ++g)
-        if (ctx->gps[g].packed_rbc != rbc) { rc = repack(ctx, ctx->gps[g], rbc); if (rc != GPFO_OK) return rc; }
+    for (int g = 0; g < ctx->ngps; ++g) {
+        if (use_cluster) rc = ensure_cluster_pack(ctx, ctx->gps[g]);
+        else if (ctx->gps[g].packed_rbc != rbc) rc = repack(ctx, ctx->gps[g], rbc);
+        if (rc != GPFO_OK) return rc;
+    }
 
     const bool hv = ctx->hprog.has_hvpoi != 0;
     const bool need_mom = hv || ctx->ngps > 1 || want_grad;
@@ -473,7 +501,7 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
         if (dev_grads) io.grads = out_grads;
         else { CK(ensure(&ctx->dgrads, &ctx->cap_grads, (size_t)N * D)); io.grads = ctx->dgrads; }
     }
-    const int grid = gpfo_contract_grid(variant, N, ctx->num_sms);
+    const int grid = use_cluster ? gpfo_contract3_clusters(N, ctx->num_sms) : gpfo_contract_grid(variant, N, ctx->num_sms);
     const int hv_grid = gpfo_hvpoi_grid(N, ctx->num_sms);
     const int pg_grid = gpfo_program_grad_grid(N, ctx->num_sms);
     int max_parts = grid > hv_grid ? grid : hv_grid;
@@ -489,8 +517,16 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
         EvalIO gio = io;
         gio.write_moments = need_mom ? 1 : 0;
         gio.run_program = (!hv && !want_grad && g == ctx->ngps - 1) ? 1 : 0;
+        if (variant == 11 || variant == 12 || (variant >= 120 && variant <= 129)) {   // per-CTA K(X*,X) scratch: ceil(nrb / 8) groups of 8*8*T doubles
+            const size_t groups = (size_t)(ctx->gps[g].Mp / 8 + 7) / 8;
+            const size_t stride = groups * 64 * (size_t)gpfo_contract_tile(variant);
+            CK(ensure(&ctx->dkx_scratch, &ctx->cap_kx_scratch, stride * (size_t)grid));
+            gio.kx_scratch = ctx->dkx_scratch;
+            gio.kx_scratch_stride = (long long)stride;
+        }
         CK(cudaEventRecord(ctx->ev[6], st));
-        CK(gpfo_contract_launch(st, variant, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
+        if (use_cluster) CK(gpfo_contract3_launch(st, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
+        else CK(gpfo_contract_launch(st, variant, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
         CK(cudaEventRecord(ctx->ev[7], st));
         ++launches;
         if (ctx->ngps > 1) {                 // per-GP timing needs a sync only when events are reused
@@ -567,7 +603,8 @@ int gpfo_predict(gpfo_ctx* ctx, int gp_id, const double* X, int64_t N, int D, do
     const double* dX = nullptr;
     int rc = stage_candidates(ctx, X, N, D, &dX);
     if (rc != GPFO_OK) return rc;
-    const int variant = effective_variant(ctx, N);
+    int variant = effective_variant(ctx, N);
+    if (variant == 10) variant = (N >= (int64_t)32 * ctx->num_sms) ? 4 : ((N >= (int64_t)16 * ctx->num_sms) ? 5 : 6);
     const int rbc = gpfo_contract_rbc(variant);
     if (g.packed_rbc != rbc) { rc = repack(ctx, g, rbc); if (rc != GPFO_OK) return rc; }
     const size_t need = (size_t)GPFO_MAX_SLOTS * N;
@@ -607,7 +644,7 @@ int gpfo_timings_get(const gpfo_ctx* ctx, gpfo_timings* out) {
 
 int gpfo_set_variant(gpfo_ctx* ctx, int variant) {
     if (!ctx) return GPFO_ERR_STATE;
-    if (variant < 0 || variant > 49) return fail(ctx, GPFO_ERR_BAD_SHAPE, "variant out of range");
+    if (variant < 0 || variant > 129) return fail(ctx, GPFO_ERR_BAD_SHAPE, "variant out of range");
     ctx->variant = variant;
     return GPFO_OK;
 }

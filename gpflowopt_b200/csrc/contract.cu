@@ -300,8 +300,9 @@ static cudaError_t launch_variant(cudaStream_t st, const GpDev* d_gp, const Prog
 // (contract2.cu).  Ablation results are meaningless numerically.
 struct VarInfo { int gen, rbc, tile; };
 static VarInfo var_info(int v) {
-    if (v == 4 || v == 9 || (v >= 40 && v <= 49)) return {2, 64, 32};
+    if (v == 4 || v == 9 || v == 11 || (v >= 40 && v <= 49)) return {2, 64, 32};
     if (v == 7 || v == 8) return {2, 128, 16};
+    if (v == 12 || v == 13 || (v >= 120 && v <= 129)) return {2, 32, 64};
     if (v == 5) return {2, 64, 16};
     if (v == 6) return {2, 64, 8};
     if (v == 3 || (v >= 30 && v <= 39)) return {1, 64, 32};

@@ -12,88 +12,6 @@
 #include <type_traits>
 #include "contract_common.cuh"
 
-template <int NW, int RBW, int NB, int S>
-struct Contract2Cfg {
-    static constexpr int THREADS = 32 * NW;
-    static constexpr int RBC = NW * RBW;
-    static constexpr int T = 8 * NB;
-    static constexpr int GROUP_SLOTS = KPC * 2 * NB * 32;
-    static constexpr int GEN_ITERS = GROUP_SLOTS / THREADS;
-    static constexpr int RING_DOUBLES_PER_WARP = S * RBW * 64;
-    static_assert(NW % NB == 0, "per-thread candidate must be fixed");
-    static_assert(GROUP_SLOTS % THREADS == 0, "gen loop must tile");
-};
-
-__device__ __forceinline__ void cp_async16(unsigned smem_dst, const void* gmem_src) {     // smem_dst: shared-window address
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// The FP64 ALU and the DMMA unit share one issue pipe on B200 (profiles/r01_fp64_pipes.log: 37.0 TF/s DMMA alone,
-// 24.4 DFMA alone, 26.6 + 6.7 together), so every FP64 instruction spent on K(X*, X) is taken from the contraction.
-// The helpers below are therefore op-count-minimal and branch-free.
-
-// sqrt(x) for normal positive x: MUFU.RSQ64H seed (2^-22), one cubically convergent step on 1/sqrt (-> 2^-66),
-// then x * y.  About 1 ulp; no IEEE slow path.  6 FP64 ops.
-__device__ __forceinline__ double fast_sqrt_pos(double x) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double e = fma(-x, y * y, 1.0);
-    y = fma(y * e, fma(e, 0.375, 0.5), y);
-    return x * y;
-}
-
-// exp(x) for x <= 0: clamp at -708 (~1e-308 instead of a denormal / 0); k = round(32 x / ln 2), x = k ln2/32 + r
-// with |r| <= ln2/64; exp(x) = 2^(k>>5) * 2^((k&31)/32) * P6(r), P6 = degree-6 Taylor (truncation 3.5e-18 relative);
-// the 32-entry table of 2^(i/32) lives in shared memory.  12 FP64 ops.
-__device__ __forceinline__ double fast_exp_neg(double x, const double* __restrict__ tab32) {
-    x = fmax(x, -708.0);
-    const double magic = 6755399441055744.0;                 // 1.5 * 2^52
-    const double t = fma(x, 46.166241308446828, magic);      // 32 / ln 2
-    const double kf = t - magic;
-    double r = fma(kf, -2.1660849392498290e-02, x);          // ln2/32 (head)
-    r = fma(kf, -7.2470213052434896e-19, r);                 // ln2/32 (tail)
-    double p = 1.3888888888888889e-03;                       // 1/6!
-    p = fma(p, r, 8.3333333333333332e-03);
-    p = fma(p, r, 4.1666666666666664e-02);
-    p = fma(p, r, 1.6666666666666666e-01);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    const int k = __double2loint(t);                         // low word of t holds k (two's complement)
-    p *= tab32[k & 31];
-    return __hiloint2double(__double2hiint(p) + ((k >> 5) << 20), __double2loint(p));
-}
-
-template <int KIND>
-__device__ __forceinline__ double kx_branchless(double variance, double r2, const double* __restrict__ tab32) {
-    if (KIND == GPFO_KERN_RBF) return variance * fast_exp_neg(-0.5 * fmax(r2, 0.0), tab32);
-    const double x = r2 + 1e-12;                             // euclid_dist: sqrt(r2 + 1e-12); square(r) == x to 1 ulp
-    const double r = fast_sqrt_pos(x);
-    if (KIND == GPFO_KERN_MATERN52) {
-        const double s5 = 2.2360679774997898;
-        return (variance * fma(5.0 / 3.0, x, fma(s5, r, 1.0))) * fast_exp_neg(-s5 * r, tab32);
-    }
-    const double s3 = 1.7320508075688772;
-    return (variance * fma(s3, r, 1.0)) * fast_exp_neg(-s3 * r, tab32);
-}
-
-// d k / d r^2 for the gradient pass: RBF -k/2; Matern52 -(5/6) s2 (1 + sqrt5 r) e^{-sqrt5 r};
-// Matern32 -(3/2) s2 e^{-sqrt3 r}, with r = sqrt(r^2 + 1e-12) as in euclid_dist.
-template <int KIND>
-__device__ __forceinline__ double dk_dr2_branchless(double variance, double r2, const double* __restrict__ tab32) {
-    if (KIND == GPFO_KERN_RBF) return (-0.5 * variance) * fast_exp_neg(-0.5 * fmax(r2, 0.0), tab32);
-    const double r = fast_sqrt_pos(r2 + 1e-12);
-    if (KIND == GPFO_KERN_MATERN52) {
-        const double s5 = 2.2360679774997898;
-        return ((-5.0 / 6.0) * variance * fma(s5, r, 1.0)) * fast_exp_neg(-s5 * r, tab32);
-    }
-    const double s3 = 1.7320508075688772;
-    return (-1.5 * variance) * fast_exp_neg(-s3 * r, tab32);
-}
-
 // ABL bit 0/1: profiling ablations.  ABL bit 2 (value 4) = GRADIENT PASS: the stream is the dense block stream of
 // K^-1, the accumulators hold W = K^-1 Kx, and the chunk epilogue forms u = (c_mu . alpha_i + c_var w_in) dk_in/dr^2
 // and reduces u [1, Xs_i] over the training points; the tile epilogue writes d acq / d Xcand.
@@ -106,12 +24,13 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     const int D = gpp->D;
     double* ring = smem;                                             // [NW][S][RBW][64]
     double* kx = ring + (size_t)NW * C::RING_DOUBLES_PER_WARP;       // [2][GROUP_SLOTS]
-    double* red = kx + 2 * C::GROUP_SLOTS;                           // [NW][T][1+RMAX]
-    double* xc = red + (size_t)NW * T * (1 + RMAX);                  // [D][T]
+    double* xc = kx + 2 * C::GROUP_SLOTS;                            // [D][T]
     double* x2 = xc + (size_t)D * T;                                 // [T]
     double* tot = x2 + T;                                            // [T][1+RMAX] running colsum(A^2), A^T V
-    double* sbest = tot + T * (1 + RMAX);                            // [2] best value, best index (as bits)
-    double* tab32 = sbest + 2;                                       // [32] 2^(i/32)
+    constexpr int EW = (T + 31) / 32;                                // epilogue warps (32 candidates each)
+    double* sbest = tot + T * (1 + RMAX);                            // [EW][2] best value, best index (as bits)
+    double* tab32 = sbest + 2 * EW;                                  // [32] 2^(i/32)
+    static_assert(C::RING_DOUBLES_PER_WARP >= T * (1 + RMAX), "the per-warp reduction slice lives in the drained ring");
     constexpr bool GRADM = (ABL & 4) != 0;
     double* gcm = tab32 + 32;                                        // [T][RMAX]  (d acq/d mean_ro) / out_scale_ro
     double* gcv = gcm + T * RMAX;                                    // [T]        -2 sum_ro (d acq/d var_ro) / out_scale_ro^2
@@ -135,7 +54,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     const int gen_jl = lane & 3;
     const bool gen_first = ((w >> 2) & 1) == 0;          // warps w, w+4, w+8, w+12 share a scheduler: 2 + 2
 
-    if (tid == 0) { sbest[0] = 0.0; reinterpret_cast<long long*>(sbest)[1] = -1; }
+    if (tid < EW) { sbest[2 * tid] = 0.0; reinterpret_cast<long long*>(sbest)[2 * tid + 1] = -1; }
     if (tid < 32) tab32[tid] = exp2(tid * (1.0 / 32.0));
 
     const int64_t ntiles = (io.N + T - 1) / T;
@@ -176,7 +95,13 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
         }
         __syncthreads();
 
-        for (int p = 0; p < geom.nchunks; ++p) {
+        // With a K(X*,X) scratch the LAST chunk (which needs every column) goes first: it generates each group once and
+        // parks it in the per-CTA scratch; the other chunks re-read their groups instead of re-generating them.  Every
+        // thread re-reads exactly the slots it wrote itself, so no synchronisation is attached to the scratch.
+        constexpr bool SCR = (ABL & 8) != 0;             // compile-time: the plain variants carry no scratch code
+        double* const scratch = SCR ? io.kx_scratch + (size_t)blockIdx.x * io.kx_scratch_stride : nullptr;
+        for (int pi = 0; pi < geom.nchunks; ++pi) {
+            const int p = SCR ? geom.nchunks - 1 - pi : pi;
             const int nr = pg_chunk_rows(geom, p);
             const int row0 = p * geom.rbc;                // first row block of this chunk
             const int kp_end = GRADM ? geom.nrb : row0 + nr;
@@ -213,6 +138,15 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             };
 
             auto gen_group = [&](int g, double* __restrict__ dst) {
+                if (SCR && pi > 0) {                  // re-read this thread's own slots (LDG + STS measured faster than cp.async 8 B)
+                    const double* __restrict__ src = scratch + (size_t)g * C::GROUP_SLOTS;
+                    double v[C::GEN_ITERS];
+#pragma unroll
+                    for (int q = 0; q < C::GEN_ITERS; ++q) v[q] = __ldcg(src + (((w + NW * q) / NB) * NB + gen_nb) * 32 + lane);
+#pragma unroll
+                    for (int q = 0; q < C::GEN_ITERS; ++q) dst[(((w + NW * q) / NB) * NB + gen_nb) * 32 + lane] = v[q];
+                    return;
+                }
                 double dot[C::GEN_ITERS];
                 int jj[C::GEN_ITERS];
 #pragma unroll
@@ -239,7 +173,9 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                         const double r2 = (-2.0 * dot[q] + __ldg(xn + jj[q])) + x2[gen_n];    // square_dist, expanded form
                         val = kx_branchless<KIND>(variance, r2, tab32);
                     }
-                    dst[(ksl * NB + gen_nb) * 32 + lane] = j < M ? val : 0.0;
+                    const double out = j < M ? val : 0.0;
+                    dst[(ksl * NB + gen_nb) * 32 + lane] = out;
+                    if (SCR) __stcg(scratch + (size_t)g * C::GROUP_SLOTS + (ksl * NB + gen_nb) * 32 + lane, out);
                 }
             };
 
@@ -341,7 +277,10 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 __syncthreads();
                 continue;
             }
-            // ---- chunk reduction (fixed order -> deterministic)
+            // ---- chunk reduction (fixed order -> deterministic).  Warp w's slice red[w][T][1+RMAX] lives at the start of its
+            // own, now drained, ring region; the next chunk's copies are issued only after the barriers below.
+            double* const red = ring;
+            constexpr int RS = C::RING_DOUBLES_PER_WARP;             // warp stride of the aliased slices
             {
                 double ss[NB][2];
 #pragma unroll
@@ -361,7 +300,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                         v += __shfl_xor_sync(0xffffffffu, v, 4);
                         v += __shfl_xor_sync(0xffffffffu, v, 8);
                         v += __shfl_xor_sync(0xffffffffu, v, 16);
-                        if (lane < 4) red[(w * T + nb * 8 + 2 * lane + c) * (1 + RMAX)] = v;
+                        if (lane < 4) red[w * RS + (nb * 8 + 2 * lane + c) * (1 + RMAX)] = v;
                     }
                 for (int ro = 0; ro < R; ++ro) {
                     double mv[NB][2];
@@ -386,7 +325,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                             v += __shfl_xor_sync(0xffffffffu, v, 4);
                             v += __shfl_xor_sync(0xffffffffu, v, 8);
                             v += __shfl_xor_sync(0xffffffffu, v, 16);
-                            if (lane < 4) red[(w * T + nb * 8 + 2 * lane + c) * (1 + RMAX) + 1 + ro] = v;
+                            if (lane < 4) red[w * RS + (nb * 8 + 2 * lane + c) * (1 + RMAX) + 1 + ro] = v;
                         }
                 }
             }
@@ -395,7 +334,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 const int n = tid / (1 + RMAX), k = tid - n * (1 + RMAX);
                 if (k <= R) {
                     double a = tot[tid];
-                    for (int ww = 0; ww < NW; ++ww) a += red[(ww * T + n) * (1 + RMAX) + k];
+                    for (int ww = 0; ww < NW; ++ww) a += red[ww * RS + n * (1 + RMAX) + k];
                     tot[tid] = a;
                 }
             }
@@ -414,29 +353,36 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             }
             continue;
         }
-        if (w == 0) {
+        if (w < EW) {                                     // epilogue warp w owns candidates 32w .. 32w+31 of the tile
+            constexpr int TE = T < 32 ? T : 32;
             double tot_mv[RMAX];
-            const int ln = lane < T ? lane : 0;
+            const int ln = 32 * w + (lane < TE ? lane : 0);
 #pragma unroll
             for (int ro = 0; ro < RMAX; ++ro) tot_mv[ro] = tot[ln * (1 + RMAX) + 1 + ro];
-            double best_v = sbest[0];
-            long long best_i = reinterpret_cast<long long*>(sbest)[1];
-            gpfo_tile_epilogue<T>(gp, prog, io, n0, lane, tot[ln * (1 + RMAX)], tot_mv, best_v, best_i);
-            if (lane == 0) { sbest[0] = best_v; reinterpret_cast<long long*>(sbest)[1] = best_i; }
+            double best_v = sbest[2 * w];
+            long long best_i = reinterpret_cast<long long*>(sbest)[2 * w + 1];
+            gpfo_tile_epilogue<TE>(gp, prog, io, n0 + 32 * w, lane, tot[ln * (1 + RMAX)], tot_mv, best_v, best_i);
+            if (lane == 0) { sbest[2 * w] = best_v; reinterpret_cast<long long*>(sbest)[2 * w + 1] = best_i; }
         }
     }
     __syncthreads();
     if (tid == 0 && io.run_program) {
-        io.part_val[blockIdx.x] = sbest[0];
-        io.part_idx[blockIdx.x] = reinterpret_cast<long long*>(sbest)[1];
+        double bv = sbest[0];
+        long long bi = reinterpret_cast<long long*>(sbest)[1];
+        for (int k = 1; k < EW; ++k)
+            if (gpfo_better(sbest[2 * k], reinterpret_cast<long long*>(sbest)[2 * k + 1], bv, bi)) {
+                bv = sbest[2 * k]; bi = reinterpret_cast<long long*>(sbest)[2 * k + 1];
+            }
+        io.part_val[blockIdx.x] = bv;
+        io.part_idx[blockIdx.x] = bi;
     }
 }
 
 template <int NW, int RBW, int NB, int S, int KIND, int ABL>
 static cudaError_t launch2_kind(cudaStream_t st, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io, int grid, int D) {
     using C = Contract2Cfg<NW, RBW, NB, S>;
-    const size_t smem = ((size_t)NW * C::RING_DOUBLES_PER_WARP + 2 * C::GROUP_SLOTS + (size_t)NW * C::T * (1 + RMAX) +
-                         (size_t)D * C::T + C::T + C::T * (1 + RMAX) + 2 + 32 +
+    const size_t smem = ((size_t)NW * C::RING_DOUBLES_PER_WARP + 2 * C::GROUP_SLOTS +
+                         (size_t)D * C::T + C::T + C::T * (1 + RMAX) + 2 * ((C::T + 31) / 32) + 32 +
                          ((ABL & 4) ? C::T * RMAX + C::T + C::T * (1 + (size_t)D) : 0)) * sizeof(double);
     auto kern = contract2_kernel<NW, RBW, NB, S, KIND, ABL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -466,6 +412,12 @@ cudaError_t gpfo_contract2_launch(cudaStream_t st, int variant, int kind, const 
         case 7: return launch2<16, 8, 2, 3>(st, kind, d_gp, d_prog, io, grid, D);
         case 8: return launch2<16, 8, 2, 2>(st, kind, d_gp, d_prog, io, grid, D);
         case 9: return launch2<16, 4, 4, 5>(st, kind, d_gp, d_prog, io, grid, D);
+        case 11: return launch2<16, 4, 4, 4, 8>(st, kind, d_gp, d_prog, io, grid, D);
+        case 12: return launch2<16, 2, 8, 4, 8>(st, kind, d_gp, d_prog, io, grid, D);
+        case 13: return launch2<16, 2, 8, 4>(st, kind, d_gp, d_prog, io, grid, D);
+        case 121: return launch2<16, 2, 8, 4, 9>(st, kind, d_gp, d_prog, io, grid, D);
+        case 122: return launch2<16, 2, 8, 4, 10>(st, kind, d_gp, d_prog, io, grid, D);
+        case 123: return launch2<16, 2, 8, 4, 11>(st, kind, d_gp, d_prog, io, grid, D);
         case 6: return launch2<16, 4, 1, 4>(st, kind, d_gp, d_prog, io, grid, D);
         case 41: return launch2<16, 4, 4, 4, 1>(st, kind, d_gp, d_prog, io, grid, D);
         case 42: return launch2<16, 4, 4, 4, 2>(st, kind, d_gp, d_prog, io, grid, D);

@@ -77,3 +77,90 @@ __device__ __forceinline__ void gpfo_tile_epilogue(const GpDev& gp, const Progra
         if (gpfo_better(val, idx, best_v, best_i)) { best_v = val; best_i = idx; }
     }
 }
+
+// ---- helpers shared by the cp.async kernels (contract2.cu, contract3.cu) ----------------------------------------
+template <int NW, int RBW, int NB, int S>
+struct Contract2Cfg {
+    static constexpr int THREADS = 32 * NW;
+    static constexpr int RBC = NW * RBW;
+    static constexpr int T = 8 * NB;
+    static constexpr int GROUP_SLOTS = KPC * 2 * NB * 32;
+    static constexpr int GEN_ITERS = GROUP_SLOTS / THREADS;
+    static constexpr int RING_DOUBLES_PER_WARP = S * RBW * 64;
+    static_assert(NW % NB == 0, "per-thread candidate must be fixed");
+    static_assert(GROUP_SLOTS % THREADS == 0, "gen loop must tile");
+};
+
+__device__ __forceinline__ void cp_async16(unsigned smem_dst, const void* gmem_src) {     // smem_dst: shared-window address
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(unsigned smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// The FP64 ALU and the DMMA unit share one issue pipe on B200 (profiles/r01_fp64_pipes.log: 37.0 TF/s DMMA alone,
+// 24.4 DFMA alone, 26.6 + 6.7 together), so every FP64 instruction spent on K(X*, X) is taken from the contraction.
+// The helpers below are therefore op-count-minimal and branch-free.
+
+// sqrt(x) for normal positive x: MUFU.RSQ64H seed (2^-22), one cubically convergent step on 1/sqrt (-> 2^-66),
+// then x * y.  About 1 ulp; no IEEE slow path.  6 FP64 ops.
+__device__ __forceinline__ double fast_sqrt_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y * y, 1.0);
+    y = fma(y * e, fma(e, 0.375, 0.5), y);
+    return x * y;
+}
+
+// exp(x) for x <= 0: clamp at -708 (~1e-308 instead of a denormal / 0); k = round(32 x / ln 2), x = k ln2/32 + r
+// with |r| <= ln2/64; exp(x) = 2^(k>>5) * 2^((k&31)/32) * P6(r), P6 = degree-6 Taylor (truncation 3.5e-18 relative);
+// the 32-entry table of 2^(i/32) lives in shared memory.  12 FP64 ops.
+__device__ __forceinline__ double fast_exp_neg(double x, const double* __restrict__ tab32) {
+    x = fmax(x, -708.0);
+    const double magic = 6755399441055744.0;                 // 1.5 * 2^52
+    const double t = fma(x, 46.166241308446828, magic);      // 32 / ln 2
+    const double kf = t - magic;
+    double r = fma(kf, -2.1660849392498290e-02, x);          // ln2/32 (head)
+    r = fma(kf, -7.2470213052434896e-19, r);                 // ln2/32 (tail)
+    double p = 1.3888888888888889e-03;                       // 1/6!
+    p = fma(p, r, 8.3333333333333332e-03);
+    p = fma(p, r, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int k = __double2loint(t);                         // low word of t holds k (two's complement)
+    p *= tab32[k & 31];
+    return __hiloint2double(__double2hiint(p) + ((k >> 5) << 20), __double2loint(p));
+}
+
+template <int KIND>
+__device__ __forceinline__ double kx_branchless(double variance, double r2, const double* __restrict__ tab32) {
+    if (KIND == GPFO_KERN_RBF) return variance * fast_exp_neg(-0.5 * fmax(r2, 0.0), tab32);
+    const double x = r2 + 1e-12;                             // euclid_dist: sqrt(r2 + 1e-12); square(r) == x to 1 ulp
+    const double r = fast_sqrt_pos(x);
+    if (KIND == GPFO_KERN_MATERN52) {
+        const double s5 = 2.2360679774997898;
+        return (variance * fma(5.0 / 3.0, x, fma(s5, r, 1.0))) * fast_exp_neg(-s5 * r, tab32);
+    }
+    const double s3 = 1.7320508075688772;
+    return (variance * fma(s3, r, 1.0)) * fast_exp_neg(-s3 * r, tab32);
+}
+
+// d k / d r^2 for the gradient pass: RBF -k/2; Matern52 -(5/6) s2 (1 + sqrt5 r) e^{-sqrt5 r};
+// Matern32 -(3/2) s2 e^{-sqrt3 r}, with r = sqrt(r^2 + 1e-12) as in euclid_dist.
+template <int KIND>
+__device__ __forceinline__ double dk_dr2_branchless(double variance, double r2, const double* __restrict__ tab32) {
+    if (KIND == GPFO_KERN_RBF) return (-0.5 * variance) * fast_exp_neg(-0.5 * fmax(r2, 0.0), tab32);
+    const double r = fast_sqrt_pos(r2 + 1e-12);
+    if (KIND == GPFO_KERN_MATERN52) {
+        const double s5 = 2.2360679774997898;
+        return ((-5.0 / 6.0) * variance * fma(s5, r, 1.0)) * fast_exp_neg(-s5 * r, tab32);
+    }
+    const double s3 = 1.7320508075688772;
+    return (-1.5 * variance) * fast_exp_neg(-s3 * r, tab32);
+}
+

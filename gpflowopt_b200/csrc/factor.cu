@@ -387,3 +387,48 @@ void gpfo_kinv_alpha(cudaStream_t st, const double* dLinv, int Mf, const double*
     ata_kernel<<<dim3(nb, nb), 256, 0, st>>>(dLinv, Mf, dKinv);
     linvT_times_v_kernel<<<(Mf + 3) / 4, 128, 0, st>>>(dLinv, Mf, dV, R, dalpha);
 }
+
+// ---- cluster layout (see ClusterGeom) -----------------------------------------------------------------------------
+void gpfo_cluster_geom(int nrb, int rbc, ClusterGeom* g, long long total[2]) {
+    g->nrb = nrb;
+    g->rbc = rbc;
+    g->nchunks = (nrb + 2 * rbc - 1) / (2 * rbc);
+    for (int c = 0; c < 2; ++c) {
+        long long off = 0;
+        for (int p = 0; p < g->nchunks; ++p) {
+            g->base[c][p] = off;
+            const int nr = cg_rows(*g, p, c), kd0 = p * 2 * rbc, ke = cg_kp_end(*g, p);
+            for (int kp = 0; kp < ke; ++kp) off += nr - cg_lo(kp - kd0, c);
+        }
+        total[c] = off;
+    }
+}
+
+__global__ void pack_linv_cluster_kernel(const double* __restrict__ Linv, int ld, ClusterGeom g, int p, int c, int nr,
+                                         double* __restrict__ packed) {
+    const int kd0 = p * 2 * g.rbc;
+    const int kp = blockIdx.x / nr, q = blockIdx.x % nr;
+    const int lo = cg_lo(kp - kd0, c);
+    if (q < lo) return;
+    long long off = g.base[c][p];
+    if (kp <= kd0) off += (long long)kp * nr;
+    else {
+        off += (long long)kd0 * nr;
+        for (int k = kd0; k < kp; ++k) off += nr - cg_lo(k - kd0, c);
+    }
+    const int e = threadIdx.x, lane = e >> 1, h = e & 1;
+    const int row = 8 * (kd0 + 2 * q + c) + (lane >> 2);
+    const int col = 8 * kp + 4 * h + (lane & 3);
+    packed[(off + (q - lo)) * 64 + e] = Linv[(size_t)row * ld + col];
+}
+
+void gpfo_pack_linv_cluster(cudaStream_t st, const double* dLinv, int ld, const ClusterGeom& g, double* dpacked0,
+                            double* dpacked1) {
+    for (int c = 0; c < 2; ++c)
+        for (int p = 0; p < g.nchunks; ++p) {
+            const int nr = cg_rows(g, p, c);
+            if (nr == 0) continue;
+            const long long pairs = (long long)cg_kp_end(g, p) * nr;
+            pack_linv_cluster_kernel<<<(unsigned)pairs, 64, 0, st>>>(dLinv, ld, g, p, c, nr, c ? dpacked1 : dpacked0);
+        }
+}

@@ -54,6 +54,35 @@ GPFO_HD int64_t pg_total_blocks(const PackGeom& g) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Cluster layout (contract3.cu): a pair of CTAs (one thread-block cluster) shares one candidate tile.  Rows are cut
+// into cluster chunks of 2*rbc row blocks; CTA rank c owns the row blocks of parity c (local block q <-> global block
+// 2*rbc*p + 2q + c), so both CTAs walk the same column blocks in lock step and the triangular work is balanced.
+// Each rank has its own block stream, ordered [chunk][kp][q] with q >= cg_lo(kd, c) only.
+// ------------------------------------------------------------------------------------------------
+#define GPFO_MAX_CCHUNKS 64
+struct ClusterGeom {
+    int nrb;        // number of 8-row blocks
+    int rbc;        // row blocks per chunk PER CTA
+    int nchunks;
+    long long base[2][GPFO_MAX_CCHUNKS];     // first block of (rank, chunk) in that rank's stream
+};
+GPFO_HD int cg_rows(const ClusterGeom& g, int p, int c) {
+    const int first = p * 2 * g.rbc + c;
+    if (first >= g.nrb) return 0;
+    const int cnt = (g.nrb - first + 1) / 2;
+    return cnt < g.rbc ? cnt : g.rbc;
+}
+GPFO_HD int cg_kp_end(const ClusterGeom& g, int p) {
+    const int e = (p + 1) * 2 * g.rbc;
+    return e < g.nrb ? e : g.nrb;
+}
+// first stored local row block for diagonal offset kd = kp - 2*rbc*p: block (q, kp) is kept iff 2q + c >= kd
+GPFO_HD int cg_lo(int kd, int c) {
+    const int t = kd - c + 1;
+    return t > 0 ? (t >> 1) : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Device-side description of one GP and of the acquisition program
 // ------------------------------------------------------------------------------------------------
 struct GpDev {
@@ -66,6 +95,8 @@ struct GpDev {
     const double* V;            // Mp x R, L^-1 Y (rows >= M are zero)
     const double* packed;       // block stream of L^-1
     PackGeom geom;
+    const double* packed_c[2];  // cluster layout: one block stream of L^-1 per CTA rank
+    ClusterGeom cgeom;
     const double* alpha;        // Mp x R, K^-1 Y = L^-T V            (gradient pass only)
     const double* packed_kinv;  // dense block stream of K^-1         (gradient pass only)
     PackGeom geom_kinv;
@@ -97,6 +128,9 @@ struct EvalIO {
     double* cva;                // [slot][N] d acq / d var_slot
     double* grads;              // N x D  d acq / d Xcand
     int grad_accumulate;        // 0: this GP's launch overwrites grads, 1: adds to it
+    // optional K(X*,X) scratch (variant 11): [grid][groups][GROUP_SLOTS] doubles, thread-private re-reads
+    double* kx_scratch;
+    long long kx_scratch_stride;   // doubles per CTA
 };
 
 #define GPFO_STABILITY 1e-6     // gpflow settings.numerics.jitter_level (ei.py:24, poi.py:23, pof.py:23, hvpoi.py:24)
@@ -234,6 +268,14 @@ int gpfo_factor_device(cudaStream_t st, int M, int Mf, int D, int R, int kind, d
                        double* dLinv /*Mf x Mf*/, const double* dY /*Mf x R*/, double* dV /*Mf x R*/,
                        int* dflag, std::string* err);
 void gpfo_pack_linv(cudaStream_t st, const double* dLinv, int ld, PackGeom g, double* dpacked);
+void gpfo_cluster_geom(int nrb, int rbc, ClusterGeom* g, long long total[2]);
+void gpfo_pack_linv_cluster(cudaStream_t st, const double* dLinv, int ld, const ClusterGeom& g, double* dpacked0,
+                            double* dpacked1);
+// contract3.cu
+cudaError_t gpfo_contract3_launch(cudaStream_t st, int kind, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io,
+                                  int nclusters, int D);
+int gpfo_contract3_rbc();
+int gpfo_contract3_clusters(int64_t N, int num_sms);
 // Kinv = Linv^T Linv (Mf x Mf, full symmetric) and alpha = Linv^T V, for the gradient pass
 void gpfo_kinv_alpha(cudaStream_t st, const double* dLinv, int Mf, const double* dV, int R, double* dKinv, double* dalpha);
 void gpfo_prepare_inputs(cudaStream_t st, const double* dX, int M, int Mp, int D, const double* d_ell,
