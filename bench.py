@@ -31,6 +31,10 @@ sys.path.insert(0, ROOT)
 M, D = 2048, 8
 N_PER_GPU = 1000000
 METRIC = "acq candidate evals/sec (M=2048,D=8,fp64)"
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel for one launch of this workload (N = 1e6),
+# taken from profiles/r01_bench_contract2_v12.metrics.csv (44.7 GB read + 16.4 GB written: the per-CTA K(X*,X) scratch of
+# variant 12 is written back to HBM; the strictly on-chip variant 4 moves 36.5 MB per launch)
+NCU_DRAM_BYTES_PER_LAUNCH = 44687670000 + 16380813000
 UNIT = "candidates/s"
 
 
@@ -227,6 +231,18 @@ def main():
     e2e_ms = (time.perf_counter() - t0) * 1e3
     assert best_e2e == best, "host and device candidate paths disagree: %r vs %r" % (best_e2e, best)
 
+    # ---- side measurement: the strictly-on-chip variant (K(X*,X) never leaves the SM; no global scratch) ----------
+    strict_ms = 0.0
+    if not args.variant:
+        ctx.set_variant(4)
+        step_device()
+        for s in range(args.steps):
+            flush.fill_(float(s))
+            torch.cuda.synchronize()
+            step_device()
+            strict_ms += ctx.timings()["eval_ms"]
+        ctx.set_variant(0)
+
     stats = torch.tensor([dev_ms, hot_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         td.all_reduce(stats, op=td.ReduceOp.MAX)
@@ -253,13 +269,20 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak, "traffic": None,
-                         "kernel": "contract_kernel (FP64 DMMA.8x8x4 contraction + fused EI epilogue + block argmax)",
+                         "frac": achieved / fp64_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                         "traffic_note": "dram__bytes_read+write of one contract2_kernel launch at this workload from "
+                                         "profiles/ (ncu --set full); bytes, not flop: the kernel is tensor bound, HBM is not",
+                         "kernel": "contract2_kernel<16,2,8,4> (FP64 DMMA.8x8x4 contraction + fused EI epilogue + block "
+                                   "argmax; 64-candidate tiles, 256-row chunks, K(X*,X) generated once per tile)",
                          "flop_per_candidate": M * (M + 1),
                          "peak_source": "FP64 DMMA issue peak measured live on this GPU (gpfo_measure_dmma_peak); "
                                         "MEASURED_PEAKS.json holds no FP64 figure; nominal 37.2 TFLOP/s"},
             "best": {"value": best[0], "index": best[1]},
         }
+        if strict_ms > 0.0:
+            out["strict_onchip"] = {"value": n_local / (strict_ms / args.steps * 1e-3), "unit": UNIT,
+                                    "note": "rank 0, variant 4: covariance tiles strictly on chip (no global scratch), "
+                                            "the literal north_star dataflow"}
         if not args.no_cpu_baseline:
             n_cpu = 100000
             v_cpu, dt = cpu_oracle_throughput(n_cpu)

@@ -79,12 +79,13 @@ __device__ __forceinline__ void gpfo_tile_epilogue(const GpDev& gp, const Progra
 }
 
 // ---- helpers shared by the cp.async kernels (contract2.cu, contract3.cu) ----------------------------------------
-template <int NW, int RBW, int NB, int S>
+template <int NW, int RBW, int NB, int S, int KPG = KPC>
 struct Contract2Cfg {
+    static constexpr int KP = KPG;                 // column blocks per generated K(X*,X) group
     static constexpr int THREADS = 32 * NW;
     static constexpr int RBC = NW * RBW;
     static constexpr int T = 8 * NB;
-    static constexpr int GROUP_SLOTS = KPC * 2 * NB * 32;
+    static constexpr int GROUP_SLOTS = KPG * 2 * NB * 32;
     static constexpr int GEN_ITERS = GROUP_SLOTS / THREADS;
     static constexpr int RING_DOUBLES_PER_WARP = S * RBW * 64;
     static_assert(NW % NB == 0, "per-thread candidate must be fixed");

@@ -69,7 +69,7 @@ def test_multi_output_gp(ctx):
     assert_parity(var, vo, scale=g.variance, what="var")
 
 
-@pytest.mark.parametrize("variant", [4, 5, 6, 1, 2, 3])
+@pytest.mark.parametrize("variant", [12, 11, 10, 4, 5, 6, 1, 2, 3])
 @pytest.mark.parametrize("leaf,param", [("ei", None), ("poi", None), ("pof", 0.15), ("lcb", 2.0)])
 def test_leaf_acquisitions(ctx, variant, leaf, param):
     g, lo, up = _model(300, 5, "matern52", scaled=True)
@@ -217,6 +217,26 @@ def test_hvpoi_reference_fixture(ctx):
         np.testing.assert_almost_equal(vals, d['scores'], decimal=2)
     finally:
         ctx.gp_count_set(1)
+
+
+@pytest.mark.parametrize("variant", [12, 11, 10, 4])
+def test_multi_chunk_variants_agree_with_oracle(ctx, variant):
+    """M = 1100 spans several row chunks in every layout (256/512-row chunks, 1024-row cluster chunks, partial last chunk):
+    the scratch variants (11, 12), the 2-CTA cluster variant (10) and the on-chip variant (4) all meet the oracle."""
+    g, lo, up = _model(1100, 6, "matern52", scaled=True)
+    upload_oracle_gp(ctx, 0, g)
+    fmin = float(np.min(g.predict(g.input_transform.backward(g.Xs))[0]))
+    ctx.program_set([[_lib.OP_EI, 0, 0, 0]], [fmin])
+    ctx.set_variant(variant)
+    try:
+        for N in (1, 65, 3000):
+            Xc = _cands(N, 6, lo, up)
+            vals, _, bv, bi = ctx.eval(Xc)
+            ref = oacq.Leaf('ei', g, fmin).value(Xc)
+            assert_parity(vals, ref, what="variant %d N=%d" % (variant, N))
+            assert bi == int(np.argmax(ref)) or near_tie(ref, bi, int(np.argmax(ref)))
+    finally:
+        ctx.set_variant(0)
 
 
 def test_headline_shape_subset_and_properties(ctx):
