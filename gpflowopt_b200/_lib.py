@@ -17,7 +17,7 @@ MAX_GPS, MAX_SLOTS, MAX_OPS, MAX_PARAMS, MAX_DIM = 16, 16, 64, 64, 64
 EXPORTS = ["gpfo_version", "gpfo_ctx_create", "gpfo_ctx_destroy", "gpfo_last_error", "gpfo_status_string",
            "gpfo_gp_set", "gpfo_gp_count_set", "gpfo_gp_get_factor", "gpfo_program_set", "gpfo_cells_set",
            "gpfo_eval", "gpfo_predict", "gpfo_timings_get", "gpfo_set_variant", "gpfo_measure_dmma_peak",
-           "gpfo_measure_fp64_pipes"]
+           "gpfo_measure_fp64_pipes", "gpfo_pareto_cells"]
 
 
 class Timings(ctypes.Structure):
@@ -72,6 +72,8 @@ def load():
     lib.gpfo_measure_dmma_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     lib.gpfo_measure_fp64_pipes.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
                                             ctypes.POINTER(ctypes.c_double)]
+    lib.gpfo_pareto_cells.argtypes = [c_dp, c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_double, c_dp, c_dp, ctypes.c_int64,
+                                      ctypes.POINTER(ctypes.c_int64)]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is ctypes.c_int and name not in ("gpfo_version",):
@@ -89,6 +91,26 @@ def _f64(a, shape=None):
     if shape is not None:
         a = a.reshape(shape)
     return a
+
+
+def pareto_cells(front, order, threshold=0.0):
+    """Cell decomposition of the non-dominated region (native host code, no GPU needed).  Returns (lb, ub) int32 C x R."""
+    lib = load()
+    front = _f64(front)
+    P, R = front.shape
+    order = np.ascontiguousarray(order, dtype=np.int32)
+    cap = max(64, 4 * P * P)
+    while True:
+        lb = np.empty((cap, R), dtype=np.int32)
+        ub = np.empty((cap, R), dtype=np.int32)
+        n = ctypes.c_int64(0)
+        st = lib.gpfo_pareto_cells(_ptr(front), _ptr(order), P, R, float(threshold), _ptr(lb), _ptr(ub), cap, ctypes.byref(n))
+        if st == OK:
+            return lb[:n.value].copy(), ub[:n.value].copy()
+        if n.value > cap:
+            cap = int(n.value)
+            continue
+        raise GpfoError(st, "gpfo_pareto_cells failed")
 
 
 class Context(object):

@@ -11,21 +11,29 @@
 #define HV_THREADS 256
 #define HV_RMAX 8          // objectives
 
+// Shared-memory tables are laid out [pf_ext row][objective][candidate] with HV_TC = 8 candidates innermost and every row
+// padded by 16 bytes (HV_ROW(R) doubles): a thread fetches the 8 candidates of one (row, objective) entry with four
+// 16-byte loads, and rows that differ by 1..7 fall into disjoint bank groups (row stride = odd multiple of 16 B mod 128),
+// so the per-cell gathers of a quarter warp are conflict free.  (First version: [candidate][row][objective] with scalar
+// gathers -> 143 ms for config #4; see profiles/r01_sweep_configs2-5.log.)
+#define HV_ROW(R) ((R) * HV_TC + 2)
+
 // GRAD: also d(Hv PoI)/d mean_j and /d var_j per candidate (closed form of SURVEY Appendix A item 10), fed through the
 // forward-mode program evaluation; writes the per-slot coefficients the contraction kernel's gradient mode consumes.
 template <int R, bool GRAD>
 __global__ void __launch_bounds__(HV_THREADS)
 hvpoi_kernel(const ProgramDev* __restrict__ prog, CellsDev cells, EvalIO io, int slot_first) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     const int n_ext = cells.n_ext;
+    constexpr int ROW = HV_ROW(R);
     constexpr int NQ = GRAD ? 2 + 3 * R : 2;           // per-candidate sums: PoI, Hv [, dPoI/dmu_j, dPoI/dsd_j, dHv/dmu_j]
-    double* pf = sm;                                   // [n_ext][R]
-    double* phi = pf + (size_t)n_ext * R;              // [HV_TC][n_ext][R]
-    double* cmu = phi + (size_t)HV_TC * n_ext * R;     // [HV_TC][R]
-    double* csd = cmu + HV_TC * R;                     // [HV_TC][R]
+    double* phi = sm;                                  // [n_ext][ROW]   Phi(z)
+    double* pdf = phi + (size_t)n_ext * ROW;           // GRAD: [n_ext][ROW] phi(z)
+    double* zpdf = pdf + (GRAD ? (size_t)n_ext * ROW : 0);           // GRAD: [n_ext][ROW] z phi(z)
+    double* pf = zpdf + (GRAD ? (size_t)n_ext * ROW : 0);            // [n_ext][R]
+    double* cmu = pf + (((size_t)n_ext * R + 1) & ~(size_t)1);    // [R][HV_TC]  (kept 16-byte aligned)
+    double* csd = cmu + HV_TC * R;                     // [R][HV_TC]
     double* red = csd + HV_TC * R;                     // [HV_THREADS/32][HV_TC][NQ]
-    double* pdf = red + (HV_THREADS / 32) * HV_TC * NQ;            // GRAD: [HV_TC][n_ext][R] phi(z)
-    double* zpdf = pdf + (GRAD ? (size_t)HV_TC * n_ext * R : 0);   // GRAD: [HV_TC][n_ext][R] z phi(z)
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
     for (int e = tid; e < n_ext * R; e += HV_THREADS) pf[e] = cells.pf_ext[e];
@@ -37,7 +45,7 @@ hvpoi_kernel(const ProgramDev* __restrict__ prog, CellsDev cells, EvalIO io, int
         const int64_t n0 = tile * HV_TC;
         __syncthreads();
         if (tid < HV_TC * R) {
-            const int t = tid / R, j = tid % R;
+            const int j = tid / HV_TC, t = tid % HV_TC;
             const int64_t n = n0 + t;
             double m = 0.0, v = 1.0;
             if (n < io.N) {
@@ -49,16 +57,16 @@ hvpoi_kernel(const ProgramDev* __restrict__ prog, CellsDev cells, EvalIO io, int
             csd[tid] = sqrt(v);
         }
         __syncthreads();
-        // Phi[t][i][j] = Normal(mu_tj, sd_tj).cdf(pf_ext[i][j])                           (hvpoi.py:112-113)
-        for (int e = tid; e < HV_TC * n_ext * R; e += HV_THREADS) {
-            const int t = e / (n_ext * R), ij = e % (n_ext * R), j = ij % R;
-            const double z = (pf[ij] - cmu[t * R + j]) / csd[t * R + j];
-            phi[e] = gpfo_ndtr(z);
+        // Phi[i][j][t] = Normal(mu_tj, sd_tj).cdf(pf_ext[i][j])                           (hvpoi.py:112-113)
+        for (int e = tid; e < n_ext * R * HV_TC; e += HV_THREADS) {
+            const int i = e / (R * HV_TC), jt = e % (R * HV_TC), j = jt / HV_TC;
+            const double z = (pf[i * R + j] - cmu[jt]) / csd[jt];
+            phi[i * ROW + jt] = gpfo_ndtr(z);
             if (GRAD) {                                // terms with infinite z vanish
                 const bool fin = isfinite(z);
                 const double pz = fin ? gpfo_std_pdf(z) : 0.0;
-                pdf[e] = pz;
-                zpdf[e] = fin ? z * pz : 0.0;
+                pdf[i * ROW + jt] = pz;
+                zpdf[i * ROW + jt] = fin ? z * pz : 0.0;
             }
         }
         __syncthreads();
@@ -72,41 +80,64 @@ hvpoi_kernel(const ProgramDev* __restrict__ prog, CellsDev cells, EvalIO io, int
             double ubp[R], lbp[R];
 #pragma unroll
             for (int j = 0; j < R; ++j) {
-                ub[j] = cells.ub[c * R + j] * R + j;
-                lb[j] = cells.lb[c * R + j] * R + j;
-                ubp[j] = pf[ub[j]];
-                lbp[j] = pf[lb[j]];
+                const int iu = cells.ub[c * R + j], il = cells.lb[c * R + j];
+                ubp[j] = pf[iu * R + j];
+                lbp[j] = pf[il * R + j];
+                ub[j] = iu * ROW + j * HV_TC;
+                lb[j] = il * ROW + j * HV_TC;
             }
+            if (!GRAD) {
+                double pr[HV_TC], ext[HV_TC];
+                bool valid[HV_TC];
 #pragma unroll
-            for (int t = 0; t < HV_TC; ++t) {
-                const double* ph = phi + (size_t)t * n_ext * R;
-                double pr = 1.0, ext = 1.0;
-                bool valid = true;
-                double dP[R], ex[R];
+                for (int t = 0; t < HV_TC; ++t) { pr[t] = 1.0; ext[t] = 1.0; valid[t] = true; }
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
-                    dP[j] = ph[ub[j]] - ph[lb[j]];
-                    pr *= dP[j];                                                           // hvpoi.py:116-120
-                    const double m = cmu[t * R + j];
-                    valid = valid && (ubp[j] > m);                                         // hvpoi.py:130-131
-                    ex[j] = ubp[j] - fmax(lbp[j], m);
-                    ext *= ex[j];                                                          // hvpoi.py:133-136
+#pragma unroll
+                    for (int t2 = 0; t2 < HV_TC / 2; ++t2) {
+                        const double2 pu = *reinterpret_cast<const double2*>(phi + ub[j] + 2 * t2);
+                        const double2 pl = *reinterpret_cast<const double2*>(phi + lb[j] + 2 * t2);
+                        const double2 m2 = *reinterpret_cast<const double2*>(cmu + j * HV_TC + 2 * t2);
+                        pr[2 * t2] *= (pu.x - pl.x);                                        // hvpoi.py:116-120
+                        pr[2 * t2 + 1] *= (pu.y - pl.y);
+                        valid[2 * t2] = valid[2 * t2] && (ubp[j] > m2.x);                   // hvpoi.py:130-131
+                        valid[2 * t2 + 1] = valid[2 * t2 + 1] && (ubp[j] > m2.y);
+                        ext[2 * t2] *= (ubp[j] - fmax(lbp[j], m2.x));                       // hvpoi.py:133-136
+                        ext[2 * t2 + 1] *= (ubp[j] - fmax(lbp[j], m2.y));
+                    }
                 }
-                q[t][0] += pr;
-                q[t][1] += valid ? ext : 0.0;
-                if (GRAD) {
-                    const double* pd = pdf + (size_t)t * n_ext * R;
-                    const double* zp = zpdf + (size_t)t * n_ext * R;
+#pragma unroll
+                for (int t = 0; t < HV_TC; ++t) {
+                    q[t][0] += pr[t];
+                    q[t][1] += valid[t] ? ext[t] : 0.0;
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < HV_TC; ++t) {
+                    double pr = 1.0, ext = 1.0;
+                    bool valid = true;
+                    double dP[R], ex[R];
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        dP[j] = phi[ub[j] + t] - phi[lb[j] + t];
+                        pr *= dP[j];
+                        const double m = cmu[j * HV_TC + t];
+                        valid = valid && (ubp[j] > m);
+                        ex[j] = ubp[j] - fmax(lbp[j], m);
+                        ext *= ex[j];
+                    }
+                    q[t][0] += pr;
+                    q[t][1] += valid ? ext : 0.0;
 #pragma unroll
                     for (int j = 0; j < R; ++j) {
                         double oP = 1.0, oE = 1.0;                                         // exclusive products
 #pragma unroll
                         for (int k = 0; k < R; ++k) if (k != j) { oP *= dP[k]; oE *= ex[k]; }
-                        const double isd = 1.0 / csd[t * R + j];
-                        q[t][2 + j] += oP * (-(pd[ub[j]] - pd[lb[j]]) * isd);              // d PoI / d mu_j
-                        q[t][2 + R + j] += oP * (-(zp[ub[j]] - zp[lb[j]]) * isd);          // d PoI / d sd_j
+                        const double isd = 1.0 / csd[j * HV_TC + t];
+                        q[t][2 + j] += oP * (-(pdf[ub[j] + t] - pdf[lb[j] + t]) * isd);    // d PoI / d mu_j
+                        q[t][2 + R + j] += oP * (-(zpdf[ub[j] + t] - zpdf[lb[j] + t]) * isd);   // d PoI / d sd_j
                         // tf.maximum(lb, mu): the gradient reaches mu only where lb < mu; the indicator carries none
-                        q[t][2 + 2 * R + j] += (valid && lbp[j] < cmu[t * R + j]) ? -oE : 0.0;   // d Hv / d mu_j
+                        q[t][2 + 2 * R + j] += (valid && lbp[j] < cmu[j * HV_TC + t]) ? -oE : 0.0;   // d Hv / d mu_j
                     }
                 }
             }
@@ -146,7 +177,7 @@ hvpoi_kernel(const ProgramDev* __restrict__ prog, CellsDev cells, EvalIO io, int
                     for (int j = 0; j < R; ++j) {
                         hdm[j] = tq[0] * tq[2 + 2 * R + j] + tq[1] * tq[2 + j];           // PoI dHv + Hv dPoI
                         const double v0 = va[slot_first + j];
-                        const double ds_dv = (v0 >= GPFO_STABILITY) ? 1.0 / (2.0 * csd[lane * R + j]) : 0.0;
+                        const double ds_dv = (v0 >= GPFO_STABILITY) ? 1.0 / (2.0 * csd[j * HV_TC + lane]) : 0.0;
                         hdv[j] = tq[1] * tq[2 + R + j] * ds_dv;
                     }
                     val = gpfo_run_program<false>(*prog, mu, va, leaf, nullptr, nullptr, nullptr, nullptr);   // same code as evaluate
@@ -177,7 +208,8 @@ hvpoi_kernel(const ProgramDev* __restrict__ prog, CellsDev cells, EvalIO io, int
 
 static size_t hv_smem(int n_ext, int R, bool grad) {
     const int nq = grad ? 2 + 3 * R : 2;
-    return ((size_t)n_ext * R * (1 + HV_TC * (grad ? 3 : 1)) + 2 * HV_TC * R + (HV_THREADS / 32) * HV_TC * nq) * sizeof(double);
+    return ((size_t)n_ext * HV_ROW(R) * (grad ? 3 : 1) + (((size_t)n_ext * R + 1) & ~(size_t)1) + 2 * HV_TC * R +
+            (HV_THREADS / 32) * HV_TC * nq) * sizeof(double);
 }
 
 template <int R, bool GRAD>

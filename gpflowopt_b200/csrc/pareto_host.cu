@@ -1,0 +1,95 @@
+// Host-side native code of the path's setup: the cell decomposition of the non-dominated region that feeds the HVPoI
+// kernel (gpflowopt/pareto.py:173-236, Pareto.divide_conquer_nd; pure-Python stack loop in the reference: ~5 s for a
+// 200-point 3-objective front, i.e. 20x the time the GPU needs to score 1e6 candidates against the result).
+// Same algorithm, same visiting order (LIFO stack, split of the widest edge, upper half pushed last), same acceptance /
+// rejection tests with stability = 1e-6, so the int32 tables are identical to the reference's row for row.
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "gpfo_internal.cuh"
+
+extern "C" int gpfo_pareto_cells(const double* front, const int32_t* order, int P, int R, double threshold, int32_t* lb,
+                                 int32_t* ub, int64_t capacity, int64_t* count) {
+    if (!front || !order || !count || P < 1 || R < 2 || R > 16 || capacity < 0) return GPFO_ERR_BAD_SHAPE;
+    const double stability = 1e-6;
+    // extended front: row 0 = min - 1 (ideal), rows 1..P = front, row P+1 = max + 1 (anti-ideal)
+    std::vector<double> ext((size_t)(P + 2) * R);
+    std::vector<int32_t> rows((size_t)(P + 2) * R);          // rows[k][j]: row of ext holding the k-th smallest value of column j
+    double total = 1.0;
+    for (int j = 0; j < R; ++j) {
+        double lo = front[j], hi = front[j];
+        for (int p = 1; p < P; ++p) { lo = std::fmin(lo, front[(size_t)p * R + j]); hi = std::fmax(hi, front[(size_t)p * R + j]); }
+        ext[j] = lo - 1.0;
+        ext[(size_t)(P + 1) * R + j] = hi + 1.0;
+        rows[j] = 0;
+        rows[(size_t)(P + 1) * R + j] = P + 1;
+        for (int p = 0; p < P; ++p) {
+            ext[(size_t)(p + 1) * R + j] = front[(size_t)p * R + j];
+            rows[(size_t)(p + 1) * R + j] = order[(size_t)p * R + j] + 1;
+        }
+    }
+    for (int j = 0; j < R; ++j) total *= ext[(size_t)(P + 1) * R + j] - ext[j];
+
+    // "the test point augments or dominates the front": smaller than every front member in at least one objective
+    auto outside = [&](const double* corner) {
+        for (int p = 0; p < P; ++p) {
+            bool any = false;
+            for (int j = 0; j < R && !any; ++j) any = corner[j] < front[(size_t)p * R + j];
+            if (!any) return false;
+        }
+        return true;
+    };
+
+    struct Cell { int32_t a[16], b[16]; };
+    std::vector<Cell> stack;
+    Cell first;
+    for (int j = 0; j < R; ++j) { first.a[j] = 0; first.b[j] = P + 1; }
+    stack.push_back(first);
+    std::vector<int32_t> out_lb, out_ub;
+    double lbv[16], ubv[16], corner[16];
+    int32_t lbr[16], ubr[16];
+    while (!stack.empty()) {
+        const Cell cell = stack.back();
+        stack.pop_back();
+        for (int j = 0; j < R; ++j) {
+            lbr[j] = rows[(size_t)cell.a[j] * R + j];
+            ubr[j] = rows[(size_t)cell.b[j] * R + j];
+            lbv[j] = ext[(size_t)lbr[j] * R + j];
+            ubv[j] = ext[(size_t)ubr[j] * R + j];
+        }
+        for (int j = 0; j < R; ++j) corner[j] = ubv[j] - stability;
+        if (outside(corner)) {                                   // valid integration cell: keep
+            out_lb.insert(out_lb.end(), lbr, lbr + R);
+            out_ub.insert(out_ub.end(), ubr, ubr + R);
+            continue;
+        }
+        for (int j = 0; j < R; ++j) corner[j] = lbv[j] + stability;
+        if (!outside(corner)) continue;                          // lower corner dominated: discard
+        int32_t width = 0, k = 0;
+        bool any_wide = false;
+        for (int j = 0; j < R; ++j) {
+            const int32_t d = cell.b[j] - cell.a[j];
+            if (d > 1) any_wide = true;
+            if (d > width) { width = d; k = j; }                 // np.argmax: first maximum
+        }
+        double vol = 1.0;
+        for (int j = 0; j < R; ++j) vol *= ubv[j] - lbv[j];
+        if (any_wide && (vol / total) > threshold) {
+            const int32_t half = (int32_t)std::nearbyint(width / 2.0);   // np.round: half to even
+            Cell lower = cell, upper = cell;
+            lower.b[k] -= half;
+            upper.a[k] += width - half;
+            stack.push_back(lower);
+            stack.push_back(upper);
+        }
+    }
+    const int64_t C = (int64_t)(out_lb.size() / R);
+    *count = C;
+    if (C > capacity) return GPFO_ERR_BAD_SHAPE;                 // caller retries with a larger buffer
+    if (C > 0 && (!lb || !ub)) return GPFO_ERR_BAD_SHAPE;
+    if (C > 0) {
+        std::memcpy(lb, out_lb.data(), out_lb.size() * sizeof(int32_t));
+        std::memcpy(ub, out_ub.data(), out_ub.size() * sizeof(int32_t));
+    }
+    return GPFO_OK;
+}

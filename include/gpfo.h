@@ -147,6 +147,15 @@ int gpfo_set_variant(gpfo_ctx* ctx, int variant);
 /* Measures this device's FP64 DMMA issue peak with a register-only mma.sync m8n8k4 loop; TFLOP/s. */
 int gpfo_measure_dmma_peak(gpfo_ctx* ctx, double* tflops);
 
+/* Host-side setup of HVPoI: cell decomposition of the non-dominated region for R >= 2 objectives.
+ * Replaces: Pareto.divide_conquer_nd (pareto.py:173-236), a pure-Python stack loop in the reference.
+ *   front   P x R, the Pareto set sorted ascending on objective 0 (pareto.py:131-144)
+ *   order   P x R int32, np.argsort(front, axis=0) (ranks are taken from the caller so that ties break as in NumPy)
+ *   lb, ub  caller buffers of `capacity` x R int32 (row indices into pf_ext); *count receives the number of cells.
+ * Returns GPFO_ERR_BAD_SHAPE with *count set when capacity is too small (call again with a larger buffer). */
+int gpfo_pareto_cells(const double* front, const int32_t* order, int P, int R, double threshold, int32_t* lb,
+                      int32_t* ub, int64_t capacity, int64_t* count);
+
 /* FP64 pipe microbenchmarks (register-only loops, 16 warps/SM): mode 0 = DMMA only, 1 = DFMA only,
    2 = half of the warps of every scheduler DMMA and half DFMA concurrently.  TFLOP/s of each instruction class. */
 int gpfo_measure_fp64_pipes(gpfo_ctx* ctx, int mode, double* dmma_tflops, double* dfma_tflops);

@@ -1,0 +1,114 @@
+"""BASELINE configs #2-#5 on one B200: throughput + oracle parity on a subset.  Writes gpurun_out/sweep.log"""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gpflowopt_b200 import _lib, synthetic, pareto            # noqa: E402
+from oracle import acq as oacq, gp as ogp                     # noqa: E402
+
+PEAK = None
+
+
+def rel(a, b):
+    return float(np.max(np.abs(a - b)) / max(1e-300, np.max(np.abs(b))))
+
+
+def upload(ctx, i, g, slot0):
+    ctx.gp_set(i, g.Xs, g.Ys, g.kind, g.lengthscales, g.variance, g.noise_variance, np.diag(g.input_transform.A),
+               g.input_transform.b, np.diag(g.output_transform.A), g.output_transform.b, slot0)
+
+
+def model(M, D, kind=ogp.MATERN52, seed=1234, col=0, constraint=False):
+    X, Y = synthetic.training_set(M, D, seed=seed, constraint=constraint)
+    h = synthetic.hypers(D)
+    return ogp.ScaledGPR(X, Y[:, [col]], kind, h["lengthscales"], h["variance"], h["noise_variance"])
+
+
+def main():
+    global PEAK
+    ctx = _lib.Context(0)
+    PEAK = ctx.measure_dmma_peak()
+    print("FP64 DMMA peak %.2f TF/s" % PEAK, flush=True)
+    # ---- config #2 / #5: EI, D = 8, M sweep, values and gradients ---------------------------------------------------
+    for M in (512, 1024, 2048, 4096, 8192):
+        g = model(M, 8)
+        t0 = time.time()
+        upload(ctx, 0, g, 0)
+        ctx.gp_count_set(1)
+        fm = ctx.timings()["factor_ms"]
+        fmin = -1.5
+        ctx.program_set([[_lib.OP_EI, 0, 0, 0]], [fmin])
+        N = int(min(4e6, 1e6 * (2048.0 / M) ** 2))
+        Xc = synthetic.candidates(N, 8)
+        ctx.eval(Xc[:4096], want_values=False)
+        vals, _, bv, bi = ctx.eval(Xc)
+        t = ctx.timings()
+        sub = np.random.RandomState(1).choice(N, 2000, replace=False)
+        ref = oacq.Leaf('ei', g, fmin).value(Xc[sub])
+        tf = N * M * (M + 1.0) / (t["hot_kernel_ms"] * 1e-3) / 1e12
+        print("values  M=%5d N=%8d: factor %.1f ms, eval %.1f ms -> %.3e cand/s, %.2f TF/s (%.1f%% of peak), parity %.1e" % (
+            M, N, fm, t["eval_ms"], N / (t["eval_ms"] * 1e-3), tf, 100 * tf / PEAK, rel(vals[sub], ref)), flush=True)
+        Ng = max(4096, N // 8)
+        ctx.eval(Xc[:2048], want_grads=True)
+        vals, grads, _, _ = ctx.eval(Xc[:Ng], want_grads=True)
+        t = ctx.timings()
+        _, rg = oacq.Leaf('ei', g, fmin).value_and_grad(Xc[:200])
+        print("grads   M=%5d N=%8d: eval %.1f ms -> %.3e cand/s (%.2f TF/s of 3M^2 executed), grad parity %.1e" % (
+            M, Ng, t["eval_ms"], Ng / (t["eval_ms"] * 1e-3), Ng * 3.0 * M * M / (t["eval_ms"] * 1e-3) / 1e12,
+            rel(grads[:200], rg)), flush=True)
+    # ---- config #3: EI x PoF, two GPs, M = 4096, D = 16 (one GPU's shard of the 1e7 / 8-GPU job) -----------------
+    M, D, N = 4096, 16, 1250000
+    g1, g2 = model(M, D, constraint=True, col=0), model(M, D, constraint=True, col=1)
+    upload(ctx, 0, g1, 0)
+    upload(ctx, 1, g2, 1)
+    ctx.gp_count_set(2)
+    fmin = -1.0
+    ctx.program_set([[_lib.OP_EI, 0, 0, 0], [_lib.OP_POF, 1, 0, 1], [_lib.OP_PROD, 2, 0, 0]], [fmin, 0.0])
+    Xc = synthetic.candidates(N, D)
+    ctx.eval(Xc[:4096], want_values=False)
+    vals, _, bv, bi = ctx.eval(Xc)
+    t = ctx.timings()
+    sub = np.random.RandomState(2).choice(N, 1000, replace=False)
+    ref = oacq.Agg('prod', [oacq.Leaf('ei', g1, fmin), oacq.Leaf('pof', g2, 0.0)]).value(Xc[sub])
+    tf = 2.0 * N * M * (M + 1.0) / (t["hot_kernel_ms"] * 1e-3) / 1e12
+    print("config3 EIxPoF M=%d D=%d N=%d (1/8 of 1e7): eval %.1f ms -> %.3e cand/s, %.2f TF/s (%.1f%%), parity %.1e, argmax==argmax(vals) %s" % (
+        M, D, N, t["eval_ms"], N / (t["eval_ms"] * 1e-3), tf, 100 * tf / PEAK, rel(vals[sub], ref), bi == int(np.argmax(vals))), flush=True)
+    # ---- config #4: HVPoI, 3 objectives, M = 1024 per GP, P ~ 200 ---------------------------------------------------
+    M, D, R, N = 1024, 4, 3, 1000000
+    X = synthetic.candidates(M, D, seed=5)
+    F = synthetic.dtlz2_objectives(X, R)
+    h = synthetic.hypers(D, 1e-3)
+    gps = [ogp.ScaledGPR(X, F[:, [j]], ogp.MATERN52, h["lengthscales"], h["variance"], h["noise_variance"]) for j in range(R)]
+    for j, g in enumerate(gps):
+        upload(ctx, j, g, j)
+    ctx.gp_count_set(R)
+    Fm = np.hstack([ctx.predict(j, X, 1)[0] for j in range(R)])
+    t0 = time.time()
+    p = pareto.Pareto(np.zeros((1, R)))
+    p.update(Fm)
+    t_pareto = time.time() - t0
+    hv = oacq.HVPoI(gps, np.asarray(p.front), np.asarray(p.bounds.lb), np.asarray(p.bounds.ub))
+    ctx.cells_set(hv.pf_ext(), hv.lb, hv.ub)
+    ctx.program_set([[_lib.OP_HVPOI, 0, R, 0]], [])
+    Xc = synthetic.candidates(N, D)
+    ctx.eval(Xc[:4096], want_values=False)
+    vals, _, bv, bi = ctx.eval(Xc)
+    t = ctx.timings()
+    sub = np.random.RandomState(3).choice(N, 300, replace=False)
+    ref = hv.value(Xc[sub])
+    C = hv.lb.shape[0]
+    cell_ms = t["eval_ms"] - t["hot_kernel_ms"]
+    print("config4 HVPoI R=3 M=%d N=%d P=%d C=%d (host cell decomposition %.1f s): eval %.1f ms (GP contractions %.1f, cells %.1f) -> %.3e cand/s; "
+          "cell kernel %.2e cell*cand/s; parity %.1e" % (M, N, p.front.shape[0], C, t_pareto, t["eval_ms"], t["hot_kernel_ms"], cell_ms,
+                                                       N / (t["eval_ms"] * 1e-3), N * C / (cell_ms * 1e-3), rel(vals[sub], ref)), flush=True)
+    vals, grads, _, _ = ctx.eval(Xc[:20000], want_grads=True)
+    t = ctx.timings()
+    rv, rg = hv.value_and_grad(Xc[:64])
+    print("config4 HVPoI gradients N=20000: eval %.1f ms, grad parity %.1e" % (t["eval_ms"], rel(grads[:64], rg)), flush=True)
+
+
+if __name__ == "__main__":
+    main()
