@@ -522,12 +522,17 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
         EvalIO gio = io;
         gio.write_moments = need_mom ? 1 : 0;
         gio.run_program = (!hv && !want_grad && g == ctx->ngps - 1) ? 1 : 0;
-        if (variant == 11 || variant == 12 || (variant >= 120 && variant <= 129)) {
+        if (variant == 11 || variant == 12 || (variant >= 120 && variant <= 129)) {   // 12x: profiling builds of 12
             // per-CTA K(X*,X) scratch: one slot per (training point, candidate of the tile), rounded up to whole groups
             const size_t cols = ((size_t)ctx->gps[g].Mp + 127) / 128 * 128;
             const size_t stride = cols * (size_t)gpfo_contract_tile(variant);
             CK(ensure(&ctx->dkx_scratch, &ctx->cap_kx_scratch, stride * (size_t)grid));
             gio.kx_scratch = ctx->dkx_scratch;
+            if (variant == 127) {          // profiling build: phase counters land at the start of the values buffer
+                CK(ensure(&ctx->dvalues, &ctx->cap_values, (size_t)(N > 65536 ? N : 65536)));
+                gio.debug = reinterpret_cast<long long*>(ctx->dvalues);
+                gio.values = nullptr;
+            }
             gio.kx_scratch_stride = (long long)stride;
         }
         CK(cudaEventRecord(ctx->ev[6], st));
@@ -650,10 +655,9 @@ int gpfo_timings_get(const gpfo_ctx* ctx, gpfo_timings* out) {
 
 int gpfo_set_variant(gpfo_ctx* ctx, int variant) {
     if (!ctx) return GPFO_ERR_STATE;
-    static const int known[] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 11 + 0, 31, 32, 33, 41, 42, 43, 121, 122, 123};
+    static const int known[] = {0, 4, 5, 6, 10, 11, 12, 41, 42, 43, 121, 122, 123, 127};
     bool ok = false;
     for (int k : known) ok = ok || k == variant;
-    if (variant >= 11 && variant <= 13) ok = true;
     if (!ok) return fail(ctx, GPFO_ERR_BAD_SHAPE, "unknown kernel variant");
     ctx->variant = variant;
     return GPFO_OK;

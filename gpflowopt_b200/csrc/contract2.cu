@@ -23,8 +23,9 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     extern __shared__ __align__(16) double smem[];
     const int D = gpp->D;
     double* ring = smem;                                             // [NW][S][RBW][64]
-    double* kx = ring + (size_t)NW * C::RING_DOUBLES_PER_WARP;       // [2][GROUP_SLOTS]
-    double* xc = kx + 2 * C::GROUP_SLOTS;                            // [D][T]
+    constexpr int KXB = (ABL & 8) ? 3 : 2;                           // K(X*,X) group buffers (3 in scratch mode, see below)
+    double* kx = ring + (size_t)NW * C::RING_DOUBLES_PER_WARP;       // [KXB][GROUP_SLOTS]
+    double* xc = kx + KXB * C::GROUP_SLOTS;                          // [D][T]
     double* x2 = xc + (size_t)D * T;                                 // [T]
     double* tot = x2 + T;                                            // [T][1+RMAX] running colsum(A^2), A^T V
     constexpr int EW = (T + 31) / 32;                                // epilogue warps (32 candidates each)
@@ -32,7 +33,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     double* tab32 = sbest + 2 * EW;                                  // [32] 2^(i/32)
     static_assert(C::RING_DOUBLES_PER_WARP >= T * (1 + RMAX), "the per-warp reduction slice lives in the drained ring");
     constexpr bool GRADM = (ABL & 4) != 0;
-    double* gcm = tab32 + 32;                                        // [T][RMAX]  (d acq/d mean_ro) / out_scale_ro
+    double* gcm = tab32 + 34;                                        // [T][RMAX]  (d acq/d mean_ro) / out_scale_ro
     double* gcv = gcm + T * RMAX;                                    // [T]        -2 sum_ro (d acq/d var_ro) / out_scale_ro^2
     double* gsum = gcv + T;                                          // [T][1+D]   sum_i u_in [1, Xs_i]
     static_assert(!GRADM || S >= NB, "the u buffer of the gradient pass reuses the ring");
@@ -54,8 +55,12 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     const int gen_jl = lane & 3;
     const bool gen_first = ((w >> 2) & 1) == 0;          // warps w, w+4, w+8, w+12 share a scheduler: 2 + 2
 
+    constexpr bool TIM = (ABL & 64) != 0;             // profiling build: per-warp cycle counters per phase
+    long long t_gen = 0, t_mma = 0, t_bar = 0, t_red = 0, t_all = 0, t_mark = 0;
+    if (TIM) t_all = clock64();
     if (tid < EW) { sbest[2 * tid] = 0.0; reinterpret_cast<long long*>(sbest)[2 * tid + 1] = -1; }
     if (tid < 32) tab32[tid] = exp2(tid * (1.0 / 32.0));
+    __syncthreads();
 
     const int64_t ntiles = (io.N + T - 1) / T;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -95,13 +100,13 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
         }
         __syncthreads();
 
-        // With a K(X*,X) scratch the LAST chunk (which needs every column) goes first: it generates each group once and
-        // parks it in the per-CTA scratch; the other chunks re-read their groups instead of re-generating them.  Every
-        // thread re-reads exactly the slots it wrote itself, so no synchronisation is attached to the scratch.
+        // With a K(X*,X) scratch every group is generated ONCE per tile -- by the chunk whose diagonal it belongs to, where
+        // the triangular DMMA work is light and leaves pipe slots for the FP64 generation -- and parked in the per-CTA
+        // scratch; later chunks copy their off-diagonal groups back asynchronously, two groups ahead of use.
         constexpr bool SCR = (ABL & 8) != 0;             // compile-time: the plain variants carry no scratch code
         double* const scratch = SCR ? io.kx_scratch + (size_t)blockIdx.x * io.kx_scratch_stride : nullptr;
         for (int pi = 0; pi < geom.nchunks; ++pi) {
-            const int p = SCR ? geom.nchunks - 1 - pi : pi;
+            const int p = pi;
             const int nr = pg_chunk_rows(geom, p);
             const int row0 = p * geom.rbc;                // first row block of this chunk
             const int kp_end = GRADM ? geom.nrb : row0 + nr;
@@ -138,15 +143,6 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             };
 
             auto gen_group = [&](int g, double* __restrict__ dst) {
-                if (SCR && pi > 0) {                  // re-read this thread's own slots (LDG + STS measured faster than cp.async 8 B)
-                    const double* __restrict__ src = scratch + (size_t)g * C::GROUP_SLOTS;
-                    double v[C::GEN_ITERS];
-#pragma unroll
-                    for (int q = 0; q < C::GEN_ITERS; ++q) v[q] = __ldcg(src + (((w + NW * q) / NB) * NB + gen_nb) * 32 + lane);
-#pragma unroll
-                    for (int q = 0; q < C::GEN_ITERS; ++q) dst[(((w + NW * q) / NB) * NB + gen_nb) * 32 + lane] = v[q];
-                    return;
-                }
                 double dot[C::GEN_ITERS];
                 int jj[C::GEN_ITERS];
 #pragma unroll
@@ -179,6 +175,19 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 }
             };
 
+            // scratch mode, re-read chunks: asynchronous copy of a whole group scratch -> shared, issued TWO groups ahead
+            // (third buffer), so its L2/HBM latency never sits between the DMMA work and the group barrier
+            auto copy_group = [&](int g) {
+                const double* __restrict__ src = scratch + (size_t)g * C::GROUP_SLOTS;
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(kx + (g % KXB) * C::GROUP_SLOTS);
+#pragma unroll
+                for (int q = 0; q < C::GROUP_SLOTS / (2 * C::THREADS); ++q) {
+                    const int ch = tid + q * C::THREADS;                 // 16-byte chunk index
+                    cp_async16(dst + ch * 16, src + 2 * ch);
+                }
+                cp_async_commit();
+            };
+
             // one column block: B fragments from the Kx group buffer, A fragments from the ring, RBW*2*NB DMMAs.
             // FULL = every row block of this warp is active (dense column block of a full chunk): no predicates.
             auto mma_kp = [&](const double* __restrict__ kbk, int lo, auto full_tag) {
@@ -207,7 +216,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 rd_stage = (rd_stage == (S - 1) * RBW * 64) ? 0 : rd_stage + RBW * 64;
             };
             auto mma_group = [&](int g) {
-                const double* __restrict__ kb = kx + (g & 1) * C::GROUP_SLOTS + lane;
+                const double* __restrict__ kb = kx + (g % KXB) * C::GROUP_SLOTS + lane;
                 const int k0 = g * KPC;
                 const int k1 = (k0 + KPC < kp_end) ? k0 + KPC : kp_end;
                 if (nr == C::RBC && k1 <= kd0) {       // whole group in the dense part of a full chunk
@@ -221,21 +230,49 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             };
 
             const int ngroups = (kp_end + KPC - 1) / KPC;
-            gen_group(0, kx);
+            const int nold = SCR ? kd0 / KPC : 0;          // groups left of the diagonal: generated by earlier chunks
+            if (nold > 0) {
+                copy_group(0);
+                if (nold > 1) copy_group(1);
+                cp_async_wait<0>();
+            } else {
+                gen_group(0, kx);
+            }
 #pragma unroll
             for (int s = 0; s < S - 1; ++s) issue();
             __syncthreads();
             for (int g = 0; g < ngroups; ++g) {
                 const bool more = g + 1 < ngroups;
-                double* nxt = kx + ((g + 1) & 1) * C::GROUP_SLOTS;
-                if (gen_first) {
-                    if (more) gen_group(g + 1, nxt);
+                double* nxt = kx + ((g + 1) % KXB) * C::GROUP_SLOTS;
+                // (A split arrive/wait barrier on an mbarrier was measured here: it moves waiting time from the barrier
+                // into pipe contention, 26.8 vs 27.2 TFLOP/s, so the plain CTA barrier stays.)
+                if (SCR && g + 2 < nold) copy_group(g + 2);
+                if (SCR && g + 1 < nold) {            // next group comes from the scratch (already in flight)
+                    if (TIM) t_mark = clock64();
                     mma_group(g);
+                    if (TIM) t_mma += clock64() - t_mark;
+                    // it was committed a whole iteration ago; only a very short group can leave it pending
+                    const int kcount = (kp_end < (g + 1) * KPC ? kp_end : (g + 1) * KPC) - g * KPC;
+                    if (kcount < S) cp_async_wait<0>();
+                } else if (gen_first) {
+                    if (TIM) t_mark = clock64();
+                    if (more) gen_group(g + 1, nxt);
+                    if (TIM) { const long long t = clock64(); t_gen += t - t_mark; t_mark = t; }
+                    mma_group(g);
+                    if (TIM) t_mma += clock64() - t_mark;
                 } else {
+                    if (TIM) t_mark = clock64();
                     mma_group(g);
+                    if (TIM) { const long long t = clock64(); t_mma += t - t_mark; t_mark = t; }
                     if (more) gen_group(g + 1, nxt);
+                    if (TIM) t_gen += clock64() - t_mark;
                 }
+                if (TIM) t_mark = clock64();
                 __syncthreads();
+                if (TIM) {                            // BAR.SYNC defers blocking to the next dependent access: force one
+                    if (*reinterpret_cast<volatile double*>(tab32) == 123.456) t_gen += 1;
+                    t_bar += clock64() - t_mark;
+                }
             }
             cp_async_wait<0>();
 
@@ -277,6 +314,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 __syncthreads();
                 continue;
             }
+            if (TIM) t_mark = clock64();
             // ---- chunk reduction (fixed order -> deterministic).  Warp w's slice red[w][T][1+RMAX] lives at the start of its
             // own, now drained, ring region; the next chunk's copies are issued only after the barriers below.
             double* const red = ring;
@@ -339,6 +377,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 }
             }
             __syncthreads();
+            if (TIM) t_red += clock64() - t_mark;
         }
         if (GRADM) {
             // d acq / d x_d = 2 a_d / l_d * (xs_d * sum_i u_i - sum_i u_i Xs_id)       (d r^2 / d x_d = 2 (xs_d - Xs_id) a_d / l_d)
@@ -365,6 +404,10 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             if (lane == 0) { sbest[2 * w] = best_v; reinterpret_cast<long long*>(sbest)[2 * w + 1] = best_i; }
         }
     }
+    if (TIM && lane == 0 && io.debug) {
+        long long* o = io.debug + ((size_t)blockIdx.x * NW + w) * 8;
+        o[0] = clock64() - t_all; o[1] = t_gen; o[2] = t_mma; o[3] = t_bar; o[4] = t_red;
+    }
     __syncthreads();
     if (tid == 0 && io.run_program) {
         double bv = sbest[0];
@@ -381,8 +424,8 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
 template <int NW, int RBW, int NB, int S, int KIND, int ABL>
 static cudaError_t launch2_kind(cudaStream_t st, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io, int grid, int D) {
     using C = Contract2Cfg<NW, RBW, NB, S>;
-    const size_t smem = ((size_t)NW * C::RING_DOUBLES_PER_WARP + 2 * C::GROUP_SLOTS +
-                         (size_t)D * C::T + C::T + C::T * (1 + RMAX) + 2 * ((C::T + 31) / 32) + 32 +
+    const size_t smem = ((size_t)NW * C::RING_DOUBLES_PER_WARP + ((ABL & 8) ? 3 : 2) * C::GROUP_SLOTS +
+                         (size_t)D * C::T + C::T + C::T * (1 + RMAX) + 2 * ((C::T + 31) / 32) + 34 +
                          ((ABL & 4) ? C::T * RMAX + C::T + C::T * (1 + (size_t)D) : 0)) * sizeof(double);
     auto kern = contract2_kernel<NW, RBW, NB, S, KIND, ABL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -401,23 +444,17 @@ static cudaError_t launch2(cudaStream_t st, int kind, const GpDev* d_gp, const P
     }
 }
 
-// v2 variants (all use 64-row-block = 512-row chunks):
-//   4: 16 warps, RBW=4, NB=4 (T=32), 4-stage ring     5: 16 warps, RBW=4, NB=2 (T=16), 4-stage ring
-//   6: 16 warps, RBW=4, NB=1 (T=8)                    41/42/43: ablations of 4 (no gen / no loads / neither)
-//   7: 16 warps, RBW=8, NB=2 (T=16), 1024-row chunks, 3-stage ring      8: same, 2-stage ring      9: as 4, 5-stage ring
+// variants: see the table in contract.cu
 cudaError_t gpfo_contract2_launch(cudaStream_t st, int variant, int kind, const GpDev* d_gp, const ProgramDev* d_prog,
                                   EvalIO io, int grid, int D) {
     switch (variant) {
         case 5: return launch2<16, 4, 2, 4>(st, kind, d_gp, d_prog, io, grid, D);
-        case 7: return launch2<16, 8, 2, 3>(st, kind, d_gp, d_prog, io, grid, D);
-        case 8: return launch2<16, 8, 2, 2>(st, kind, d_gp, d_prog, io, grid, D);
-        case 9: return launch2<16, 4, 4, 5>(st, kind, d_gp, d_prog, io, grid, D);
         case 11: return launch2<16, 4, 4, 4, 8>(st, kind, d_gp, d_prog, io, grid, D);
         case 12: return launch2<16, 2, 8, 4, 8>(st, kind, d_gp, d_prog, io, grid, D);
-        case 13: return launch2<16, 2, 8, 4>(st, kind, d_gp, d_prog, io, grid, D);
         case 121: return launch2<16, 2, 8, 4, 9>(st, kind, d_gp, d_prog, io, grid, D);
         case 122: return launch2<16, 2, 8, 4, 10>(st, kind, d_gp, d_prog, io, grid, D);
         case 123: return launch2<16, 2, 8, 4, 11>(st, kind, d_gp, d_prog, io, grid, D);
+        case 127: return launch2<16, 2, 8, 4, 8 + 64>(st, kind, d_gp, d_prog, io, grid, D);
         case 6: return launch2<16, 4, 1, 4>(st, kind, d_gp, d_prog, io, grid, D);
         case 41: return launch2<16, 4, 4, 4, 1>(st, kind, d_gp, d_prog, io, grid, D);
         case 42: return launch2<16, 4, 4, 4, 2>(st, kind, d_gp, d_prog, io, grid, D);

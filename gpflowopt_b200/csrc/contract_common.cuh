@@ -95,6 +95,22 @@ struct Contract2Cfg {
 __device__ __forceinline__ void cp_async16(unsigned smem_dst, const void* gmem_src) {     // smem_dst: shared-window address
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
+// CTA-scope split barrier on an mbarrier: arrive (release) as soon as this thread's shared-memory writes are done,
+// wait (acquire) only right before the first dependent read.  `phase` is the per-thread parity bit.
+__device__ __forceinline__ void mbar_init(unsigned bar_s, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar_s) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar_s) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar_s, unsigned& phase) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t}" ::"r"(bar_s), "r"(phase) : "memory");
+    phase ^= 1u;
+}
 __device__ __forceinline__ void cp_async8(unsigned smem_dst, const void* gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }

@@ -131,6 +131,7 @@ struct EvalIO {
     // optional K(X*,X) scratch (variant 11): [grid][groups][GROUP_SLOTS] doubles, thread-private re-reads
     double* kx_scratch;
     long long kx_scratch_stride;   // doubles per CTA
+    long long* debug;              // profiling builds only (ABL bit 64): per-warp phase cycle counters
 };
 
 #define GPFO_STABILITY 1e-6     // gpflow settings.numerics.jitter_level (ei.py:24, poi.py:23, pof.py:23, hvpoi.py:24)
