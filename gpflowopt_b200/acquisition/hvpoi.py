@@ -1,7 +1,7 @@
 """Hypervolume-based Probability of Improvement (mirror of gpflowopt/acquisition/hvpoi.py)."""
 import numpy as np
 
-from ..pareto import Pareto
+from ..pareto import Pareto, merge_cells
 from .acquisition import Acquisition
 
 
@@ -13,6 +13,7 @@ class HVProbabilityOfImprovement(Acquisition):
         self.pareto = Pareto(np.empty((0, num_objectives)))
         self.reference = np.ones((1, num_objectives))
         self._cells_version = 0
+        self._merged, self._merged_version = None, -1
 
     def _estimate_reference(self):
         pf = self.pareto.front
@@ -32,5 +33,7 @@ class HVProbabilityOfImprovement(Acquisition):
     def build_acquisition(self, Xcand):
         outdim = self.data[1].shape[1]
         pf_ext = np.vstack((-np.inf * np.ones((1, outdim)), self.pareto.front, self.reference))
-        return Xcand.hvpoi(self.models, pf_ext, self.pareto.bounds.lb, self.pareto.bounds.ub,
-                           (id(self), self._cells_version))
+        if self._merged_version != self._cells_version:     # coarsen once per Pareto update (same region, fewer cells)
+            self._merged = merge_cells(pf_ext, self.pareto.bounds.lb, self.pareto.bounds.ub)
+            self._merged_version = self._cells_version
+        return Xcand.hvpoi(self.models, pf_ext, self._merged[0], self._merged[1], (id(self), self._cells_version))

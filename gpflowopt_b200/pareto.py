@@ -157,3 +157,42 @@ class Pareto(object):
         ub = pseudo[np.asarray(self.bounds.ub), cols]
         lb = pseudo[np.asarray(self.bounds.lb), cols]
         return float(np.prod(reference[None, :] - min_pf) - np.sum(np.prod(ub - lb, axis=1)))
+
+
+def merge_cells(pf_ext, lb, ub):
+    """Coarsens a cell decomposition without changing the region it covers: cells that agree in all objectives but one
+    and touch in that one (``a.ub[d] == b.lb[d]``, same row of ``pf_ext``) are fused, repeatedly, along every objective.
+
+    The divide-and-conquer of the reference emits ~P^2 small cells (47 777 for a 204-point 3-objective front); fusing
+    leaves ~P (1 736).  Both HVPoI terms are additive over such splits exactly -- Phi(c) - Phi(a) = (Phi(b) - Phi(a)) +
+    (Phi(c) - Phi(b)) and (c - max(a, mu))+ = (b - max(a, mu))+ + (c - max(b, mu))+ -- so the acquisition value is the same
+    function (differences are re-association roundings, ~1e-16 relative); the device kernel's cost is linear in the cell count.
+    ``Pareto.bounds`` keeps the reference tables; only the copy uploaded to the device is coarsened.
+    """
+    lb = np.asarray(lb, dtype=np.int64)
+    ub = np.asarray(ub, dtype=np.int64)
+    if lb.shape[0] < 2:
+        return lb.astype(np_int_type), ub.astype(np_int_type)
+    R = lb.shape[1]
+    pf_ext = np.asarray(pf_ext, dtype=np.float64)
+    changed = True
+    while changed:
+        changed = False
+        for d in range(R):
+            others = [k for k in range(R) if k != d]
+            keys = [pf_ext[lb[:, d], d]]                   # last key of lexsort is the primary one: others first, then d
+            for k in reversed(others):
+                keys += [ub[:, k], lb[:, k]]
+            order = np.lexsort(keys)
+            lb, ub = lb[order], ub[order]
+            glue = np.all(lb[1:, others] == lb[:-1, others], axis=1) & np.all(ub[1:, others] == ub[:-1, others], axis=1) & \
+                (lb[1:, d] == ub[:-1, d])
+            if not glue.any():
+                continue
+            changed = True
+            starts = np.flatnonzero(np.concatenate(([True], ~glue)))         # first cell of every run
+            ends = np.concatenate((starts[1:] - 1, [lb.shape[0] - 1]))       # last cell of every run
+            new_ub = ub[starts].copy()
+            new_ub[:, d] = ub[ends, d]
+            lb, ub = lb[starts], new_ub
+    return lb.astype(np_int_type), ub.astype(np_int_type)
