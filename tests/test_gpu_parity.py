@@ -361,3 +361,82 @@ def test_gradient_large_m_and_finite_difference(ctx):
         e[d] = eps
         fd = (ctx.eval(Xc + e)[0] - ctx.eval(Xc - e)[0])[:, 0] / (2 * eps)
         assert np.max(np.abs(fd - grads[:, d])) <= 1e-5 * np.max(np.abs(grads))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# shape / parameter edge cases
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("D", [1, 2, 7, 33, 64])
+def test_input_dimensions(ctx, D):
+    X, Y = synthetic.training_set(90, D)
+    g = oracle_gp(X, Y, ogp.MATERN52, synthetic.hypers(D))
+    upload_oracle_gp(ctx, 0, g)
+    ctx.program_set([[_lib.OP_LCB, 0, 0, 0]], [1.0])
+    Xc = synthetic.candidates(500, D)
+    vals, grads, _, _ = ctx.eval(Xc, want_grads=True)
+    rv, rg = oacq.Leaf('lcb', g, 1.0).value_and_grad(Xc)
+    assert_parity(vals, rv, what="LCB D=%d" % D)
+    assert_parity(grads, rg, what="LCB grad D=%d" % D)
+
+
+def test_isotropic_lengthscale_and_kernel_families(ctx):
+    """Non-ARD kernels (one lengthscale for all inputs), as create_vlmop2_model builds them (testing/utility.py:61-62)."""
+    X, Y = synthetic.training_set(120, 3)
+    for kind in (ogp.RBF, ogp.MATERN52, ogp.MATERN32):
+        h = dict(lengthscales=np.array([0.8]), variance=0.9, noise_variance=1e-3)
+        g = oracle_gp(X, Y, kind, h)
+        upload_oracle_gp(ctx, 0, g)
+        Xc = synthetic.candidates(300, 3)
+        mean, var = ctx.predict(0, Xc, 1)
+        mo, vo = g.predict(Xc)
+        assert_parity(mean, mo, what="mean kind %d" % kind)
+        assert_parity(var, vo, scale=g.variance, what="var kind %d" % kind)
+
+
+def test_leaf_on_second_output_column_and_slot_offsets(ctx):
+    """Programs may reference any moment slot: a 3-output GP in slots 0..2 and a 1-output GP in slot 3."""
+    D = 3
+    X, Y = synthetic.training_set(80, D, constraint=True)
+    Y3 = np.hstack((Y, (Y[:, [0]] * Y[:, [1]])))
+    h = synthetic.hypers(D)
+    g3 = oracle_gp(X, Y3, ogp.RBF, h)
+    g1 = oracle_gp(X, Y[:, [1]], ogp.MATERN32, h)
+    upload_oracle_gp(ctx, 0, g3, slot0=0)
+    upload_oracle_gp(ctx, 1, g1, slot0=3)
+    ctx.gp_count_set(2)
+    try:
+        # EI on column 2 of the first GP times PoF of the second GP, plus the mean of column 1
+        ctx.program_set([[_lib.OP_EI, 2, 0, 0], [_lib.OP_POF, 3, 0, 1], [_lib.OP_PROD, 2, 0, 0], [_lib.OP_MEAN, 1, 0, 0],
+                         [_lib.OP_SUM, 2, 0, 0]], [0.1, 0.0])
+        Xc = synthetic.candidates(400, D)
+        vals, grads, _, _ = ctx.eval(Xc, want_grads=True)
+        m3, v3 = g3.predict(Xc)
+        ei = oacq.Leaf('ei', g3, 0.1)._value(m3[:, [2]], v3[:, [2]])
+        pof = oacq.Leaf('pof', g1, 0.0).value(Xc)
+        assert_parity(vals, ei * pof + m3[:, [1]], what="multi-output slots")
+        eps = 1e-6
+        e = np.zeros(D)
+        e[1] = eps
+        fd = (ctx.eval(Xc + e)[0] - ctx.eval(Xc - e)[0])[:, 0] / (2 * eps)
+        assert np.max(np.abs(fd - grads[:, 1])) <= 2e-5 * np.max(np.abs(grads))
+    finally:
+        ctx.gp_count_set(1)
+
+
+def test_large_candidate_batch_device_resident(ctx):
+    """10^7 candidates resident on the device (config #3's per-job size), M small: exercises 64-bit indexing and the
+    device-pointer path of gpfo_eval; checked through sub-batch consistency."""
+    import torch
+    g, lo, up = _model(64, 4, "rbf")
+    upload_oracle_gp(ctx, 0, g)
+    ctx.program_set([[_lib.OP_EI, 0, 0, 0]], [-0.3])
+    N = 10_000_000
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    Xd = torch.rand((N, 4), dtype=torch.float64, device="cuda", generator=gen)
+    vd = torch.empty(N, dtype=torch.float64, device="cuda")
+    bv, bi = ctx.eval_device(Xd.data_ptr(), N, 4, vd.data_ptr())
+    torch.cuda.synchronize()
+    assert int(torch.argmax(vd)) == bi and float(vd[bi]) == bv
+    tail = Xd[N - 1000:].cpu().numpy()
+    ref = oacq.Leaf('ei', g, -0.3).value(tail)
+    assert_parity(vd[N - 1000:].cpu().numpy()[:, None], ref, what="tail of a 1e7 batch")
