@@ -17,7 +17,7 @@ MAX_GPS, MAX_SLOTS, MAX_OPS, MAX_PARAMS, MAX_DIM = 16, 16, 64, 64, 64
 EXPORTS = ["gpfo_version", "gpfo_ctx_create", "gpfo_ctx_destroy", "gpfo_last_error", "gpfo_status_string",
            "gpfo_gp_set", "gpfo_gp_count_set", "gpfo_gp_get_factor", "gpfo_program_set", "gpfo_cells_set",
            "gpfo_eval", "gpfo_predict", "gpfo_timings_get", "gpfo_set_variant", "gpfo_measure_dmma_peak",
-           "gpfo_measure_fp64_pipes", "gpfo_pareto_cells"]
+           "gpfo_measure_fp64_pipes", "gpfo_pareto_cells", "gpfo_eval_random", "gpfo_random_rows"]
 
 
 class Timings(ctypes.Structure):
@@ -72,6 +72,9 @@ def load():
     lib.gpfo_measure_dmma_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     lib.gpfo_measure_fp64_pipes.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
                                             ctypes.POINTER(ctypes.c_double)]
+    lib.gpfo_eval_random.argtypes = [vp, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, c_dp, c_dp, c_dp,
+                                     ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]
+    lib.gpfo_random_rows.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, c_dp, c_dp, c_dp]
     lib.gpfo_pareto_cells.argtypes = [c_dp, c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_double, c_dp, c_dp, ctypes.c_int64,
                                       ctypes.POINTER(ctypes.c_int64)]
     for name in EXPORTS:
@@ -91,6 +94,17 @@ def _f64(a, shape=None):
     if shape is not None:
         a = a.reshape(shape)
     return a
+
+
+def random_rows(seed, first_row, n, lower, upper):
+    """Rows [first_row, first_row + n) of the device candidate stream, regenerated on the host (no GPU needed)."""
+    lib = load()
+    lower, upper = _f64(lower).ravel(), _f64(upper).ravel()
+    out = np.empty((int(n), lower.size))
+    st = lib.gpfo_random_rows(int(seed), int(first_row), int(n), lower.size, _ptr(lower), _ptr(upper), _ptr(out) if n else None)
+    if st != OK and n:
+        raise GpfoError(st, "gpfo_random_rows failed")
+    return out
 
 
 def pareto_cells(front, order, threshold=0.0):
@@ -208,6 +222,15 @@ class Context(object):
                                         ctypes.c_void_p(grads_ptr) if grads_ptr else None,
                                         ctypes.byref(bv), ctypes.byref(bi)))
         return bv.value, bi.value
+
+    def eval_random(self, seed, first_row, N, lower, upper, want_values=False):
+        """Scores N device-generated candidates (rows first_row .. first_row+N-1 of the stream keyed by seed)."""
+        lower, upper = _f64(lower).ravel(), _f64(upper).ravel()
+        vals = np.empty((N, 1)) if want_values else None
+        bv, bi = ctypes.c_double(0.0), ctypes.c_int64(-1)
+        self._check(self._lib.gpfo_eval_random(self._h, int(seed), int(first_row), int(N), lower.size, _ptr(lower), _ptr(upper),
+                                               _ptr(vals) if (want_values and N) else None, ctypes.byref(bv), ctypes.byref(bi)))
+        return vals, bv.value, bi.value
 
     def predict(self, gp_id, X, R):
         X = _f64(X)

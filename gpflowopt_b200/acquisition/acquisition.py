@@ -152,6 +152,12 @@ class Acquisition(object):
         This is the fused form of ``np.argmin(-evaluate(X))`` in MCOptimizer._optimize (gpflowopt/optim.py:155-164)."""
         return self._get_engine().argmax(self, Xcand)
 
+    @setup_required
+    def argmax_random(self, seed, first_row, n, lower, upper):
+        """``argmax`` over candidates generated on the device (rows first_row .. first_row+n-1 of the stream keyed by
+        ``seed``, uniform in the box [lower, upper]); nothing of size N crosses PCIe in either direction."""
+        return self._get_engine().argmax_random(self, seed, first_row, n, lower, upper)
+
     def __add__(self, other):
         if isinstance(other, AcquisitionSum):
             return AcquisitionSum([self] + other.operands)

@@ -46,6 +46,8 @@ struct gpfo_ctx {
     double *dcmu = nullptr, *dcva = nullptr; size_t cap_coef = 0;
     double* dgrads = nullptr; size_t cap_grads = 0;
     double* dkx_scratch = nullptr; size_t cap_kx_scratch = 0;
+    double* dgen = nullptr;                                  // 2 * GPFO_MAX_DIM doubles: affine map of the device candidate generator
+    bool gen_active = false; unsigned long long gen_seed = 0; long long gen_first = 0;
     double* dpart_val = nullptr; long long* dpart_idx = nullptr; int cap_parts = 0;
     double* dbest_val = nullptr; long long* dbest_idx = nullptr;
     int* dflag = nullptr;
@@ -143,7 +145,7 @@ int gpfo_ctx_destroy(gpfo_ctx* ctx) {
     for (int i = 0; i < GPFO_MAX_GPS; ++i) free_gp(ctx->gps[i]);
     cudaFree(ctx->dprog); cudaFree(ctx->dpf); cudaFree(ctx->dlb); cudaFree(ctx->dub);
     cudaFree(ctx->dXc); cudaFree(ctx->dvalues); cudaFree(ctx->dmom_mean); cudaFree(ctx->dmom_var);
-    cudaFree(ctx->dcmu); cudaFree(ctx->dcva); cudaFree(ctx->dgrads); cudaFree(ctx->dkx_scratch);
+    cudaFree(ctx->dcmu); cudaFree(ctx->dcva); cudaFree(ctx->dgrads); cudaFree(ctx->dkx_scratch); cudaFree(ctx->dgen);
     cudaFree(ctx->dpart_val); cudaFree(ctx->dpart_idx); cudaFree(ctx->dbest_val); cudaFree(ctx->dbest_idx);
     cudaFree(ctx->dflag);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
@@ -453,14 +455,19 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
         ctx->tm.launches = 0;
         return GPFO_OK;
     }
-    if (!Xcand) return fail(ctx, GPFO_ERR_BAD_SHAPE, "null candidates");
+    const bool generate = ctx->gen_active;
+    if (!Xcand && !generate) return fail(ctx, GPFO_ERR_BAD_SHAPE, "null candidates");
+    if (generate && want_grad) return fail(ctx, GPFO_ERR_UNSUPPORTED, "gradients of generated candidates are not supported");
     cudaStream_t st = ctx->stream;
     const double* dX = nullptr;
-    int rc = stage_candidates(ctx, Xcand, N, D, &dX);
+    int rc = GPFO_OK;
+    if (!generate) rc = stage_candidates(ctx, Xcand, N, D, &dX);
+    else ctx->tm.h2d_ms = 0.0;
     if (rc != GPFO_OK) return rc;
-    const bool host_in = (dX != Xcand);
+    const bool host_in = !generate && (dX != Xcand);
 
-    const int variant = effective_variant(ctx, N);
+    int variant = effective_variant(ctx, N);
+    if (generate && variant == 10) variant = 12;
     const bool use_cluster = variant == 10;
     const int rbc = gpfo_contract_rbc(variant);
     for (int g = 0; g < ctx->ngps; ++g) {
@@ -476,6 +483,10 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     EvalIO io;
     memset(&io, 0, sizeof(io));
     io.X = dX; io.N = N;
+    if (generate) {
+        io.gen_A = ctx->dgen; io.gen_b = ctx->dgen + GPFO_MAX_DIM;
+        io.gen_seed = ctx->gen_seed; io.gen_first = ctx->gen_first;
+    }
     if (need_mom) {
         const size_t need = (size_t)GPFO_MAX_SLOTS * N;
         if (ctx->cap_mom < need) {
@@ -598,6 +609,43 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     if (ctx->ngps == 1) { cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); hot_ms = ms; }
     ctx->tm.hot_kernel_ms = hot_ms;
     ctx->tm.launches = launches;
+    return GPFO_OK;
+}
+
+// affine map of design.py:55-70 for generative_domain = unit cube: A = upper - lower, b = -1 * A + upper
+static void gen_map(int D, const double* lower, const double* upper, double* A, double* b) {
+    for (int d = 0; d < D; ++d) {
+        A[d] = (upper[d] - lower[d]) / (1.0 - 0.0);
+        b[d] = -1.0 * A[d] + upper[d];
+    }
+}
+
+int gpfo_eval_random(gpfo_ctx* ctx, uint64_t seed, int64_t first_row, int64_t N, int D, const double* lower,
+                     const double* upper, double* out_values, double* best_value, int64_t* best_index) {
+    if (!ctx) return GPFO_ERR_STATE;
+    if (D < 1 || D > GPFO_MAX_DIM || !lower || !upper || first_row < 0) return fail(ctx, GPFO_ERR_BAD_SHAPE, "bad generator arguments");
+    cudaSetDevice(ctx->device);
+    double host[2 * GPFO_MAX_DIM] = {0.0};
+    gen_map(D, lower, upper, host, host + GPFO_MAX_DIM);
+    if (!ctx->dgen) CK(cudaMalloc((void**)&ctx->dgen, sizeof(host)));
+    CK(cudaMemcpy(ctx->dgen, host, sizeof(host), cudaMemcpyHostToDevice));
+    ctx->gen_active = true; ctx->gen_seed = seed; ctx->gen_first = first_row;
+    const int rc = gpfo_eval(ctx, nullptr, N, D, out_values, nullptr, best_value, best_index);
+    ctx->gen_active = false;
+    return rc;
+}
+
+int gpfo_random_rows(uint64_t seed, int64_t first_row, int64_t n, int D, const double* lower, const double* upper,
+                     double* out) {
+    if (D < 1 || D > GPFO_MAX_DIM || !lower || !upper || !out || n < 0 || first_row < 0) return GPFO_ERR_BAD_SHAPE;
+    double A[GPFO_MAX_DIM], b[GPFO_MAX_DIM];
+    gen_map(D, lower, upper, A, b);
+    for (int64_t r = 0; r < n; ++r)
+        for (int d = 0; d < D; ++d) {
+            const double u = gpfo_uniform(seed, (unsigned long long)(first_row + r) * D + d);
+            volatile double prod = u * A[d];               // separate roundings, as the device's __dmul_rn / __dadd_rn
+            out[r * D + d] = prod + b[d];
+        }
     return GPFO_OK;
 }
 

@@ -88,7 +88,14 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
         for (int e = tid; e < T * D; e += C::THREADS) {
             const int n = e / D, d = e - n * D;
             double x = 0.0;
-            if (n0 + n < io.N) x = io.X[(size_t)(n0 + n) * D + d];
+            if (n0 + n < io.N) {
+                if (io.gen_A) {     // RandomDesign on the device: unit-cube draw, then generative_domain >> domain (design.py:55-70, 93-94)
+                    const double u = gpfo_uniform(io.gen_seed, (unsigned long long)(io.gen_first + n0 + n) * D + d);
+                    x = __dadd_rn(__dmul_rn(u, io.gen_A[d]), io.gen_b[d]);
+                } else {
+                    x = io.X[(size_t)(n0 + n) * D + d];
+                }
+            }
             const double xt = __dadd_rn(__dmul_rn(x, gp.in_scale[d]), gp.in_shift[d]);
             xc[d * T + n] = xt / gp.ell[d];
         }

@@ -132,7 +132,25 @@ struct EvalIO {
     double* kx_scratch;
     long long kx_scratch_stride;   // doubles per CTA
     long long* debug;              // profiling builds only (ABL bit 64): per-warp phase cycle counters
+    // on-device candidate generation: row r, column d = gen_b[d] + gen_A[d] * U(seed, (gen_first + r) * D + d)
+    const double* gen_A;           // device, D values (null: candidates are read from X)
+    const double* gen_b;
+    unsigned long long gen_seed;
+    long long gen_first;           // global index of this call's row 0 (lets every rank generate its own shard)
 };
+
+// Counter-based uniform generator shared by the device prologue and the host regeneration (gpfo_random_rows):
+// two rounds of the splitmix64 finaliser over (seed, element counter); the top 53 bits become a double in [0, 1).
+GPFO_HD unsigned long long gpfo_mix64(unsigned long long x) {
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return x;
+}
+GPFO_HD double gpfo_uniform(unsigned long long seed, unsigned long long counter) {
+    const unsigned long long bits = gpfo_mix64(seed ^ gpfo_mix64(counter + 0x9E3779B97F4A7C15ull));
+    return (double)(bits >> 11) * (1.0 / 9007199254740992.0);
+}
 
 #define GPFO_STABILITY 1e-6     // gpflow settings.numerics.jitter_level (ei.py:24, poi.py:23, pof.py:23, hvpoi.py:24)
 

@@ -52,6 +52,17 @@ def broadcast_points(points):
     return buf.cpu().numpy()
 
 
+def broadcast_int(value):
+    """Rank 0's integer on every rank (seed of the device candidate generator)."""
+    td = _pg()
+    if td is None or td.get_world_size() == 1:
+        return int(value)
+    import torch
+    t = torch.tensor([int(value)], dtype=torch.int64, device=_device_for_collectives(td))
+    td.broadcast(t, src=0)
+    return int(t[0])
+
+
 def reduce_pairs(values, indices):
     """Lexicographic reduce over per-rank (value, global index) pairs: max value, ties -> lowest index;
     index < 0 marks an empty shard; NaN never wins."""

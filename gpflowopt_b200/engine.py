@@ -163,6 +163,12 @@ class Engine(object):
         _, _, bv, bi = self.ctx.eval(X, want_values=False, want_grads=False)
         return bv, bi
 
+    def argmax_random(self, acq, seed, first_row, n, lower, upper):
+        """Best (value, LOCAL index) over rows first_row .. first_row+n-1 of the device-generated candidate stream."""
+        self.prepare(acq)
+        _, bv, bi = self.ctx.eval_random(seed, first_row, n, lower, upper)
+        return bv, bi
+
     def argmax_device(self, acq, x_ptr, N, D, values_ptr=None):
         self.prepare(acq)
         return self.ctx.eval_device(x_ptr, N, D, values_ptr)

@@ -72,9 +72,14 @@ class Optimizer(object):
 class MCOptimizer(Optimizer):
     """Scores ``nsamples`` uniformly random points and returns the best (gpflowopt/optim.py:131-172)."""
 
-    def __init__(self, domain, nsamples):
+    def __init__(self, domain, nsamples, device_rng=False):
+        """``device_rng=True`` (opt-in): for gpflowopt_b200 acquisitions the candidates are generated
+        inside the scoring kernel from a counter-based stream (seeded from ``np.random``), every rank producing its own
+        shard, so no N x D array is built, copied or broadcast; the winning row is regenerated on the host.  The points
+        differ from ``np.random.rand``'s, which is why the default keeps the reference's host generation."""
         super(MCOptimizer, self).__init__(domain, exclude_gradient=True)
         self._nsamples = nsamples
+        self._device_rng = device_rng
         self.set_initial(np.empty((0, self.domain.size)))
 
     @property
@@ -88,9 +93,27 @@ class MCOptimizer(Optimizer):
     def _get_eval_points(self):
         return RandomDesign(self._nsamples, self.domain).generate()
 
+    def _optimize_device_rng(self, objective, acq):
+        from ._lib import random_rows
+        n, lower, upper = self._nsamples, self.domain.lower, self.domain.upper
+        seed = dist.broadcast_int(np.random.randint(0, 2 ** 62))
+        rank, ws = dist.world()
+        lo, hi = dist.shard_bounds(n, rank, ws)
+        if hi > lo:
+            v, i = acq.argmax_random(seed, lo, hi - lo, lower, upper)
+            i = i + lo if i >= 0 else -1
+        else:
+            v, i = 0.0, -1
+        best, idx = dist.reduce_pairs(*dist.allgather_pair(v, i))
+        objective.counter += n
+        x = random_rows(seed, idx, 1, lower, upper)
+        return OptimizeResult(x=x, success=True, fun=np.array([[-best]]), nfev=n, message="OK", seed=seed, index=idx)
+
     def _optimize(self, objective):
-        points = self._get_eval_points()
         acq = getattr(objective, 'acquisition', None)
+        if acq is not None and self._device_rng and type(self)._get_eval_points is MCOptimizer._get_eval_points:
+            return self._optimize_device_rng(objective, acq)
+        points = self._get_eval_points()
         if acq is not None:
             # fused route: argmin of -acq == argmax of acq with the same first-occurrence tie-break
             points = dist.broadcast_points(points)

@@ -134,6 +134,18 @@ int gpfo_cells_set(gpfo_ctx* ctx, const double* pf_ext, int n_ext_rows, int R, c
 int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_values, double* out_grads,
               double* best_value, int64_t* best_index);
 
+/* Scores N candidates GENERATED ON THE DEVICE instead of read from memory (no N x D host array, no H2D copy).
+ * Replaces: RandomDesign.generate() + evaluate of MCOptimizer._optimize (design.py:55-70, 83-94; optim.py:152-164).
+ * Row r (global index first_row + r), column d is  lower[d] + (upper[d] - lower[d]) * U  with U in [0,1) from a
+ * counter-based generator keyed by (seed, (first_row + r) * D + d): any shard of rows can be produced independently, and
+ * gpfo_random_rows reproduces the same rows on the host bit for bit (used to return the winning point).
+ * The stream differs from np.random.rand by construction, hence opt-in (MCOptimizer(..., device_rng=True)). */
+int gpfo_eval_random(gpfo_ctx* ctx, uint64_t seed, int64_t first_row, int64_t N, int D, const double* lower,
+                     const double* upper, double* out_values, double* best_value, int64_t* best_index);
+/* Host regeneration of rows [first_row, first_row + n) of the stream above; needs no GPU and no ctx. */
+int gpfo_random_rows(uint64_t seed, int64_t first_row, int64_t n, int D, const double* lower, const double* upper,
+                     double* out);
+
 /* Predictive mean and variance of one GP at N points (original coordinates), un-scaled outputs.
  * Replaces: DataScaler.predict_f (scaling.py:192-197) as used by _setup (ei.py:67, poi.py:60,
  * hvpoi.py:92).  mean, var: N x R, host or device, either may be NULL. */

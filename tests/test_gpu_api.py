@@ -243,3 +243,27 @@ def test_bayesian_optimizer_end_to_end():
                             optimizer=MCOptimizer(domain, 500))
     r2 = bo2.optimize(branin, n_iter=3)
     assert r2.success and bo2.acquisition.data[0].shape[0] == 23
+
+
+def test_mc_optimizer_device_rng():
+    """Opt-in on-device candidate generation: the kernel scores the same rows the host regenerates."""
+    from gpflowopt_b200._lib import random_rows
+    X = _design(20, seed=8)
+    ei = ExpectedImprovement(_gpr(X, parabola2d(X)))
+
+    def inverse_acquisition(x):
+        return -ei.evaluate(np.atleast_2d(x))
+    inverse_acquisition.acquisition = ei
+    np.random.seed(11)
+    r = MCOptimizer(DOMAIN, 50000, device_rng=True).optimize(inverse_acquisition)
+    assert r.success and r.nfev == 50000 and r.x.shape == (1, 2) and r.x in DOMAIN
+    pts = random_rows(r.seed, 0, 50000, DOMAIN.lower, DOMAIN.upper)          # the stream, regenerated on the host
+    scores = ei.evaluate(pts)
+    assert int(np.argmax(scores)) == r.index
+    np.testing.assert_array_equal(r.x, pts[[r.index]])
+    assert float(np.ravel(r.fun)[0]) == -scores[r.index, 0]
+    # device values of generated rows == values of the regenerated rows (bit for bit), any shard offset
+    eng = ei._get_engine()
+    eng.prepare(ei)
+    vals, bv, bi = eng.ctx.eval_random(r.seed, 1234, 3000, DOMAIN.lower, DOMAIN.upper, want_values=True)
+    np.testing.assert_array_equal(vals, scores[1234:4234])

@@ -139,3 +139,17 @@ def test_program_builder_postfix():
     b.scale(None, 0.5)
     assert b.ops == [(_lib.OP_EI, 0, 0, 0), (_lib.OP_POF, 1, 0, 1), (_lib.OP_PROD, 2, 0, 0), (_lib.OP_SCALE, 0, 0, 2)]
     assert b.params == [0.25, 0.0, 0.5]
+
+
+def test_device_candidate_stream_host_regeneration(libgpfo):
+    """gpfo_random_rows (host, no GPU): rows are reproducible, shard-independent and inside the box."""
+    from gpflowopt_b200._lib import random_rows
+    lower, upper = np.array([-5.0, 0.0, 2.0]), np.array([10.0, 15.0, 2.5])
+    a = random_rows(123, 0, 1000, lower, upper)
+    b = np.vstack((random_rows(123, 0, 400, lower, upper), random_rows(123, 400, 600, lower, upper)))
+    assert np.array_equal(a, b)
+    assert np.all(a >= lower) and np.all(a < upper)
+    assert not np.array_equal(a, random_rows(124, 0, 1000, lower, upper))
+    u = (a - lower) / (upper - lower)
+    assert abs(u.mean() - 0.5) < 0.02 and abs(u.var() - 1.0 / 12.0) < 0.01          # uniform first moments
+    assert abs(np.corrcoef(u[:-1, 0], u[1:, 0])[0, 1]) < 0.08                        # no obvious serial correlation
