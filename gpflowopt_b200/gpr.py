@@ -11,13 +11,40 @@ from scipy.optimize import OptimizeResult
 from . import _lib
 
 
+class DataHolder(object):
+    """``.value`` / ``.shape`` view of an array, as GPflow's DataHolder offers."""
+
+    def __init__(self, array):
+        self._array = np.asarray(array, dtype=np.float64)
+
+    @property
+    def value(self):
+        return self._array.copy()
+
+    @property
+    def shape(self):
+        return self._array.shape
+
+
+def _same(a, b):
+    if isinstance(a, DataHolder) and isinstance(b, DataHolder):
+        return a.shape == b.shape and np.array_equal(a._array, b._array)
+    if isinstance(a, (float, int, np.ndarray)) and isinstance(b, (float, int, np.ndarray)):
+        return np.shape(a) == np.shape(b) and bool(np.array_equal(a, b))
+    return a is b
+
+
 class _Versioned(object):
     """Bumps ``version`` on every public attribute assignment so engines can see stale device state."""
 
     def __setattr__(self, key, value):
+        old = self.__dict__.get(key, _Versioned)
         object.__setattr__(self, key, value)
-        if not key.startswith('_') and key != 'version':
-            object.__setattr__(self, 'version', getattr(self, 'version', 0) + 1)
+        if key.startswith('_') or key == 'version':
+            return
+        if old is not _Versioned and _same(old, value):
+            return                       # e.g. set_state() with unchanged hyper-parameters: no re-factorisation
+        object.__setattr__(self, 'version', getattr(self, 'version', 0) + 1)
 
 
 class Stationary(_Versioned):
@@ -52,21 +79,6 @@ class Matern32(Stationary):
 class Gaussian(_Versioned):
     def __init__(self, variance=1.0):
         self.variance = float(variance)
-
-
-class DataHolder(object):
-    """``.value`` / ``.shape`` view of an array, as GPflow's DataHolder offers."""
-
-    def __init__(self, array):
-        self._array = np.asarray(array, dtype=np.float64)
-
-    @property
-    def value(self):
-        return self._array.copy()
-
-    @property
-    def shape(self):
-        return self._array.shape
 
 
 class GPR(_Versioned):
