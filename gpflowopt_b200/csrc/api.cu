@@ -19,6 +19,10 @@ struct GpHost {
     size_t cap_packed_c[2] = {0, 0};
     bool cluster_ready = false;
     int packed_rbc = 0;
+    // small-chunk copies of both block streams for the row-split launches (few candidates)
+    double *dpacked_s = nullptr, *dpacked_kinv_s = nullptr;
+    size_t cap_packed_s = 0, cap_kinv_s = 0;
+    PackGeom geom_s, geom_kinv_s;
     size_t cap_mf = 0, cap_d = 0, cap_r = 0, cap_packed = 0, cap_alpha = 0, cap_kinv = 0;
     GpDev hdev;
     GpDev* ddev = nullptr;
@@ -46,6 +50,7 @@ struct gpfo_ctx {
     double *dcmu = nullptr, *dcva = nullptr; size_t cap_coef = 0;
     double* dgrads = nullptr; size_t cap_grads = 0;
     double* dkx_scratch = nullptr; size_t cap_kx_scratch = 0;
+    double* dpartials = nullptr; size_t cap_partials = 0;    // row-split partial sums
     double* dgen = nullptr;                                  // 2 * GPFO_MAX_DIM doubles: affine map of the device candidate generator
     bool gen_active = false; unsigned long long gen_seed = 0; long long gen_first = 0;
     double* dpart_val = nullptr; long long* dpart_idx = nullptr; int cap_parts = 0;
@@ -135,6 +140,7 @@ static void free_gp(GpHost& g) {
     cudaFree(g.dX); cudaFree(g.dell); cudaFree(g.dXs); cudaFree(g.dxn); cudaFree(g.dY); cudaFree(g.dV);
     cudaFree(g.dL); cudaFree(g.dLinv); cudaFree(g.dpacked); cudaFree(g.ddev);
     cudaFree(g.dalpha); cudaFree(g.dpacked_kinv); cudaFree(g.dpacked_c[0]); cudaFree(g.dpacked_c[1]);
+    cudaFree(g.dpacked_s); cudaFree(g.dpacked_kinv_s);
     g = GpHost();
 }
 
@@ -146,6 +152,7 @@ int gpfo_ctx_destroy(gpfo_ctx* ctx) {
     cudaFree(ctx->dprog); cudaFree(ctx->dpf); cudaFree(ctx->dlb); cudaFree(ctx->dub);
     cudaFree(ctx->dXc); cudaFree(ctx->dvalues); cudaFree(ctx->dmom_mean); cudaFree(ctx->dmom_var);
     cudaFree(ctx->dcmu); cudaFree(ctx->dcva); cudaFree(ctx->dgrads); cudaFree(ctx->dkx_scratch); cudaFree(ctx->dgen);
+    cudaFree(ctx->dpartials);
     cudaFree(ctx->dpart_val); cudaFree(ctx->dpart_idx); cudaFree(ctx->dbest_val); cudaFree(ctx->dbest_idx);
     cudaFree(ctx->dflag);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
@@ -165,12 +172,32 @@ static int effective_variant(const gpfo_ctx* ctx, int64_t N) {
     return (N >= (int64_t)16 * ctx->num_sms) ? 5 : 6;
 }
 
-static int repack(gpfo_ctx* ctx, GpHost& g, int rbc) {
+static PackGeom make_geom(int nrb, int rbc, int dense) {
     PackGeom geom;
-    geom.nrb = g.Mp / 8;
+    geom.nrb = nrb;
     geom.rbc = rbc;
-    geom.nchunks = (geom.nrb + rbc - 1) / rbc;
-    geom.dense = 0;
+    geom.nchunks = (nrb + rbc - 1) / rbc;
+    geom.dense = dense;
+    return geom;
+}
+
+// Row split: with few candidate tiles the rows of the block stream are spread over the SMs (nsplit CTAs per tile).
+// Returns the CTAs per tile, 1 = no split.  Explicit kernel variants (gpfo_set_variant) keep their own launch shape.
+static int split_count(const gpfo_ctx* ctx, int64_t N, int T, int nchunks) {
+    if (ctx->variant != 0) return 1;
+    const int64_t ntiles = (N + T - 1) / T;
+    if (ntiles * 2 > ctx->num_sms || nchunks < 2) return 1;
+    const int ns = (int)(ctx->num_sms / ntiles);
+    return ns < nchunks ? ns : nchunks;
+}
+
+static int ensure_partials(gpfo_ctx* ctx) {
+    CK(ensure(&ctx->dpartials, &ctx->cap_partials, (size_t)ctx->num_sms * 32 * (1 + GPFO_MAX_DIM)));
+    return GPFO_OK;
+}
+
+static int repack(gpfo_ctx* ctx, GpHost& g, int rbc) {
+    const PackGeom geom = make_geom(g.Mp / 8, rbc, 0);
     const size_t need = (size_t)pg_total_blocks(geom) * 64;
     CK(ensure(&g.dpacked, &g.cap_packed, need));
     gpfo_pack_linv(ctx->stream, g.dLinv, g.Mf, geom, g.dpacked);
@@ -211,12 +238,15 @@ static int ensure_kinv(gpfo_ctx* ctx, GpHost& g) {
     geom.rbc = gpfo_contract_grad_rbc();
     geom.nchunks = (geom.nrb + geom.rbc - 1) / geom.rbc;
     geom.dense = 1;
+    g.geom_kinv_s = make_geom(geom.nrb, gpfo_split_rbc(), 1);
     CK(ensure(&g.dalpha, &g.cap_alpha, (size_t)g.Mf * g.R));
     CK(ensure(&g.dpacked_kinv, &g.cap_kinv, (size_t)pg_total_blocks(geom) * 64));
+    CK(ensure(&g.dpacked_kinv_s, &g.cap_kinv_s, (size_t)pg_total_blocks(g.geom_kinv_s) * 64));
     double* dKinv = nullptr;
     CK(cudaMalloc((void**)&dKinv, (size_t)g.Mf * g.Mf * sizeof(double)));
     gpfo_kinv_alpha(st, g.dLinv, g.Mf, g.dV, g.R, dKinv, g.dalpha);
     gpfo_pack_linv(st, dKinv, g.Mf, geom, g.dpacked_kinv);
+    gpfo_pack_linv(st, dKinv, g.Mf, g.geom_kinv_s, g.dpacked_kinv_s);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(dKinv);
@@ -295,6 +325,9 @@ int gpfo_gp_set(gpfo_ctx* ctx, int gp_id, int64_t M64, int D, int R, const doubl
     g.hdev.M = M; g.hdev.Mp = Mp; g.hdev.D = D; g.hdev.R = R; g.hdev.kind = kernel_kind; g.hdev.slot0 = slot0;
     g.hdev.variance = kern_variance;
     g.hdev.Xs = g.dXs; g.hdev.xn = g.dxn; g.hdev.V = g.dV;
+    g.geom_s = make_geom(Mp / 8, gpfo_split_rbc(), 0);
+    CK(ensure(&g.dpacked_s, &g.cap_packed_s, (size_t)pg_total_blocks(g.geom_s) * 64));
+    gpfo_pack_linv(st, g.dLinv, g.Mf, g.geom_s, g.dpacked_s);
     rc = repack(ctx, g, gpfo_contract_rbc(ctx->variant));
     if (rc != GPFO_OK) return rc;
     CK(cudaEventRecord(ctx->ev[1], st));
@@ -522,12 +555,15 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     const int pg_grid = gpfo_program_grad_grid(N, ctx->num_sms);
     int max_parts = grid > hv_grid ? grid : hv_grid;
     if (pg_grid > max_parts) max_parts = pg_grid;
+    if (max_parts < ctx->num_sms) max_parts = ctx->num_sms;      // row-split finish kernel: <= num_sms / 2 * 8 / 128 blocks
     rc = ensure_parts(ctx, max_parts);
     if (rc != GPFO_OK) return rc;
     io.part_val = ctx->dpart_val; io.part_idx = ctx->dpart_idx;
 
-    int launches = 0;
+    int launches = 0, fwd_parts = grid;
     float hot_ms = 0.f;
+    rc = ensure_partials(ctx);
+    if (rc != GPFO_OK) return rc;
     CK(cudaEventRecord(ctx->ev[4], st));
     for (int g = 0; g < ctx->ngps; ++g) {
         EvalIO gio = io;
@@ -547,8 +583,18 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
             gio.kx_scratch_stride = (long long)stride;
         }
         CK(cudaEventRecord(ctx->ev[6], st));
-        if (use_cluster) CK(gpfo_contract3_launch(st, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
-        else CK(gpfo_contract_launch(st, variant, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
+        const int ns = generate ? 1 : split_count(ctx, N, gpfo_split_tile(), ctx->gps[g].geom_s.nchunks);
+        if (ns > 1) {
+            gio.packed_o = ctx->gps[g].dpacked_s; gio.geom_o = ctx->gps[g].geom_s;
+            gio.nsplit = ns; gio.partials = ctx->dpartials;
+            CK(gpfo_contract_split_launch(st, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, D));
+            ++launches;
+            fwd_parts = (int)((N + 127) / 128);
+        } else {
+            if (use_cluster) CK(gpfo_contract3_launch(st, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
+            else CK(gpfo_contract_launch(st, variant, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
+            fwd_parts = grid;
+        }
         CK(cudaEventRecord(ctx->ev[7], st));
         ++launches;
         if (ctx->ngps > 1) {                 // per-GP timing needs a sync only when events are reused
@@ -556,7 +602,7 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
             float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); hot_ms += ms;
         }
     }
-    int nparts = grid;
+    int nparts = fwd_parts;
     if (hv) {
         EvalIO hio = io;
         hio.run_program = 1;
@@ -581,7 +627,19 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
         for (int g = 0; g < ctx->ngps; ++g) {
             EvalIO gio = io;
             gio.grad_accumulate = g > 0 ? 1 : 0;
-            CK(gpfo_contract_grad_launch(st, ctx->gps[g].kind, ctx->gps[g].ddev, gio, ggrid, D));
+            const GpHost& gh = ctx->gps[g];
+            const int ns_small = split_count(ctx, N, gpfo_split_tile(), gh.geom_kinv_s.nchunks);
+            const int ns_wide = ns_small > 1 ? 1 : split_count(ctx, N, 32, gh.hdev.geom_kinv.nchunks);
+            if (ns_small > 1 || ns_wide > 1) {
+                gio.partials = ctx->dpartials;
+                gio.nsplit = ns_small > 1 ? ns_small : ns_wide;
+                gio.packed_o = ns_small > 1 ? gh.dpacked_kinv_s : gh.dpacked_kinv;
+                gio.geom_o = ns_small > 1 ? gh.geom_kinv_s : gh.hdev.geom_kinv;
+                CK(gpfo_contract_grad_split_launch(st, gh.kind, gh.ddev, gio, D, ns_small > 1 ? 0 : 1));
+                ++launches;
+            } else {
+                CK(gpfo_contract_grad_launch(st, gh.kind, gh.ddev, gio, ggrid, D));
+            }
             ++launches;
         }
     }
@@ -682,7 +740,15 @@ int gpfo_predict(gpfo_ctx* ctx, int gp_id, const double* X, int64_t N, int D, do
     io.X = dX; io.N = N; io.mom_mean = ctx->dmom_mean; io.mom_var = ctx->dmom_var;
     io.part_val = ctx->dpart_val; io.part_idx = ctx->dpart_idx;
     io.write_moments = 1; io.run_program = 0;
-    CK(gpfo_contract_launch(st, variant, g.kind, g.ddev, ctx->dprog, io, grid, D));
+    const int ns = split_count(ctx, N, gpfo_split_tile(), g.geom_s.nchunks);
+    if (ns > 1) {
+        rc = ensure_partials(ctx);
+        if (rc != GPFO_OK) return rc;
+        io.packed_o = g.dpacked_s; io.geom_o = g.geom_s; io.nsplit = ns; io.partials = ctx->dpartials;
+        CK(gpfo_contract_split_launch(st, g.kind, g.ddev, ctx->dprog, io, D));
+    } else {
+        CK(gpfo_contract_launch(st, variant, g.kind, g.ddev, ctx->dprog, io, grid, D));
+    }
     // [slot][N] -> N x R
     for (int r = 0; r < g.R; ++r) {
         const size_t off = (size_t)(g.slot0 + r) * N;

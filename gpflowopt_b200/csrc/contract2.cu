@@ -45,8 +45,14 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     const double* __restrict__ Xs = gp.Xs;
     const double* __restrict__ xn = gp.xn;
     const double* __restrict__ Vv = gp.V;
-    const PackGeom geom = GRADM ? gp.geom_kinv : gp.geom;
-    const double* __restrict__ packed = GRADM ? gp.packed_kinv : gp.packed;
+    // ABL bit 16 = ROW SPLIT (few candidates): CTA (tile, split) takes chunks split, split + nsplit, ... of the block stream
+    // and leaves its partial sums in io.partials; split_final_*_kernel adds them in a fixed order and runs the epilogue.
+    // The stream layout may differ from the GP's default one (smaller chunks), so it travels in the launch record.
+    constexpr bool SPLIT = (ABL & 16) != 0;
+    const PackGeom geom = SPLIT ? io.geom_o : (GRADM ? gp.geom_kinv : gp.geom);
+    const double* __restrict__ packed = SPLIT ? io.packed_o : (GRADM ? gp.packed_kinv : gp.packed);
+    const int nsplit = SPLIT ? io.nsplit : 1;
+    const int split = SPLIT ? (int)(blockIdx.x % nsplit) : 0;
     double* myring = ring + (size_t)w * C::RING_DOUBLES_PER_WARP + 2 * lane;
     const unsigned myring_s = (unsigned)__cvta_generic_to_shared(myring);     // same location, shared-window address
 
@@ -63,7 +69,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     __syncthreads();
 
     const int64_t ntiles = (io.N + T - 1) / T;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int64_t tile = blockIdx.x / nsplit; tile < ntiles; tile += gridDim.x / nsplit) {
         const int64_t n0 = tile * T;
         __syncthreads();
         if (tid < T * (1 + RMAX)) tot[tid] = 0.0;
@@ -112,7 +118,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
         // scratch; later chunks copy their off-diagonal groups back asynchronously, two groups ahead of use.
         constexpr bool SCR = (ABL & 8) != 0;             // compile-time: the plain variants carry no scratch code
         double* const scratch = SCR ? io.kx_scratch + (size_t)blockIdx.x * io.kx_scratch_stride : nullptr;
-        for (int pi = 0; pi < geom.nchunks; ++pi) {
+        for (int pi = split; pi < geom.nchunks; pi += nsplit) {
             const int p = pi;
             const int nr = pg_chunk_rows(geom, p);
             const int row0 = p * geom.rbc;                // first row block of this chunk
@@ -386,6 +392,12 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             __syncthreads();
             if (TIM) t_red += clock64() - t_mark;
         }
+        if (SPLIT) {
+            double* part = io.partials + ((size_t)tile * nsplit + split) * (size_t)(T * (GRADM ? 1 + D : 1 + RMAX));
+            if (GRADM) for (int e = tid; e < T * (1 + D); e += C::THREADS) part[e] = gsum[e];
+            else if (tid < T * (1 + RMAX)) part[tid] = tot[tid];
+            continue;
+        }
         if (GRADM) {
             // d acq / d x_d = 2 a_d / l_d * (xs_d * sum_i u_i - sum_i u_i Xs_id)       (d r^2 / d x_d = 2 (xs_d - Xs_id) a_d / l_d)
             for (int e = tid; e < T * D; e += C::THREADS) {
@@ -428,6 +440,64 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     }
 }
 
+// Row-split finish, forward: sums the per-split partials of every candidate in split order, then the usual epilogue
+// (moments, acquisition program, argmax).  One warp per 32 candidates, T = candidates per tile of the split launch.
+__global__ void __launch_bounds__(128)
+split_final_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ prog, EvalIO io, int T) {
+    __shared__ double sv[4];
+    __shared__ long long si[4];
+    const GpDev& gp = *gpp;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t n0 = (int64_t)blockIdx.x * 128 + 32 * w, n = n0 + lane;
+    double ss = 0.0, mv[RMAX];
+#pragma unroll
+    for (int ro = 0; ro < RMAX; ++ro) mv[ro] = 0.0;
+    if (n < io.N) {
+        const int64_t tile = n / T;
+        const int ln = (int)(n - tile * T);
+        for (int s = 0; s < io.nsplit; ++s) {
+            const double* p = io.partials + (((size_t)tile * io.nsplit + s) * T + ln) * (1 + RMAX);
+            ss += p[0];
+#pragma unroll
+            for (int ro = 0; ro < RMAX; ++ro) mv[ro] += p[1 + ro];
+        }
+    }
+    double best_v = 0.0;
+    long long best_i = -1;
+    gpfo_tile_epilogue<32>(gp, prog, io, n0, lane, ss, mv, best_v, best_i);
+    if (lane == 0) { sv[w] = best_v; si[w] = best_i; }
+    __syncthreads();
+    if (threadIdx.x == 0 && io.run_program) {
+        double bv = sv[0];
+        long long bi = si[0];
+        for (int k = 1; k < 4; ++k)
+            if (gpfo_better(sv[k], si[k], bv, bi)) { bv = sv[k]; bi = si[k]; }
+        io.part_val[blockIdx.x] = bv;
+        io.part_idx[blockIdx.x] = bi;
+    }
+}
+
+// Row-split finish, gradient pass: d acq / d x_d from the summed (sum_i u_i, sum_i u_i Xs_id) partials.
+__global__ void __launch_bounds__(128)
+split_final_grad_kernel(const GpDev* __restrict__ gpp, EvalIO io, int T, int D) {
+    const GpDev& gp = *gpp;
+    const int64_t e = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (e >= io.N * D) return;
+    const int64_t n = e / D;
+    const int d = (int)(e - n * D);
+    const int64_t tile = n / T;
+    const int ln = (int)(n - tile * T);
+    double s0 = 0.0, sd = 0.0;
+    for (int s = 0; s < io.nsplit; ++s) {
+        const double* p = io.partials + (((size_t)tile * io.nsplit + s) * T + ln) * (size_t)(1 + D);
+        s0 += p[0];
+        sd += p[1 + d];
+    }
+    const double xt = __dadd_rn(__dmul_rn(io.X[e], gp.in_scale[d]), gp.in_shift[d]);
+    const double g = 2.0 * gp.in_scale[d] / gp.ell[d] * ((xt / gp.ell[d]) * s0 - sd);
+    io.grads[e] = io.grad_accumulate ? io.grads[e] + g : g;
+}
+
 template <int NW, int RBW, int NB, int S, int KIND, int ABL>
 static cudaError_t launch2_kind(cudaStream_t st, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io, int grid, int D) {
     using C = Contract2Cfg<NW, RBW, NB, S>;
@@ -468,6 +538,30 @@ cudaError_t gpfo_contract2_launch(cudaStream_t st, int variant, int kind, const 
         case 43: return launch2<16, 4, 4, 4, 3>(st, kind, d_gp, d_prog, io, grid, D);
         default: return launch2<16, 4, 4, 4>(st, kind, d_gp, d_prog, io, grid, D);
     }
+}
+
+// ---- row-split launches (few candidates: the rows of the block stream are spread over the SMs) ----------------------
+// forward: T = 8 candidates per tile, 128-row chunks; grid = tiles * nsplit, then the finish kernel
+int gpfo_split_rbc() { return 16; }
+int gpfo_split_tile() { return 8; }
+cudaError_t gpfo_contract_split_launch(cudaStream_t st, int kind, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io,
+                                       int D) {
+    const int64_t ntiles = (io.N + 7) / 8;
+    cudaError_t e = launch2<16, 1, 1, 4, 16>(st, kind, d_gp, d_prog, io, (int)(ntiles * io.nsplit), D);
+    if (e != cudaSuccess) return e;
+    split_final_kernel<<<(unsigned)((io.N + 127) / 128), 128, 0, st>>>(d_gp, d_prog, io, 8);
+    return cudaGetLastError();
+}
+// gradient pass: `wide` = 0: T = 8, 128-row chunks (its own dense stream layout); 1: T = 32 over the default K^-1 layout
+cudaError_t gpfo_contract_grad_split_launch(cudaStream_t st, int kind, const GpDev* d_gp, EvalIO io, int D, int wide) {
+    const int T = wide ? 32 : 8;
+    const int64_t ntiles = (io.N + T - 1) / T;
+    const int grid = (int)(ntiles * io.nsplit);
+    cudaError_t e = wide ? launch2<16, 4, 4, 4, 4 + 16>(st, kind, d_gp, nullptr, io, grid, D)
+                         : launch2<16, 1, 1, 4, 4 + 16>(st, kind, d_gp, nullptr, io, grid, D);
+    if (e != cudaSuccess) return e;
+    split_final_grad_kernel<<<(unsigned)((io.N * D + 127) / 128), 128, 0, st>>>(d_gp, io, T, D);
+    return cudaGetLastError();
 }
 
 // gradient pass launcher (dense K^-1 stream; T = 32 candidates per tile, 512-row chunks)

@@ -137,6 +137,11 @@ struct EvalIO {
     const double* gen_b;
     unsigned long long gen_seed;
     long long gen_first;           // global index of this call's row 0 (lets every rank generate its own shard)
+    // row-split launches (few candidates): block stream + layout of this launch, CTAs per tile, per-(tile, split) partial sums
+    const double* packed_o;
+    PackGeom geom_o;
+    int nsplit;
+    double* partials;              // forward: [tile][split][T][1+RMAX]; gradient pass: [tile][split][T][1+D]
 };
 
 // Counter-based uniform generator shared by the device prologue and the host regeneration (gpfo_random_rows):
@@ -331,3 +336,8 @@ int gpfo_program_grad_grid(int64_t N, int num_sms);
 cudaError_t gpfo_contract_grad_launch(cudaStream_t st, int kind, const GpDev* d_gp, EvalIO io, int grid, int D);
 int gpfo_contract_grad_grid(int64_t N, int num_sms);
 int gpfo_contract_grad_rbc();
+// row-split launches for few candidates (contract2.cu): contraction over a slice of the rows per CTA + a finish kernel
+int gpfo_split_rbc();
+int gpfo_split_tile();
+cudaError_t gpfo_contract_split_launch(cudaStream_t st, int kind, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io, int D);
+cudaError_t gpfo_contract_grad_split_launch(cudaStream_t st, int kind, const GpDev* d_gp, EvalIO io, int D, int wide);

@@ -440,3 +440,35 @@ def test_large_candidate_batch_device_resident(ctx):
     tail = Xd[N - 1000:].cpu().numpy()
     ref = oacq.Leaf('ei', g, -0.3).value(tail)
     assert_parity(vd[N - 1000:].cpu().numpy()[:, None], ref, what="tail of a 1e7 batch")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# row-split launches (few candidates: the rows of the block stream are spread over the SMs, partial sums added by a
+# finish kernel).  Covers every split shape: forward + gradient small tiles (N <= 592), wide gradient tiles
+# (592 < N <= 2368), partial last chunk (M % 128 != 0), multi-output, and agreement with the un-split kernel.
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,D", [(300, 3), (1100, 8), (2048, 8)])
+def test_row_split_small_batches(ctx, M, D):
+    g, lo, up = _model(M, D, "matern52", scaled=True)
+    upload_oracle_gp(ctx, 0, g)
+    fmin = float(np.min(g.predict(g.input_transform.backward(g.Xs))[0])) + 0.05
+    ctx.program_set([[_lib.OP_EI, 0, 0, 0]], [fmin])
+    leaf = oacq.Leaf('ei', g, fmin)
+    for N in (1, 7, 8, 9, 100, 592, 593, 1500):
+        Xc = _cands(N, D, lo, up, seed=N)
+        vals, grads, bv, bi = ctx.eval(Xc, want_grads=True)
+        rv, rg = leaf.value_and_grad(Xc)
+        assert_parity(vals, rv, what="split value M=%d N=%d" % (M, N))
+        assert_parity(grads, rg, what="split grad M=%d N=%d" % (M, N))
+        assert bi == int(np.argmax(vals)) and bv == vals[bi, 0]
+        mean, var = ctx.predict(0, Xc, 1)
+        rm, rvv = g.predict(Xc)
+        assert_parity(mean, rm, what="split predict mean")
+        assert_parity(var, rvv, scale=g.variance / g.output_transform.A[0, 0] ** 2, what="split predict var")
+        ctx.set_variant(6)                    # explicit variant: same inputs through the un-split kernels
+        try:
+            v6, g6, _, i6 = ctx.eval(Xc, want_grads=True)
+        finally:
+            ctx.set_variant(0)
+        assert_parity(vals, v6, tol=1e-12, what="split vs un-split value")
+        assert_parity(grads, g6, tol=1e-11, what="split vs un-split grad")
