@@ -23,6 +23,10 @@ struct GpHost {
     double *dpacked_s = nullptr, *dpacked_kinv_s = nullptr;
     size_t cap_packed_s = 0, cap_kinv_s = 0;
     PackGeom geom_s, geom_kinv_s;
+    // reversed transposed triangular stream of L^-1 for the stored-A backward pass (large gradient batches), built lazily
+    double* dpacked_rt = nullptr; size_t cap_packed_rt = 0;
+    PackGeom geom_rt;
+    bool rt_ready = false;
     size_t cap_mf = 0, cap_d = 0, cap_r = 0, cap_packed = 0, cap_alpha = 0, cap_kinv = 0;
     GpDev hdev;
     GpDev* ddev = nullptr;
@@ -51,6 +55,7 @@ struct gpfo_ctx {
     double* dgrads = nullptr; size_t cap_grads = 0;
     double* dkx_scratch = nullptr; size_t cap_kx_scratch = 0;
     double* dpartials = nullptr; size_t cap_partials = 0;    // row-split partial sums
+    double* da_scratch = nullptr; size_t cap_a_scratch = 0;  // stored-A gradient pass: A = L^-1 Kx of one slab of tiles
     double* dgen = nullptr;                                  // 2 * GPFO_MAX_DIM doubles: affine map of the device candidate generator
     bool gen_active = false; unsigned long long gen_seed = 0; long long gen_first = 0;
     double* dpart_val = nullptr; long long* dpart_idx = nullptr; int cap_parts = 0;
@@ -140,7 +145,7 @@ static void free_gp(GpHost& g) {
     cudaFree(g.dX); cudaFree(g.dell); cudaFree(g.dXs); cudaFree(g.dxn); cudaFree(g.dY); cudaFree(g.dV);
     cudaFree(g.dL); cudaFree(g.dLinv); cudaFree(g.dpacked); cudaFree(g.ddev);
     cudaFree(g.dalpha); cudaFree(g.dpacked_kinv); cudaFree(g.dpacked_c[0]); cudaFree(g.dpacked_c[1]);
-    cudaFree(g.dpacked_s); cudaFree(g.dpacked_kinv_s);
+    cudaFree(g.dpacked_s); cudaFree(g.dpacked_kinv_s); cudaFree(g.dpacked_rt);
     g = GpHost();
 }
 
@@ -152,7 +157,7 @@ int gpfo_ctx_destroy(gpfo_ctx* ctx) {
     cudaFree(ctx->dprog); cudaFree(ctx->dpf); cudaFree(ctx->dlb); cudaFree(ctx->dub);
     cudaFree(ctx->dXc); cudaFree(ctx->dvalues); cudaFree(ctx->dmom_mean); cudaFree(ctx->dmom_var);
     cudaFree(ctx->dcmu); cudaFree(ctx->dcva); cudaFree(ctx->dgrads); cudaFree(ctx->dkx_scratch); cudaFree(ctx->dgen);
-    cudaFree(ctx->dpartials);
+    cudaFree(ctx->dpartials); cudaFree(ctx->da_scratch);
     cudaFree(ctx->dpart_val); cudaFree(ctx->dpart_idx); cudaFree(ctx->dbest_val); cudaFree(ctx->dbest_idx);
     cudaFree(ctx->dflag);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
@@ -259,6 +264,24 @@ static int ensure_kinv(gpfo_ctx* ctx, GpHost& g) {
     return GPFO_OK;
 }
 
+// Stored-A backward pass state: block stream of the reversed transpose of L^-1 (built on first use).
+static int ensure_rt(gpfo_ctx* ctx, GpHost& g) {
+    if (g.rt_ready) return GPFO_OK;
+    cudaStream_t st = ctx->stream;
+    g.geom_rt = make_geom(g.Mp / 8, gpfo_contract_bwd_rbc(), 0);
+    CK(ensure(&g.dpacked_rt, &g.cap_packed_rt, (size_t)pg_total_blocks(g.geom_rt) * 64));
+    double* tmp = nullptr;
+    CK(cudaMalloc((void**)&tmp, (size_t)g.Mf * g.Mf * sizeof(double)));
+    gpfo_reverse_transpose(st, g.dLinv, g.Mf, g.Mp, tmp);
+    gpfo_pack_linv(st, tmp, g.Mf, g.geom_rt, g.dpacked_rt);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(ctx, GPFO_ERR_CUDA, std::string("ensure_rt: ") + cudaGetErrorString(e));
+    g.rt_ready = true;
+    return GPFO_OK;
+}
+
 int gpfo_gp_set(gpfo_ctx* ctx, int gp_id, int64_t M64, int D, int R, const double* X, const double* Y,
                 int kernel_kind, int ard, const double* lengthscales, double kern_variance, double noise_variance,
                 const double* in_scale, const double* in_shift, const double* out_scale, const double* out_shift,
@@ -294,6 +317,7 @@ int gpfo_gp_set(gpfo_ctx* ctx, int gp_id, int64_t M64, int D, int R, const doubl
     g.valid = false;
     g.kinv_ready = false;
     g.cluster_ready = false;
+    g.rt_ready = false;
     g.M = M; g.Mp = Mp; g.Mf = Mf; g.D = D; g.R = R; g.kind = kernel_kind; g.slot0 = slot0;
     memset(&g.hdev, 0, sizeof(GpDev));
     double ell[GPFO_MAX_DIM];
@@ -513,9 +537,15 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     const bool need_mom = hv || ctx->ngps > 1 || want_grad;
     if (want_grad)
         for (int g = 0; g < ctx->ngps; ++g) { rc = ensure_kinv(ctx, ctx->gps[g]); if (rc != GPFO_OK) return rc; }
+    // large gradient batches take the stored-A path (GPFO_GRAD_DENSE=1 keeps the dense K^-1 pass, for comparisons)
+    const char* env_dense = getenv("GPFO_GRAD_DENSE");
+    const bool astore = want_grad && variant == 12 && gpfo_contract_bwd_smem(D) <= (size_t)227 * 1024 &&
+                        !(env_dense && atoi(env_dense) != 0);
+    if (astore)
+        for (int g = 0; g < ctx->ngps; ++g) { rc = ensure_rt(ctx, ctx->gps[g]); if (rc != GPFO_OK) return rc; }
     EvalIO io;
     memset(&io, 0, sizeof(io));
-    io.X = dX; io.N = N;
+    io.X = dX; io.N = N; io.mstride = N;
     if (generate) {
         io.gen_A = ctx->dgen; io.gen_b = ctx->dgen + GPFO_MAX_DIM;
         io.gen_seed = ctx->gen_seed; io.gen_first = ctx->gen_first;
@@ -565,82 +595,170 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     rc = ensure_partials(ctx);
     if (rc != GPFO_OK) return rc;
     CK(cudaEventRecord(ctx->ev[4], st));
-    for (int g = 0; g < ctx->ngps; ++g) {
-        EvalIO gio = io;
-        gio.write_moments = need_mom ? 1 : 0;
-        gio.run_program = (!hv && !want_grad && g == ctx->ngps - 1) ? 1 : 0;
-        if (variant == 11 || variant == 12 || (variant >= 120 && variant <= 129)) {   // 12x: profiling builds of 12
-            // per-CTA K(X*,X) scratch: one slot per (training point, candidate of the tile), rounded up to whole groups
-            const size_t cols = ((size_t)ctx->gps[g].Mp + 127) / 128 * 128;
-            const size_t stride = cols * (size_t)gpfo_contract_tile(variant);
-            CK(ensure(&ctx->dkx_scratch, &ctx->cap_kx_scratch, stride * (size_t)grid));
-            gio.kx_scratch = ctx->dkx_scratch;
-            if (variant == 127) {          // profiling build: phase counters land at the start of the values buffer
-                CK(ensure(&ctx->dvalues, &ctx->cap_values, (size_t)(N > 65536 ? N : 65536)));
-                gio.debug = reinterpret_cast<long long*>(ctx->dvalues);
-                gio.values = nullptr;
-            }
-            gio.kx_scratch_stride = (long long)stride;
-        }
-        CK(cudaEventRecord(ctx->ev[6], st));
-        const int ns = generate ? 1 : split_count(ctx, N, gpfo_split_tile(), ctx->gps[g].geom_s.nchunks);
-        if (ns > 1) {
-            gio.packed_o = ctx->gps[g].dpacked_s; gio.geom_o = ctx->gps[g].geom_s;
-            gio.nsplit = ns; gio.partials = ctx->dpartials;
-            CK(gpfo_contract_split_launch(st, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, D));
-            ++launches;
-            fwd_parts = (int)((N + 127) / 128);
-        } else {
-            if (use_cluster) CK(gpfo_contract3_launch(st, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
-            else CK(gpfo_contract_launch(st, variant, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
-            fwd_parts = grid;
-        }
-        CK(cudaEventRecord(ctx->ev[7], st));
-        ++launches;
-        if (ctx->ngps > 1) {                 // per-GP timing needs a sync only when events are reused
-            CK(cudaEventSynchronize(ctx->ev[7]));
-            float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); hot_ms += ms;
-        }
-    }
-    int nparts = fwd_parts;
-    if (hv) {
-        EvalIO hio = io;
-        hio.run_program = 1;
-        int slot_first = 0;
+    int nparts = grid;
+    int slot_first = 0;
+    if (hv)
         for (int i = 0; i < ctx->hprog.nops; ++i)
             if (ctx->hprog.ops[4 * i] == GPFO_OP_HVPOI) {
                 slot_first = ctx->hprog.ops[4 * i + 1];
                 if (ctx->hprog.ops[4 * i + 2] != ctx->cells.R)
                     return fail(ctx, GPFO_ERR_BAD_SHAPE, "HVPoI objective count does not match the cell tables");
             }
-        CK(gpfo_hvpoi_launch(st, ctx->dprog, ctx->cells, hio, hv_grid, slot_first, want_grad ? 1 : 0));
-        ++launches;
-        nparts = hv_grid;
-    } else if (want_grad) {
-        CK(gpfo_program_grad_launch(st, ctx->dprog, io, pg_grid));
-        ++launches;
-        nparts = pg_grid;
-    }
-    if (want_grad) {
-        // chain rule through each GP: W = K^-1 Kx on DMMA, then the (1+D)-wide reduction over the training points
-        const int ggrid = gpfo_contract_grad_grid(N, ctx->num_sms);
+    if (astore) {
+        // ---- large gradient batch: forward launches park A = L^-1 Kx, backward launches contract it with the reversed
+        // transposed stream (2 M^2 flop per candidate and GP in total instead of 3 M^2).  A lives in a bounded scratch, so
+        // the batch is processed in slabs of whole tiles: forward (all GPs) -> program partials -> backward (all GPs).
+        const int Tt = gpfo_contract_bwd_tile();
+        const int64_t ntiles = (N + Tt - 1) / Tt;
+        size_t per_tile = 0;                                   // doubles of A per tile, all GPs
+        for (int g = 0; g < ctx->ngps; ++g) per_tile += (size_t)gpfo_contract_astore_stride(ctx->gps[g].Mp / 8);
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        size_t budget = (free_b + ctx->cap_a_scratch * sizeof(double)) / 4;
+        if (budget > ((size_t)8 << 30)) budget = (size_t)8 << 30;
+        if (const char* mb = getenv("GPFO_ASTORE_BUDGET_MB")) budget = (size_t)atoll(mb) << 20;      // tests: force several slabs
+        int64_t slab_tiles = (int64_t)(budget / (per_tile * sizeof(double)));
+        if (slab_tiles < ctx->num_sms) slab_tiles = ctx->num_sms;
+        if (slab_tiles > ntiles) slab_tiles = ntiles;
+        CK(ensure(&ctx->da_scratch, &ctx->cap_a_scratch, (size_t)slab_tiles * per_tile));
+        const int64_t nslabs = (ntiles + slab_tiles - 1) / slab_tiles;
+        const int sgrid = (int)(slab_tiles < ctx->num_sms ? slab_tiles : ctx->num_sms);
+        const int64_t slab_n = slab_tiles * Tt;
+        const int ppg = hv ? gpfo_hvpoi_grid(slab_n, ctx->num_sms) : gpfo_program_grad_grid(slab_n, ctx->num_sms);
+        rc = ensure_parts(ctx, (int)(nslabs * ppg));
+        if (rc != GPFO_OK) return rc;
+        io.part_val = ctx->dpart_val; io.part_idx = ctx->dpart_idx;
+        size_t kx_need = 0;
         for (int g = 0; g < ctx->ngps; ++g) {
-            EvalIO gio = io;
-            gio.grad_accumulate = g > 0 ? 1 : 0;
-            const GpHost& gh = ctx->gps[g];
-            const int ns_small = split_count(ctx, N, gpfo_split_tile(), gh.geom_kinv_s.nchunks);
-            const int ns_wide = ns_small > 1 ? 1 : split_count(ctx, N, 32, gh.hdev.geom_kinv.nchunks);
-            if (ns_small > 1 || ns_wide > 1) {
-                gio.partials = ctx->dpartials;
-                gio.nsplit = ns_small > 1 ? ns_small : ns_wide;
-                gio.packed_o = ns_small > 1 ? gh.dpacked_kinv_s : gh.dpacked_kinv;
-                gio.geom_o = ns_small > 1 ? gh.geom_kinv_s : gh.hdev.geom_kinv;
-                CK(gpfo_contract_grad_split_launch(st, gh.kind, gh.ddev, gio, D, ns_small > 1 ? 0 : 1));
+            const size_t cols = ((size_t)ctx->gps[g].Mp + 127) / 128 * 128;
+            if (cols * Tt * (size_t)sgrid > kx_need) kx_need = cols * Tt * (size_t)sgrid;
+        }
+        CK(ensure(&ctx->dkx_scratch, &ctx->cap_kx_scratch, kx_need));
+        nparts = 0;
+        for (int64_t k = 0; k < nslabs; ++k) {
+            const int64_t n0 = k * slab_n;
+            const int64_t ns = (N - n0 < slab_n) ? N - n0 : slab_n;
+            const int64_t st_tiles = (ns + Tt - 1) / Tt;
+            const int g_s = (int)(st_tiles < sgrid ? st_tiles : sgrid);
+            EvalIO sio = io;
+            sio.X = io.X + (size_t)n0 * D; sio.N = ns; sio.idx0 = n0;
+            sio.mom_mean = io.mom_mean + n0; sio.mom_var = io.mom_var + n0;
+            sio.cmu = io.cmu + n0; sio.cva = io.cva + n0;
+            if (io.values) sio.values = io.values + n0;
+            sio.grads = io.grads + (size_t)n0 * D;
+            sio.part_val = io.part_val + nparts; sio.part_idx = io.part_idx + nparts;
+            size_t a_off = 0;
+            for (int g = 0; g < ctx->ngps; ++g) {
+                const GpHost& gh = ctx->gps[g];
+                EvalIO gio = sio;
+                gio.write_moments = 1; gio.run_program = 0;
+                gio.kx_scratch = ctx->dkx_scratch;
+                gio.kx_scratch_stride = (long long)(((size_t)gh.Mp + 127) / 128 * 128 * Tt);
+                gio.a_scratch = ctx->da_scratch + a_off;
+                gio.a_stride = gpfo_contract_astore_stride(gh.Mp / 8);
+                a_off += (size_t)slab_tiles * (size_t)gio.a_stride;
+                if (k == 0 && g == 0) CK(cudaEventRecord(ctx->ev[6], st));
+                CK(gpfo_contract_astore_launch(st, gh.kind, gh.ddev, ctx->dprog, gio, g_s, D));
+                if (k == 0 && g == 0) CK(cudaEventRecord(ctx->ev[7], st));
                 ++launches;
+            }
+            int parts_k;
+            if (hv) {
+                EvalIO hio = sio;
+                hio.run_program = 1;
+                parts_k = gpfo_hvpoi_grid(ns, ctx->num_sms);
+                CK(gpfo_hvpoi_launch(st, ctx->dprog, ctx->cells, hio, parts_k, slot_first, 1));
             } else {
-                CK(gpfo_contract_grad_launch(st, gh.kind, gh.ddev, gio, ggrid, D));
+                parts_k = gpfo_program_grad_grid(ns, ctx->num_sms);
+                CK(gpfo_program_grad_launch(st, ctx->dprog, sio, parts_k));
             }
             ++launches;
+            nparts += parts_k;
+            a_off = 0;
+            for (int g = 0; g < ctx->ngps; ++g) {
+                const GpHost& gh = ctx->gps[g];
+                EvalIO gio = sio;
+                gio.grad_accumulate = g > 0 ? 1 : 0;
+                gio.packed_o = gh.dpacked_rt; gio.geom_o = gh.geom_rt;
+                gio.a_scratch = ctx->da_scratch + a_off;
+                gio.a_stride = gpfo_contract_astore_stride(gh.Mp / 8);
+                a_off += (size_t)slab_tiles * (size_t)gio.a_stride;
+                CK(gpfo_contract_bwd_launch(st, gh.kind, gh.ddev, gio, g_s, D));
+                ++launches;
+            }
+        }
+        if (ctx->ngps > 1) { CK(cudaEventSynchronize(ctx->ev[7])); float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); hot_ms = ms; }
+    } else {
+        for (int g = 0; g < ctx->ngps; ++g) {
+            EvalIO gio = io;
+            gio.write_moments = need_mom ? 1 : 0;
+            gio.run_program = (!hv && !want_grad && g == ctx->ngps - 1) ? 1 : 0;
+            if (variant == 11 || variant == 12 || (variant >= 120 && variant <= 129)) {   // 12x: profiling builds of 12
+                // per-CTA K(X*,X) scratch: one slot per (training point, candidate of the tile), rounded up to whole groups
+                const size_t cols = ((size_t)ctx->gps[g].Mp + 127) / 128 * 128;
+                const size_t stride = cols * (size_t)gpfo_contract_tile(variant);
+                CK(ensure(&ctx->dkx_scratch, &ctx->cap_kx_scratch, stride * (size_t)grid));
+                gio.kx_scratch = ctx->dkx_scratch;
+                if (variant == 127) {          // profiling build: phase counters land at the start of the values buffer
+                    CK(ensure(&ctx->dvalues, &ctx->cap_values, (size_t)(N > 65536 ? N : 65536)));
+                    gio.debug = reinterpret_cast<long long*>(ctx->dvalues);
+                    gio.values = nullptr;
+                }
+                gio.kx_scratch_stride = (long long)stride;
+            }
+            CK(cudaEventRecord(ctx->ev[6], st));
+            const int ns = generate ? 1 : split_count(ctx, N, gpfo_split_tile(), ctx->gps[g].geom_s.nchunks);
+            if (ns > 1) {
+                gio.packed_o = ctx->gps[g].dpacked_s; gio.geom_o = ctx->gps[g].geom_s;
+                gio.nsplit = ns; gio.partials = ctx->dpartials;
+                CK(gpfo_contract_split_launch(st, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, D));
+                ++launches;
+                fwd_parts = (int)((N + 127) / 128);
+            } else {
+                if (use_cluster) CK(gpfo_contract3_launch(st, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
+                else CK(gpfo_contract_launch(st, variant, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
+                fwd_parts = grid;
+            }
+            CK(cudaEventRecord(ctx->ev[7], st));
+            ++launches;
+            if (ctx->ngps > 1) {                 // per-GP timing needs a sync only when events are reused
+                CK(cudaEventSynchronize(ctx->ev[7]));
+                float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); hot_ms += ms;
+            }
+        }
+        nparts = fwd_parts;
+        if (hv) {
+            EvalIO hio = io;
+            hio.run_program = 1;
+            CK(gpfo_hvpoi_launch(st, ctx->dprog, ctx->cells, hio, hv_grid, slot_first, want_grad ? 1 : 0));
+            ++launches;
+            nparts = hv_grid;
+        } else if (want_grad) {
+            CK(gpfo_program_grad_launch(st, ctx->dprog, io, pg_grid));
+            ++launches;
+            nparts = pg_grid;
+        }
+        if (want_grad) {
+            // chain rule through each GP: W = K^-1 Kx on DMMA, then the (1+D)-wide reduction over the training points
+            const int ggrid = gpfo_contract_grad_grid(N, ctx->num_sms);
+            for (int g = 0; g < ctx->ngps; ++g) {
+                EvalIO gio = io;
+                gio.grad_accumulate = g > 0 ? 1 : 0;
+                const GpHost& gh = ctx->gps[g];
+                const int ns_small = split_count(ctx, N, gpfo_split_tile(), gh.geom_kinv_s.nchunks);
+                const int ns_wide = ns_small > 1 ? 1 : split_count(ctx, N, 32, gh.hdev.geom_kinv.nchunks);
+                if (ns_small > 1 || ns_wide > 1) {
+                    gio.partials = ctx->dpartials;
+                    gio.nsplit = ns_small > 1 ? ns_small : ns_wide;
+                    gio.packed_o = ns_small > 1 ? gh.dpacked_kinv_s : gh.dpacked_kinv;
+                    gio.geom_o = ns_small > 1 ? gh.geom_kinv_s : gh.hdev.geom_kinv;
+                    CK(gpfo_contract_grad_split_launch(st, gh.kind, gh.ddev, gio, D, ns_small > 1 ? 0 : 1));
+                    ++launches;
+                } else {
+                    CK(gpfo_contract_grad_launch(st, gh.kind, gh.ddev, gio, ggrid, D));
+                }
+                ++launches;
+            }
         }
     }
     gpfo_argmax_final(st, ctx->dpart_val, ctx->dpart_idx, nparts, ctx->dbest_val, ctx->dbest_idx);
@@ -737,7 +855,7 @@ int gpfo_predict(gpfo_ctx* ctx, int gp_id, const double* X, int64_t N, int D, do
     if (rc != GPFO_OK) return rc;
     EvalIO io;
     memset(&io, 0, sizeof(io));
-    io.X = dX; io.N = N; io.mom_mean = ctx->dmom_mean; io.mom_var = ctx->dmom_var;
+    io.X = dX; io.N = N; io.mstride = N; io.mom_mean = ctx->dmom_mean; io.mom_var = ctx->dmom_var;
     io.part_val = ctx->dpart_val; io.part_idx = ctx->dpart_idx;
     io.write_moments = 1; io.run_program = 0;
     const int ns = split_count(ctx, N, gpfo_split_tile(), g.geom_s.nchunks);

@@ -23,7 +23,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     extern __shared__ __align__(16) double smem[];
     const int D = gpp->D;
     double* ring = smem;                                             // [NW][S][RBW][64]
-    constexpr int KXB = (ABL & 8) ? 3 : 2;                           // K(X*,X) group buffers (3 in scratch mode, see below)
+    constexpr int KXB = (ABL & (8 | 32)) ? 3 : 2;                    // K(X*,X) group buffers (3 in scratch mode, see below)
     double* kx = ring + (size_t)NW * C::RING_DOUBLES_PER_WARP;       // [KXB][GROUP_SLOTS]
     double* xc = kx + KXB * C::GROUP_SLOTS;                          // [D][T]
     double* x2 = xc + (size_t)D * T;                                 // [T]
@@ -32,11 +32,18 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     double* sbest = tot + T * (1 + RMAX);                            // [EW][2] best value, best index (as bits)
     double* tab32 = sbest + 2 * EW;                                  // [32] 2^(i/32)
     static_assert(C::RING_DOUBLES_PER_WARP >= T * (1 + RMAX), "the per-warp reduction slice lives in the drained ring");
-    constexpr bool GRADM = (ABL & 4) != 0;
+    // Gradient pass, two forms.  DENSEM (bit 4): dense stream of K^-1, K(X*,X) generated here, 2 M^2 flop per candidate.
+    // BWD (bit 32): the forward launch ran with ASTORE (bit 128) and parked A = L^-1 Kx per tile; this launch contracts it
+    // with the reversed transposed triangular stream (row i' = Mp-1-i): W = L^-T A at M^2 flop, nothing generated.
+    constexpr bool DENSEM = (ABL & 4) != 0;
+    constexpr bool BWD = (ABL & 32) != 0;
+    constexpr bool ASTORE = (ABL & 128) != 0;
+    constexpr bool GRADM = DENSEM || BWD;
     double* gcm = tab32 + 34;                                        // [T][RMAX]  (d acq/d mean_ro) / out_scale_ro
     double* gcv = gcm + T * RMAX;                                    // [T]        -2 sum_ro (d acq/d var_ro) / out_scale_ro^2
     double* gsum = gcv + T;                                          // [T][1+D]   sum_i u_in [1, Xs_i]
-    static_assert(!GRADM || S >= NB, "the u buffer of the gradient pass reuses the ring");
+    static_assert(!GRADM || NW * C::RING_DOUBLES_PER_WARP + KXB * C::GROUP_SLOTS >= 8 * C::RBC * T,
+                  "the u buffer of the gradient pass reuses the ring and the group buffers");
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
     const GpDev& gp = *gpp;
@@ -49,8 +56,8 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     // and leaves its partial sums in io.partials; split_final_*_kernel adds them in a fixed order and runs the epilogue.
     // The stream layout may differ from the GP's default one (smaller chunks), so it travels in the launch record.
     constexpr bool SPLIT = (ABL & 16) != 0;
-    const PackGeom geom = SPLIT ? io.geom_o : (GRADM ? gp.geom_kinv : gp.geom);
-    const double* __restrict__ packed = SPLIT ? io.packed_o : (GRADM ? gp.packed_kinv : gp.packed);
+    const PackGeom geom = (SPLIT || BWD) ? io.geom_o : (DENSEM ? gp.geom_kinv : gp.geom);
+    const double* __restrict__ packed = (SPLIT || BWD) ? io.packed_o : (DENSEM ? gp.packed_kinv : gp.packed);
     const int nsplit = SPLIT ? io.nsplit : 1;
     const int split = SPLIT ? (int)(blockIdx.x % nsplit) : 0;
     double* myring = ring + (size_t)w * C::RING_DOUBLES_PER_WARP + 2 * lane;
@@ -82,7 +89,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 for (int ro = 0; ro < RMAX; ++ro) {
                     double cm = 0.0;
                     if (ro < R && n < io.N) {
-                        const size_t o = (size_t)(gp.slot0 + ro) * io.N + n;
+                        const size_t o = (size_t)(gp.slot0 + ro) * io.mstride + n;
                         cm = io.cmu[o] / gp.out_scale[ro];
                         cv += -2.0 * io.cva[o] / (gp.out_scale[ro] * gp.out_scale[ro]);
                     }
@@ -116,14 +123,15 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
         // With a K(X*,X) scratch every group is generated ONCE per tile -- by the chunk whose diagonal it belongs to, where
         // the triangular DMMA work is light and leaves pipe slots for the FP64 generation -- and parked in the per-CTA
         // scratch; later chunks copy their off-diagonal groups back asynchronously, two groups ahead of use.
-        constexpr bool SCR = (ABL & 8) != 0;             // compile-time: the plain variants carry no scratch code
-        double* const scratch = SCR ? io.kx_scratch + (size_t)blockIdx.x * io.kx_scratch_stride : nullptr;
+        constexpr bool SCR = (ABL & (8 | 32)) != 0;      // compile-time: the plain variants carry no scratch code
+        double* const scratch = BWD ? io.a_scratch + (size_t)tile * io.a_stride
+                                    : (SCR ? io.kx_scratch + (size_t)blockIdx.x * io.kx_scratch_stride : nullptr);
         for (int pi = split; pi < geom.nchunks; pi += nsplit) {
             const int p = pi;
             const int nr = pg_chunk_rows(geom, p);
             const int row0 = p * geom.rbc;                // first row block of this chunk
-            const int kp_end = GRADM ? geom.nrb : row0 + nr;
-            const int kd0 = GRADM ? kp_end : row0;        // first diagonal column block (none in the dense stream)
+            const int kp_end = DENSEM ? geom.nrb : row0 + nr;
+            const int kd0 = DENSEM ? kp_end : row0;       // first diagonal column block (none in the dense stream)
             const double* __restrict__ cbase = packed + pg_chunk_base(geom, p) * 64 + 2 * lane;
 
             double acc[RBW][NB][2];
@@ -243,12 +251,13 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             };
 
             const int ngroups = (kp_end + KPC - 1) / KPC;
-            const int nold = SCR ? kd0 / KPC : 0;          // groups left of the diagonal: generated by earlier chunks
+            // groups left of the diagonal were generated by earlier chunks (backward pass: every group is a stored one)
+            const int nold = BWD ? ngroups : (SCR ? kd0 / KPC : 0);
             if (nold > 0) {
                 copy_group(0);
                 if (nold > 1) copy_group(1);
                 cp_async_wait<0>();
-            } else {
+            } else if (!BWD) {
                 gen_group(0, kx);
             }
 #pragma unroll
@@ -269,7 +278,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                     if (kcount < S) cp_async_wait<0>();
                 } else if (gen_first) {
                     if (TIM) t_mark = clock64();
-                    if (more) gen_group(g + 1, nxt);
+                    if (!BWD && more) gen_group(g + 1, nxt);
                     if (TIM) { const long long t = clock64(); t_gen += t - t_mark; t_mark = t; }
                     mma_group(g);
                     if (TIM) t_mma += clock64() - t_mark;
@@ -277,7 +286,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                     if (TIM) t_mark = clock64();
                     mma_group(g);
                     if (TIM) { const long long t = clock64(); t_mma += t - t_mark; t_mark = t; }
-                    if (more) gen_group(g + 1, nxt);
+                    if (!BWD && more) gen_group(g + 1, nxt);
                     if (TIM) t_gen += clock64() - t_mark;
                 }
                 if (TIM) t_mark = clock64();
@@ -292,12 +301,14 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             if (GRADM) {
                 // ---- gradient pass: u_in = (sum_ro c_mu[n][ro] alpha[i][ro] + c_var[n] w_in) * dk_in/dr^2 into the (drained) ring
                 __syncthreads();                          // every warp is done reading its ring
-                double* ubuf = ring;                      // [8 * RBC][T]
+                double* ubuf = ring;                      // [8 * RBC][T]  (spills into the group buffers when S < NB)
+                const int rev = 8 * geom.nrb - 1;         // backward pass: stream row i' is training point rev - i'
 #pragma unroll
                 for (int r = 0; r < RBW; ++r) {
                     const int rbl = r * NW + w;
                     const int il = 8 * rbl + (lane >> 2);
-                    const int gi = 8 * (row0 + rbl) + (lane >> 2);
+                    const int gs = 8 * (row0 + rbl) + (lane >> 2);
+                    const int gi = BWD ? rev - gs : gs;
 #pragma unroll
                     for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
@@ -321,11 +332,31 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                     double a = gsum[e];
                     if (dd == 0) for (int il = 0; il < 8 * nr; ++il) a += ubuf[il * T + n];
                     else for (int il = 0; il < 8 * nr; ++il)
-                        a = fma(ubuf[il * T + n], __ldg(Xs + (size_t)(8 * row0 + il) * D + dd - 1), a);
+                        a = fma(ubuf[il * T + n], __ldg(Xs + (size_t)(BWD ? rev - (8 * row0 + il) : 8 * row0 + il) * D + dd - 1), a);
                     gsum[e] = a;
                 }
                 __syncthreads();
                 continue;
+            }
+            if (ASTORE) {
+                // park A of this chunk for the backward launch: reversed row order, B-fragment group layout (the slot of
+                // element (j', n) is the one gen_group uses for K(X*,X) element (j', n))
+                double* const at = io.a_scratch + (size_t)tile * io.a_stride;
+                const int i8 = 7 - (lane >> 2);
+#pragma unroll
+                for (int r = 0; r < RBW; ++r) {
+                    const int rbl = r * NW + w;
+                    if (rbl < nr) {
+                        const int rbrev = geom.nrb - 1 - (row0 + rbl);
+                        double* const o = at + (size_t)(rbrev >> 3) * C::GROUP_SLOTS +
+                                          (((rbrev & 7) * 2 + (i8 >> 2)) * NB) * 32 + (i8 & 3) + 8 * (lane & 3);
+#pragma unroll
+                        for (int nb = 0; nb < NB; ++nb) {
+                            __stcg(o + nb * 32, acc[r][nb][0]);
+                            __stcg(o + nb * 32 + 4, acc[r][nb][1]);
+                        }
+                    }
+                }
             }
             if (TIM) t_mark = clock64();
             // ---- chunk reduction (fixed order -> deterministic).  Warp w's slice red[w][T][1+RMAX] lives at the start of its
@@ -501,9 +532,9 @@ split_final_grad_kernel(const GpDev* __restrict__ gpp, EvalIO io, int T, int D) 
 template <int NW, int RBW, int NB, int S, int KIND, int ABL>
 static cudaError_t launch2_kind(cudaStream_t st, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io, int grid, int D) {
     using C = Contract2Cfg<NW, RBW, NB, S>;
-    const size_t smem = ((size_t)NW * C::RING_DOUBLES_PER_WARP + ((ABL & 8) ? 3 : 2) * C::GROUP_SLOTS +
+    const size_t smem = ((size_t)NW * C::RING_DOUBLES_PER_WARP + ((ABL & (8 | 32)) ? 3 : 2) * C::GROUP_SLOTS +
                          (size_t)D * C::T + C::T + C::T * (1 + RMAX) + 2 * ((C::T + 31) / 32) + 34 +
-                         ((ABL & 4) ? C::T * RMAX + C::T + C::T * (1 + (size_t)D) : 0)) * sizeof(double);
+                         ((ABL & (4 | 32)) ? C::T * RMAX + C::T + C::T * (1 + (size_t)D) : 0)) * sizeof(double);
     auto kern = contract2_kernel<NW, RBW, NB, S, KIND, ABL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -562,6 +593,24 @@ cudaError_t gpfo_contract_grad_split_launch(cudaStream_t st, int kind, const GpD
     if (e != cudaSuccess) return e;
     split_final_grad_kernel<<<(unsigned)((io.N * D + 127) / 128), 128, 0, st>>>(d_gp, io, T, D);
     return cudaGetLastError();
+}
+
+// ---- stored-A gradient pass for large batches: forward = the default kernel (T = 64, 256-row chunks, K(X*,X) scratch) that
+// also parks A per tile; backward = the same tiles over the reversed transposed stream, all groups read back, M^2 flop.
+int gpfo_contract_bwd_rbc() { return 32; }
+int gpfo_contract_bwd_tile() { return 64; }
+long long gpfo_contract_astore_stride(int nrb) { return (long long)((nrb + KPC - 1) / KPC) * Contract2Cfg<16, 2, 8, 4>::GROUP_SLOTS; }
+size_t gpfo_contract_bwd_smem(int D) {
+    using C = Contract2Cfg<16, 2, 8, 4>;
+    return ((size_t)16 * C::RING_DOUBLES_PER_WARP + 3 * C::GROUP_SLOTS + (size_t)D * C::T + C::T + C::T * (1 + RMAX) +
+            2 * ((C::T + 31) / 32) + 34 + C::T * RMAX + C::T + C::T * (1 + (size_t)D)) * sizeof(double);
+}
+cudaError_t gpfo_contract_astore_launch(cudaStream_t st, int kind, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io,
+                                        int grid, int D) {
+    return launch2<16, 2, 8, 4, 8 + 128>(st, kind, d_gp, d_prog, io, grid, D);
+}
+cudaError_t gpfo_contract_bwd_launch(cudaStream_t st, int kind, const GpDev* d_gp, EvalIO io, int grid, int D) {
+    return launch2<16, 2, 8, 4, 32>(st, kind, d_gp, nullptr, io, grid, D);
 }
 
 // gradient pass launcher (dense K^-1 stream; T = 32 candidates per tile, 512-row chunks)

@@ -50,21 +50,21 @@ __device__ __forceinline__ void gpfo_tile_epilogue(const GpDev& gp, const Progra
                 const double v_o = fvar / (gp.out_scale[ro] * gp.out_scale[ro]);
                 mu[s] = m_o; va[s] = v_o;
                 if (io.write_moments) {
-                    io.mom_mean[(size_t)s * io.N + n] = m_o;
-                    io.mom_var[(size_t)s * io.N + n] = v_o;
+                    io.mom_mean[(size_t)s * io.mstride + n] = m_o;
+                    io.mom_var[(size_t)s * io.mstride + n] = v_o;
                 }
             }
         }
         if (io.run_program) {
             for (int s = 0; s < prog->nslots; ++s) {
                 if (s < gp.slot0 || s >= gp.slot0 + R) {
-                    mu[s] = io.mom_mean[(size_t)s * io.N + n];
-                    va[s] = io.mom_var[(size_t)s * io.N + n];
+                    mu[s] = io.mom_mean[(size_t)s * io.mstride + n];
+                    va[s] = io.mom_var[(size_t)s * io.mstride + n];
                 }
             }
             val = gpfo_run_program<false>(*prog, mu, va, 0.0, nullptr, nullptr, nullptr, nullptr);
             if (io.values) io.values[n] = val;
-            idx = n;
+            idx = io.idx0 + n;
         }
     }
     if (io.run_program) {

@@ -388,6 +388,27 @@ void gpfo_kinv_alpha(cudaStream_t st, const double* dLinv, int Mf, const double*
     linvT_times_v_kernel<<<(Mf + 3) / 4, 128, 0, st>>>(dLinv, Mf, dV, R, dalpha);
 }
 
+// dst[i][k] = src[n-1-k][n-1-i]: the transpose of a lower-triangular matrix, re-indexed so that it is lower triangular
+// again (stored-A backward pass: W = L^-T A runs through the same triangular block-stream code as A = L^-1 Kx)
+__global__ void reverse_transpose_kernel(const double* __restrict__ src, int ld, int n, double* __restrict__ dst) {
+    __shared__ double t[32][33];
+    const int i0 = blockIdx.y * 32, k0 = blockIdx.x * 32;       // dst tile rows i0.., cols k0..
+    for (int r = threadIdx.y; r < 32; r += 8) {                  // read src rows n-1-(k0+r), cols n-1-(i0+c): coalesced over c
+        const int k = k0 + r, i = i0 + threadIdx.x;
+        t[r][threadIdx.x] = (k < n && i < n) ? src[(size_t)(n - 1 - k) * ld + (n - 1 - i)] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int i = i0 + r, k = k0 + threadIdx.x;
+        if (i < n && k < n) dst[(size_t)i * ld + k] = t[threadIdx.x][r];
+    }
+}
+
+void gpfo_reverse_transpose(cudaStream_t st, const double* src, int ld, int n, double* dst) {
+    dim3 blk(32, 8), grd((n + 31) / 32, (n + 31) / 32);
+    reverse_transpose_kernel<<<grd, blk, 0, st>>>(src, ld, n, dst);
+}
+
 // ---- cluster layout (see ClusterGeom) -----------------------------------------------------------------------------
 void gpfo_cluster_geom(int nrb, int rbc, ClusterGeom* g, long long total[2]) {
     g->nrb = nrb;

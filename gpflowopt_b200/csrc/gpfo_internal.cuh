@@ -116,6 +116,8 @@ struct ProgramDev {
 struct EvalIO {
     const double* X;            // N x D candidates (device)
     int64_t N;
+    long long mstride;          // slot stride of the [slot][.] arrays below (= candidates of the whole call)
+    long long idx0;             // index of this launch's row 0 within the whole call (added to the argmax index)
     double* mom_mean;           // [slot][N] scratch (may be null when not needed)
     double* mom_var;
     double* values;             // N (may be null)
@@ -142,6 +144,10 @@ struct EvalIO {
     PackGeom geom_o;
     int nsplit;
     double* partials;              // forward: [tile][split][T][1+RMAX]; gradient pass: [tile][split][T][1+D]
+    // stored-A gradient pass (large batches): the forward launch parks A = L^-1 Kx of every tile, reversed row order, in
+    // B-fragment group layout; the backward launch contracts it with the reversed transposed stream: W = L^-T A
+    double* a_scratch;             // [tile][groups][GROUP_SLOTS]
+    long long a_stride;            // doubles per tile
 };
 
 // Counter-based uniform generator shared by the device prologue and the host regeneration (gpfo_random_rows):
@@ -336,6 +342,15 @@ int gpfo_program_grad_grid(int64_t N, int num_sms);
 cudaError_t gpfo_contract_grad_launch(cudaStream_t st, int kind, const GpDev* d_gp, EvalIO io, int grid, int D);
 int gpfo_contract_grad_grid(int64_t N, int num_sms);
 int gpfo_contract_grad_rbc();
+// stored-A gradient pass for large batches (contract2.cu)
+int gpfo_contract_bwd_rbc();
+int gpfo_contract_bwd_tile();
+long long gpfo_contract_astore_stride(int nrb);
+size_t gpfo_contract_bwd_smem(int D);
+cudaError_t gpfo_contract_astore_launch(cudaStream_t st, int kind, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io, int grid, int D);
+cudaError_t gpfo_contract_bwd_launch(cudaStream_t st, int kind, const GpDev* d_gp, EvalIO io, int grid, int D);
+// reversed transpose of the top-left n x n corner: dst[i][k] = src[n-1-k][n-1-i] (factor.cu)
+void gpfo_reverse_transpose(cudaStream_t st, const double* src, int ld, int n, double* dst);
 // row-split launches for few candidates (contract2.cu): contraction over a slice of the rows per CTA + a finish kernel
 int gpfo_split_rbc();
 int gpfo_split_tile();

@@ -16,19 +16,19 @@ __global__ void __launch_bounds__(PG_THREADS) program_grad_kernel(const ProgramD
     for (int64_t n = (int64_t)blockIdx.x * PG_THREADS + threadIdx.x; n < io.N; n += (int64_t)gridDim.x * PG_THREADS) {
         double mu[GPFO_MAX_SLOTS], va[GPFO_MAX_SLOTS], dmu[GPFO_MAX_SLOTS], dva[GPFO_MAX_SLOTS];
         for (int s = 0; s < ns; ++s) {
-            mu[s] = io.mom_mean[(size_t)s * io.N + n];
-            va[s] = io.mom_var[(size_t)s * io.N + n];
+            mu[s] = io.mom_mean[(size_t)s * io.mstride + n];
+            va[s] = io.mom_var[(size_t)s * io.mstride + n];
         }
         // the VALUE comes from the same instantiation the plain evaluate path uses, so evaluate(X) == evaluate_with_gradients(X)[0]
         // bit for bit (reference testing/unit/test_implementations.py:33); the forward-mode pass supplies the partials only
         const double val = gpfo_run_program<false>(*prog, mu, va, 0.0, nullptr, nullptr, nullptr, nullptr);
         gpfo_run_program<true>(*prog, mu, va, 0.0, nullptr, nullptr, dmu, dva);
         for (int s = 0; s < ns; ++s) {
-            io.cmu[(size_t)s * io.N + n] = dmu[s];
-            io.cva[(size_t)s * io.N + n] = dva[s];
+            io.cmu[(size_t)s * io.mstride + n] = dmu[s];
+            io.cva[(size_t)s * io.mstride + n] = dva[s];
         }
         if (io.values) io.values[n] = val;
-        if (gpfo_better(val, n, best_v, best_i)) { best_v = val; best_i = n; }
+        if (gpfo_better(val, io.idx0 + n, best_v, best_i)) { best_v = val; best_i = io.idx0 + n; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

@@ -49,8 +49,8 @@ hvpoi_kernel(const ProgramDev* __restrict__ prog, CellsDev cells, EvalIO io, int
             const int64_t n = n0 + t;
             double m = 0.0, v = 1.0;
             if (n < io.N) {
-                m = io.mom_mean[(size_t)(slot_first + j) * io.N + n];
-                v = io.mom_var[(size_t)(slot_first + j) * io.N + n];
+                m = io.mom_mean[(size_t)(slot_first + j) * io.mstride + n];
+                v = io.mom_var[(size_t)(slot_first + j) * io.mstride + n];
             }
             v = fmax(v, GPFO_STABILITY);               // hvpoi.py:109
             cmu[tid] = m;
@@ -168,8 +168,8 @@ hvpoi_kernel(const ProgramDev* __restrict__ prog, CellsDev cells, EvalIO io, int
                 const double leaf = tq[1] * tq[0];                                         // Hv * PoI, hvpoi.py:140
                 double mu[GPFO_MAX_SLOTS], va[GPFO_MAX_SLOTS];
                 for (int s = 0; s < prog->nslots; ++s) {
-                    mu[s] = io.mom_mean[(size_t)s * io.N + n];
-                    va[s] = io.mom_var[(size_t)s * io.N + n];
+                    mu[s] = io.mom_mean[(size_t)s * io.mstride + n];
+                    va[s] = io.mom_var[(size_t)s * io.mstride + n];
                 }
                 if (GRAD) {
                     double hdm[R], hdv[R], dmu[GPFO_MAX_SLOTS], dva[GPFO_MAX_SLOTS];
@@ -183,13 +183,13 @@ hvpoi_kernel(const ProgramDev* __restrict__ prog, CellsDev cells, EvalIO io, int
                     val = gpfo_run_program<false>(*prog, mu, va, leaf, nullptr, nullptr, nullptr, nullptr);   // same code as evaluate
                     gpfo_run_program<true>(*prog, mu, va, leaf, hdm, hdv, dmu, dva);
                     for (int s = 0; s < prog->nslots; ++s) {
-                        io.cmu[(size_t)s * io.N + n] = dmu[s];
-                        io.cva[(size_t)s * io.N + n] = dva[s];
+                        io.cmu[(size_t)s * io.mstride + n] = dmu[s];
+                        io.cva[(size_t)s * io.mstride + n] = dva[s];
                     }
                 } else
                 val = gpfo_run_program<false>(*prog, mu, va, leaf, nullptr, nullptr, nullptr, nullptr);
                 if (io.values) io.values[n] = val;
-                idx = n;
+                idx = io.idx0 + n;
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {

@@ -472,3 +472,84 @@ def test_row_split_small_batches(ctx, M, D):
             ctx.set_variant(0)
         assert_parity(vals, v6, tol=1e-12, what="split vs un-split value")
         assert_parity(grads, g6, tol=1e-11, what="split vs un-split grad")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# stored-A gradient pass (large batches, N >= 64 * 4 * SMs): forward launches park A = L^-1 Kx, backward launches
+# contract it with the reversed transposed stream.  Checked against the oracle on a row subset, against the dense
+# K^-1 pass on every row, across several slabs, for a two-GP product and for HVPoI.
+# ------------------------------------------------------------------------------------------------------------------
+def _with_env(name, value, fn):
+    import os
+    old = os.environ.get(name)
+    os.environ[name] = value
+    try:
+        return fn()
+    finally:
+        if old is None:
+            del os.environ[name]
+        else:
+            os.environ[name] = old
+
+
+@pytest.mark.parametrize("M,D,kind", [(1100, 8, "matern52"), (300, 3, "rbf"), (515, 32, "matern32")])
+def test_stored_a_gradients_large_batch(ctx, M, D, kind):
+    N = 40000
+    g, lo, up = _model(M, D, kind, scaled=True)
+    upload_oracle_gp(ctx, 0, g)
+    fmin = float(np.min(g.predict(g.input_transform.backward(g.Xs))[0])) + 0.05
+    ctx.program_set([[_lib.OP_EI, 0, 0, 0]], [fmin])
+    Xc = _cands(N, D, lo, up)
+    vals, grads, bv, bi = ctx.eval(Xc, want_grads=True)
+    assert ctx.timings()["launches"] == 4                         # forward + partials + backward + argmax: one slab
+    sub = np.arange(0, N, 97)
+    rv, rg = oacq.Leaf('ei', g, fmin).value_and_grad(Xc[sub])
+    assert_parity(vals[sub], rv, what="stored-A value")
+    assert_parity(grads[sub], rg, what="stored-A grad")
+    v_only, _, bv2, bi2 = ctx.eval(Xc)
+    np.testing.assert_array_equal(v_only, vals)
+    assert bi == bi2 == int(np.argmax(vals)) and bv == bv2
+    vd, gd, _, _ = _with_env("GPFO_GRAD_DENSE", "1", lambda: ctx.eval(Xc, want_grads=True))
+    np.testing.assert_array_equal(vd, vals)
+    assert_parity(grads, gd, tol=1e-10, what="stored-A vs dense K^-1 pass")
+    # several slabs (bounded A scratch): same numbers, slab by slab
+    vs, gs, bvs, bis = _with_env("GPFO_ASTORE_BUDGET_MB", "1", lambda: ctx.eval(Xc, want_grads=True))
+    assert ctx.timings()["launches"] > 4
+    np.testing.assert_array_equal(vs, vals)
+    np.testing.assert_array_equal(gs, grads)
+    assert bis == bi and bvs == bv
+
+
+def test_stored_a_product_of_two_gps_and_hvpoi(ctx):
+    D, N = 4, 38400
+    g1, lo, up = _model(200, D, "matern52", scaled=True)
+    g2, _, _ = _model(333, D, "rbf", seed=77, scaled=True, R=1)
+    for i, g in enumerate((g1, g2)):
+        upload_oracle_gp(ctx, i, g, slot0=i)
+    ctx.gp_count_set(2)
+    try:
+        Xc = _cands(N, D, lo, up)
+        sub = np.arange(5, N, 101)
+        f1 = float(np.min(g1.predict(g1.input_transform.backward(g1.Xs))[0]))
+        ctx.program_set([[_lib.OP_EI, 0, 0, 0], [_lib.OP_POF, 1, 0, 1], [_lib.OP_PROD, 2, 0, 0]], [f1, 2.5])
+        vals, grads, _, bi = _with_env("GPFO_ASTORE_BUDGET_MB", "8", lambda: ctx.eval(Xc, want_grads=True))
+        node = oacq.Agg('prod', [oacq.Leaf('ei', g1, f1), oacq.Leaf('pof', g2, 2.5)])
+        rv, rg = node.value_and_grad(Xc[sub])
+        assert_parity(vals[sub], rv, what="stored-A product value")
+        assert_parity(grads[sub], rg, what="stored-A product grad")
+        assert bi == int(np.argmax(vals))
+        # HVPoI over the two means as objectives
+        X = g1.input_transform.backward(g1.Xs)
+        p = opareto.Pareto(np.zeros((1, 2)))
+        gps = [g1, g2]
+        p.update(np.hstack([g.predict(X)[0] for g in gps]))
+        hv = oacq.HVPoI(gps, p.front, p.lb, p.ub)
+        ctx.cells_set(hv.pf_ext(), p.lb, p.ub)
+        ctx.program_set([[_lib.OP_HVPOI, 0, 2, 0]], [])
+        vals, grads, _, bi = ctx.eval(Xc, want_grads=True)
+        rv, rg = hv.value_and_grad(Xc[sub])
+        assert_parity(vals[sub], rv, what="stored-A HVPoI value")
+        assert_parity(grads[sub], rg, what="stored-A HVPoI grad")
+        assert bi == int(np.argmax(vals))
+    finally:
+        ctx.gp_count_set(1)
