@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libgpfo.so")
 
 OK, ERR_NOT_SPD, ERR_BAD_SHAPE, ERR_CUDA, ERR_UNSUPPORTED, ERR_BAD_PROGRAM, ERR_STATE = range(7)
 KERN_RBF, KERN_MATERN52, KERN_MATERN32 = 0, 1, 2
-OP_EI, OP_POI, OP_POF, OP_LCB, OP_HVPOI, OP_SUM, OP_PROD, OP_SCALE, OP_MEAN, OP_VAR = range(1, 11)
+OP_EI, OP_POI, OP_POF, OP_LCB, OP_HVPOI, OP_SUM, OP_PROD, OP_SCALE, OP_MEAN, OP_VAR, OP_MES = range(1, 12)
 MAX_GPS, MAX_SLOTS, MAX_OPS, MAX_PARAMS, MAX_DIM = 16, 16, 64, 64, 64
 
 # every symbol include/gpfo.h declares

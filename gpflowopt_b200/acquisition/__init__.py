@@ -4,3 +4,4 @@ from .hvpoi import HVProbabilityOfImprovement
 from .lcb import LowerConfidenceBound
 from .pof import ProbabilityOfFeasibility
 from .poi import ProbabilityOfImprovement
+from .mes import MinValueEntropySearch

@@ -405,6 +405,12 @@ int gpfo_program_set(gpfo_ctx* ctx, const int32_t* ops, int nops, const double* 
                 if (a + 1 > nslots) nslots = a + 1;
                 ++sp;
                 break;
+            case GPFO_OP_MES:
+                if (a < 0 || a >= GPFO_MAX_SLOTS) return fail(ctx, GPFO_ERR_BAD_PROGRAM, "moment slot out of range");
+                if (b < 1 || c < 0 || c + b > nparams) return fail(ctx, GPFO_ERR_BAD_PROGRAM, "MES sample range outside params");
+                if (a + 1 > nslots) nslots = a + 1;
+                ++sp;
+                break;
             case GPFO_OP_HVPOI:
                 if (hv) return fail(ctx, GPFO_ERR_UNSUPPORTED, "at most one HVPoI leaf per program");
                 if (a < 0 || b < 2 || b > 6 || a + b > GPFO_MAX_SLOTS)

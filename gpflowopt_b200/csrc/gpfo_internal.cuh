@@ -182,6 +182,21 @@ __device__ __forceinline__ double gpfo_std_pdf(double z) {
     const double half_log_2pi = 0.91893853320467267;
     return exp(-0.5 * (z * z) - half_log_2pi);
 }
+// TF1 log_ndtr (Normal.log_cdf, float64 segments): -ndtr(-x) above 8, log(ndtr(x)) in (-20, 8], the 3-term asymptotic series
+// below; d = derivative of the selected branch (what tf.gradients returns through tf.where).
+__device__ __forceinline__ double gpfo_log_ndtr(double x, double* d) {
+    const double half_log_2pi = 0.91893853320467267;
+    if (x > 8.0) { if (d) *d = gpfo_std_pdf(x); return -gpfo_ndtr(-x); }
+    if (x > -20.0) {
+        const double c = gpfo_ndtr(x);
+        if (d) *d = gpfo_std_pdf(x) / c;
+        return log(c);
+    }
+    const double x2 = x * x, x4 = x2 * x2, x6 = x4 * x2;
+    const double ser = 1.0 + 3.0 / x4 - (1.0 / x2 + 15.0 / x6);
+    if (d) { const double x3 = x2 * x; *d = (-x - 1.0 / x) + (2.0 / x3 - 12.0 / (x3 * x2) + 90.0 / (x3 * x3 * x)) / ser; }
+    return (-0.5 * x2 - log(-x) - half_log_2pi) + log(ser);
+}
 // Normal(loc, scale).prob(x) = exp(-0.5 z^2 - (0.5 log 2pi + log scale))
 __device__ __forceinline__ double gpfo_normal_prob(double x, double loc, double scale) {
     const double half_log_2pi = 0.91893853320467267;
@@ -239,6 +254,28 @@ __device__ __forceinline__ double gpfo_run_program(const ProgramDev& pr, const d
                 gm[sp][a] = d_m; gv[sp][a] = d_v;
             }
             ++sp;
+        } else if (op == GPFO_OP_MES) {                         // mes.py:96-102; no variance clamp in the reference
+            const double m = mu[a], v0 = va[a];
+            const double s = sqrt(v0);
+            double acc = 0.0, d_m = 0.0, d_v = 0.0;
+            for (int k = 0; k < b; ++k) {
+                const double g = (m - pr.params[c + k]) / s;
+                const double pdf = gpfo_std_pdf(g), cdf = gpfo_ndtr(g);
+                double dl = 0.0;
+                const double lc = gpfo_log_ndtr(g, GRAD ? &dl : nullptr);
+                acc += __dsub_rn(__dmul_rn(g, pdf) / __dmul_rn(2.0, cdf), lc);
+                if (GRAD) {
+                    const double dh = ((pdf - g * g * pdf) / (2.0 * cdf) - g * pdf * pdf / (2.0 * cdf * cdf)) - dl;
+                    d_m += dh;
+                    d_v += dh * (-g / (2.0 * v0));
+                }
+            }
+            st[sp] = acc / (double)b;
+            if (GRAD) {
+                for (int s2 = 0; s2 < ns; ++s2) { gm[sp][s2] = 0.0; gv[sp][s2] = 0.0; }
+                gm[sp][a] = d_m / s / (double)b; gv[sp][a] = d_v / (double)b;
+            }
+            ++sp;
         } else if (op == GPFO_OP_HVPOI) {
             st[sp] = hv;
             if (GRAD) {
@@ -284,8 +321,8 @@ __device__ __forceinline__ double gpfo_run_program(const ProgramDev& pr, const d
 
 // (value, index) ordering used at every reduction level: larger value wins; ties -> lower index; NaN never wins.
 __device__ __forceinline__ bool gpfo_better(double v, long long i, double bv, long long bi) {
-    if (i < 0) return false;
-    if (bi < 0) return !(v != v);
+    if (i < 0 || v != v) return false;                 // an empty or NaN challenger never wins ...
+    if (bi < 0 || bv != bv) return true;               // ... and an empty or NaN incumbent always yields to a number
     return (v > bv) || (v == bv && i < bi);
 }
 

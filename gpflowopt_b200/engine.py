@@ -58,6 +58,13 @@ class ProgramBuilder(object):
     def lcb(self, model, sigma):
         return self._leaf(_lib.OP_LCB, model, sigma)
 
+    def mes(self, model, samples):
+        samples = np.asarray(samples, dtype=np.float64).ravel()
+        first = len(self.params)
+        self.params.extend(float(v) for v in samples)
+        self.ops.append((_lib.OP_MES, self._slot_of[id(model)], samples.size, first))
+        return len(self.ops) - 1
+
     def mean(self, model, column=0):
         self.ops.append((_lib.OP_MEAN, self._slot_of[id(model)] + column, 0, 0))
         return len(self.ops) - 1

@@ -53,7 +53,9 @@ enum {
     GPFO_OP_PROD = 7,   /* a = number of operands popped                         (acquisition.py:360-362, 382-393) */
     GPFO_OP_SCALE = 8,  /* c = index of constant factor (MCMC mean 1/n)          (acquisition.py:446-448) */
     GPFO_OP_MEAN = 9,   /* a = moment slot: pushes the predictive mean (identity epilogue; predict_f) */
-    GPFO_OP_VAR = 10    /* a = moment slot: pushes the predictive variance */
+    GPFO_OP_VAR = 10,   /* a = moment slot: pushes the predictive variance */
+    GPFO_OP_MES = 11    /* a = moment slot, b = number of y* samples, c = index of the first sample in params[]
+                           (acquisition/mes.py:96-102: mean over samples of g pdf(g)/(2 cdf(g)) - log cdf(g)) */
 };
 
 #define GPFO_MAX_GPS 16

@@ -11,6 +11,7 @@ Restated reference sites (relative to /root/reference):
   * LowerConfidenceBound.build_acquisition     gpflowopt/acquisition/lcb.py:54-57
   * AcquisitionSum / Product / MCMC mean       gpflowopt/acquisition/acquisition.py:360-362, 446-448
   * HVProbabilityOfImprovement                 gpflowopt/acquisition/hvpoi.py:79-140
+  * MinValueEntropySearch.build_acquisition    gpflowopt/acquisition/mes.py:96-102 (Gumbel sampling of y*: mes.py:63-94)
   * tf.gradients(acq, Xcand)                   gpflowopt/acquisition/acquisition.py:256-257
   * MCOptimizer._optimize (argmin)             gpflowopt/optim.py:155-164
 """
@@ -44,6 +45,76 @@ def normal_prob(x, loc, scale):
 
 def std_pdf(z):
     return np.exp(-0.5 * np.square(z) - HALF_LOG_2PI)
+
+
+LOGNDTR_LOWER, LOGNDTR_UPPER = -20.0, 8.0     # TF1 special_math float64 segments (RECALLED)
+
+
+def _log_ndtr_series(x):
+    """TF1 ``_log_ndtr_asymptotic_series`` with series_order = 3: 1 + 3/x^4 - (1/x^2 + 15/x^6)."""
+    x2 = np.square(x)
+    x4 = x2 * x2
+    x6 = x4 * x2
+    even_sum = 3.0 / x4
+    odd_sum = 1.0 / x2 + 15.0 / x6
+    return 1.0 + even_sum - odd_sum
+
+
+def log_ndtr(x):
+    """TF1 ``log_ndtr`` (Normal.log_cdf): -ndtr(-x) above 8, log(ndtr(x)) in (-20, 8], asymptotic series below."""
+    x = np.asarray(x, dtype=np.float64)
+    xl = np.minimum(x, LOGNDTR_LOWER)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        lower = (-0.5 * np.square(xl) - np.log(-xl) - HALF_LOG_2PI) + np.log(_log_ndtr_series(xl))
+        mid = np.log(ndtr(np.maximum(x, LOGNDTR_LOWER)))
+    return np.where(x > LOGNDTR_UPPER, -ndtr(-x), np.where(x > LOGNDTR_LOWER, mid, lower))
+
+
+def dlog_ndtr(x):
+    """Derivative TF's gradient of the selected ``where`` branch produces."""
+    x = np.asarray(x, dtype=np.float64)
+    xl = np.minimum(x, LOGNDTR_LOWER)
+    x3 = xl * xl * xl
+    dser = 2.0 / x3 - 12.0 / (x3 * xl * xl) + 90.0 / (x3 * x3 * xl)
+    lower = (-xl - 1.0 / xl) + dser / _log_ndtr_series(xl)
+    xm = np.maximum(x, LOGNDTR_LOWER)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        mid = std_pdf(xm) / ndtr(xm)
+    return np.where(x > LOGNDTR_UPPER, std_pdf(x), np.where(x > LOGNDTR_LOWER, mid, lower))
+
+
+class MES:
+    """mes.py:96-102: mean over the y* samples of gamma pdf(gamma) / (2 cdf(gamma)) - log cdf(gamma),
+    gamma = (mean - y*) / sqrt(var) (no variance clamp in the reference)."""
+
+    kind = 'mes'
+
+    def __init__(self, gp, samples):
+        self.gp, self.samples = gp, np.asarray(samples, dtype=np.float64).ravel()
+
+    def gps(self):
+        return [self.gp]
+
+    def _terms(self, mean, var):
+        gamma = (mean - self.samples[None, :]) / np.sqrt(var)
+        pdf, cdf = std_pdf(gamma), ndtr(gamma)
+        return gamma, pdf, cdf
+
+    def value(self, X):
+        mean, var = self.gp.predict(X)
+        gamma, pdf, cdf = self._terms(mean[:, [0]], var[:, [0]])
+        return np.sum(gamma * pdf / (2.0 * cdf) - log_ndtr(gamma), axis=1, keepdims=True) / self.samples.size
+
+    def value_and_grad(self, X):
+        mean, var, dmean, dvar = self.gp.predict_with_grads(X)
+        mean, var, dmean, dvar = mean[:, [0]], var[:, [0]], dmean[:, :, 0], dvar[:, :, 0]
+        gamma, pdf, cdf = self._terms(mean, var)
+        val = np.sum(gamma * pdf / (2.0 * cdf) - log_ndtr(gamma), axis=1, keepdims=True) / self.samples.size
+        dA = (pdf - gamma * gamma * pdf) / (2.0 * cdf) - gamma * pdf * pdf / (2.0 * cdf * cdf)
+        dh = dA - dlog_ndtr(gamma)                                   # d term / d gamma, N x S
+        c_m = np.sum(dh, axis=1, keepdims=True) / np.sqrt(var)       # d gamma / d mean = 1 / s
+        c_v = np.sum(dh * (-gamma / (2.0 * var)), axis=1, keepdims=True)
+        return val, (c_m * dmean + c_v * dvar) / self.samples.size
 
 
 # --------------------------------------------------------------------------------------------------

@@ -8,6 +8,7 @@ import gpflowopt_b200 as gpfo
 from gpflowopt_b200 import synthetic
 from gpflowopt_b200.acquisition import (AcquisitionProduct, AcquisitionSum, ExpectedImprovement,
                                         HVProbabilityOfImprovement, LowerConfidenceBound, MCMCAcquistion,
+                                        MinValueEntropySearch,
                                         ProbabilityOfFeasibility, ProbabilityOfImprovement)
 from gpflowopt_b200.design import FactorialDesign, RandomDesign
 from gpflowopt_b200.domain import ContinuousParameter
@@ -267,3 +268,27 @@ def test_mc_optimizer_device_rng():
     eng.prepare(ei)
     vals, bv, bi = eng.ctx.eval_random(r.seed, 1234, 3000, DOMAIN.lower, DOMAIN.upper, want_values=True)
     np.testing.assert_array_equal(vals, scores[1234:4234])
+
+
+def test_min_value_entropy_search_class():                 # reference test_implementations.py:190-218
+    X = FactorialDesign(4, DOMAIN).generate() + 0.05       # 16 points, none at the minimiser
+    model = _gpr(X, parabola2d(X))
+    np.random.seed(7)
+    mes = MinValueEntropySearch(model, DOMAIN)
+    assert np.array_equal(mes.objective_indices(), np.arange(1, dtype=int))
+    rs = np.random.RandomState(5)
+    Xcenter = rs.rand(20, 2) * 0.25 - 0.125
+    Xr = rs.rand(100, 2) * 2 - 1
+    Xborder = np.vstack((Xr[np.abs(Xr[:, 0]) > 0.8], Xr[np.abs(Xr[:, 1]) > 0.8]))
+    s_border, s_center = mes.evaluate(Xborder), mes.evaluate(Xcenter)
+    assert mes.samples.shape == (mes.num_samples,) and np.min(mes.data[1]) > 0
+    assert np.min(s_center) + 1e-6 > np.max(s_border)
+    assert np.all(mes.feasible_data_index())
+    # same numbers as the oracle restatement fed the same y* samples
+    g = _ogp(X, parabola2d(X))
+    node = oacq.MES(g, mes.samples)
+    assert_parity(s_center, node.value(Xcenter), what="MES class value")
+    v, gr = mes.evaluate_with_gradients(Xcenter)
+    rv, rg = node.value_and_grad(Xcenter)
+    assert_parity(gr, rg, what="MES class gradient")
+    np.testing.assert_array_equal(v, s_center)

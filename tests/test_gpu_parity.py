@@ -553,3 +553,54 @@ def test_stored_a_product_of_two_gps_and_hvpoi(ctx):
         assert bi == int(np.argmax(vals))
     finally:
         ctx.gp_count_set(1)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Min-value entropy search leaf (reference mes.py:96-102): values and gradients, all log_ndtr segments
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["rbf", "matern52"])
+def test_mes_leaf_values_and_gradients(ctx, kind):
+    g, lo, up = _model(260, 5, kind, scaled=True)
+    upload_oracle_gp(ctx, 0, g)
+    fmin = float(np.min(g.predict(g.input_transform.backward(g.Xs))[0]))
+    m0, v0 = g.predict(_cands(700, 5, lo, up))
+    # samples below the best mean (the usual case), one far below (gamma > 8) and one above the means by ~25 predictive
+    # standard deviations (gamma < -20: series segment; where cdf underflows both sides give NaN, as the reference would)
+    samples = np.concatenate((fmin - np.array([0.02, 0.1, 0.3, 0.8, 2.0, 60.0, 0.5, 1.0]),
+                              [np.median(m0) + 25.0 * np.median(np.sqrt(v0))]))
+    node = oacq.MES(g, samples)
+    for nsamp in (8, 9):
+        ctx.program_set([[_lib.OP_MES, 0, nsamp, 0]], list(samples))
+        node = oacq.MES(g, samples[:nsamp])
+        Xtr = g.input_transform.backward(g.Xs)
+        xbest = Xtr[[int(np.argmin(g.predict(Xtr)[0]))]]
+        for N in (1, 33, 700, 5000):
+            # N = 1: a point next to the incumbent (gamma ~ 1; far from the data MES is ~1e-60 and its own scale)
+            Xc = _cands(N, 5, lo, up) if N > 1 else np.clip(xbest + 0.05, lo, up)
+            vals, grads, bv, bi = ctx.eval(Xc, want_grads=True)
+            with np.errstate(all='ignore'):
+                rv, rg = node.value_and_grad(Xc)
+            # compare where both sides are finite (cdf underflow makes 0/0 on either side, a few ulp apart in gamma)
+            ok = np.isfinite(rv[:, 0]) & np.isfinite(vals[:, 0]) & np.all(np.isfinite(rg), axis=1) & np.all(np.isfinite(grads), axis=1)
+            pm, pv = g.predict(Xc)                         # ... and where cdf(gamma) is a normal number (gamma > -37)
+            gmin = np.min((pm - node.samples[None, :]) / np.sqrt(pv), axis=1)
+            ok &= gmin > -37.0
+            # d/dgamma of gamma pdf / (2 cdf) - log cdf cancels from O(gamma^3) terms down to O(1/gamma) for gamma << 0: an
+            # erfc difference of 1e-13 between two libms is amplified by gamma^4 / 2, so the 1e-9 gradient bar is meaningful
+            # only for gamma > -10 (always the case for y* samples below the posterior means); beyond that 1e-4.
+            well = ok & (gmin > -10.0)
+            assert (N == 1 or ok.mean() > 0.5) and (nsamp == 9 or ok.all())
+            v_only, _, _, bi2 = ctx.eval(Xc)
+            np.testing.assert_array_equal(v_only, vals)
+            if ok.any():
+                assert_parity(vals[ok], rv[ok], what="MES value N=%d" % N)
+                if well.any():
+                    assert_parity(grads[well], rg[well], what="MES grad N=%d" % N)
+                assert_parity(grads[ok], rg[ok], tol=1e-4, what="MES grad (ill-conditioned rows) N=%d" % N)
+                assert bi == bi2 == int(np.nanargmax(vals))
+            else:
+                assert bi == bi2 == -1                      # NaN never wins (reference: np.argmin over NaN is undefined)
+    gam = (m0 - samples[8]) / np.sqrt(v0)
+    assert np.any((gam < -20.0) & (gam > -37.0)) and np.any((m0 - samples[5]) / np.sqrt(v0) > 8.0)     # segments were hit
+    with pytest.raises(_lib.GpfoError):
+        ctx.program_set([[_lib.OP_MES, 0, 5, 2]], [0.0] * 6)       # sample range runs past params

@@ -196,8 +196,13 @@ def _autograd_reference(node, Xc):
     a_out, b_out = float(np.diag(g.output_transform.A)[0]), float(g.output_transform.b[0])
     mean = ((A.T @ V)[:, 0] - b_out) / a_out
     var = (g.variance - (A ** 2).sum(0)) / a_out ** 2
-    p = node.param
-    if node.kind == 'lcb':
+    p = getattr(node, 'param', None)
+    if node.kind == 'mes':
+        gamma = (mean[:, None] - torch.from_numpy(node.samples)[None, :]) / torch.sqrt(var)[:, None]
+        pdf = torch.exp(-0.5 * gamma ** 2 - 0.5 * np.log(2 * np.pi))
+        cdf = 0.5 * (1 + torch.erf(gamma / np.sqrt(2.0)))
+        val = (gamma * pdf / (2.0 * cdf) - torch.special.log_ndtr(gamma)).sum(1) / node.samples.size
+    elif node.kind == 'lcb':
         val = mean - p * torch.sqrt(torch.clamp(var, min=0.0))
     else:
         v = torch.clamp(var, min=1e-6)
@@ -227,6 +232,51 @@ def test_closed_form_gradient_matches_autograd(kind, leaf):
     assert np.max(np.abs(grad - g_ref)) <= 1e-9 * np.max(np.abs(g_ref))
     # and the value returned with gradients equals evaluate() (reference test_implementations.py:19-33)
     np.testing.assert_array_equal(val, node.value(Xc))
+
+
+def test_log_ndtr_branches_against_mpmath():
+    """TF1 log_ndtr segments (float64: series below -20, log(ndtr) up to 8, -ndtr(-x) above) against exact values; the
+    3-term series itself is only good to 105 / x^8 (4e-9 at the switch point), which bounds what the reference computes."""
+    mp.mp.dps = 50
+    x = np.array([-40.0, -25.0, -20.5, -20.0, -19.99, -8.0, -1.0, 0.0, 0.7, 3.0, 7.99, 8.0, 8.01, 12.0])
+    got, dgot = oacq.log_ndtr(x), oacq.dlog_ndtr(x)
+    for xi, g_, d_ in zip(x, got, dgot):
+        ref = float(mp.log(mp.ncdf(mp.mpf(xi))))
+        dref = float(mp.npdf(mp.mpf(xi)) / mp.ncdf(mp.mpf(xi)))
+        tol = 1.1 * 105.0 / xi ** 8 if xi <= -20.0 else 1e-13 * abs(ref) + 2.3e-16    # log(1 - q): one ulp of 1
+        assert abs(g_ - ref) <= tol, (xi, g_, ref)
+        dtol = 1e-6 * abs(dref) if xi <= -20.0 else 1e-12 * abs(dref) + 1e-30
+        assert abs(d_ - dref) <= dtol, (xi, d_, dref)
+
+
+@pytest.mark.parametrize("kind", [ogp.RBF, ogp.MATERN52])
+def test_mes_value_against_mpmath_and_gradient_against_autograd(kind):
+    """mes.py:96-102 restated: value against 50-digit arithmetic on the mpmath posterior, gradient against autograd."""
+    M, D, N = 24, 2, 12
+    X, Y = synthetic.training_set(M, D)
+    lo, up = np.array([-5.0, 0.0]), np.array([10.0, 15.0])
+    Xd = lo + X * (up - lo)
+    g = oracle_gp(Xd, Y * 2 + 1, kind, synthetic.hypers(D), lower=lo, upper=up, normalize=True)
+    Xc = lo + synthetic.candidates(N, D) * (up - lo)
+    fmin = float(np.min(g.predict(Xd)[0]))
+    samples = fmin - np.array([0.05, 0.2, 0.6, 1.5, 4.0])
+    node = oacq.MES(g, samples)
+    val = node.value(Xc)[:, 0]
+    m_mp, v_mp = _mp_predict(g, Xc)
+    ref = []
+    for m, v in zip(m_mp, v_mp):
+        acc = mp.mpf(0)
+        for y in samples:
+            gam = (m - mp.mpf(float(y))) / mp.sqrt(v)
+            acc += gam * mp.npdf(gam) / (2 * mp.ncdf(gam)) - mp.log(mp.ncdf(gam))
+        ref.append(float(acc / len(samples)))
+    assert np.max(np.abs(val - np.array(ref))) <= 1e-9 * np.max(np.abs(ref))
+    v2, grad = node.value_and_grad(Xc)
+    np.testing.assert_array_equal(v2[:, 0], val)
+    if kind in (ogp.RBF, ogp.MATERN52):
+        v_ref, g_ref = _autograd_reference(node, Xc)
+        np.testing.assert_allclose(val, v_ref, rtol=1e-10, atol=1e-14)
+        assert np.max(np.abs(grad - g_ref)) <= 1e-9 * np.max(np.abs(g_ref))
 
 
 def test_product_and_hvpoi_gradients_by_finite_differences():
