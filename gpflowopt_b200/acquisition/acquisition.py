@@ -158,6 +158,11 @@ class Acquisition(object):
         ``seed``, uniform in the box [lower, upper]); nothing of size N crosses PCIe in either direction."""
         return self._get_engine().argmax_random(self, seed, first_row, n, lower, upper)
 
+    @setup_required
+    def evaluate_random(self, seed, first_row, n, lower, upper):
+        """``evaluate`` over device-generated candidates: only the n scores come back (``_lib.random_rows`` regenerates rows)."""
+        return self._get_engine().evaluate_random(self, seed, first_row, n, lower, upper)
+
     def __add__(self, other):
         if isinstance(other, AcquisitionSum):
             return AcquisitionSum([self] + other.operands)

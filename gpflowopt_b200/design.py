@@ -31,7 +31,7 @@ class RandomDesign(Design):
     """Uniform random points: the MC candidate source (gpflowopt/design.py:83-94)."""
 
     def create_design(self):
-        return np.random.rand(self.size, self.domain.size).astype(np.float64)
+        return np.asarray(np.random.rand(self.size, self.domain.size), dtype=np.float64)
 
 
 class FactorialDesign(Design):

@@ -45,9 +45,12 @@ class Domain(object):
         X = np.atleast_2d(X)
         if X.shape[1] != self.size:
             return False
-        lo, up = self.lower, self.upper
-        return bool(np.all(np.logical_and(np.logical_or(lo < X, np.isclose(lo, X)),
-                                          np.logical_or(X < up, np.isclose(up, X)))))
+        # same predicate as the reference (domain.py:68-73): inside, or np.isclose to a bound -- with the tolerance test run
+        # only on the entries that fail the strict comparison (none, for a design of 1e6 interior points)
+        for bound, outside in ((self.lower, ~(self.lower < X)), (self.upper, ~(X < self.upper))):
+            if outside.any() and not np.all(np.isclose(np.broadcast_to(bound, X.shape)[outside], X[outside])):
+                return False
+        return True
 
     def __iter__(self):
         for v in chain(*map(iter, self._parameters)):

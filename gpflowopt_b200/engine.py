@@ -176,6 +176,12 @@ class Engine(object):
         _, bv, bi = self.ctx.eval_random(seed, first_row, n, lower, upper)
         return bv, bi
 
+    def evaluate_random(self, acq, seed, first_row, n, lower, upper):
+        """Scores (n x 1) of rows first_row .. first_row+n-1 of the device-generated candidate stream."""
+        self.prepare(acq)
+        vals, _, _ = self.ctx.eval_random(seed, first_row, n, lower, upper, want_values=True)
+        return vals
+
     def argmax_device(self, acq, x_ptr, N, D, values_ptr=None):
         self.prepare(acq)
         return self.ctx.eval_device(x_ptr, N, D, values_ptr)

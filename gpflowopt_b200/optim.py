@@ -10,6 +10,7 @@ evaluate-then-np.argmin route of the reference.
 import contextlib
 import os
 import sys
+import threading
 import warnings
 
 import numpy as np
@@ -171,6 +172,128 @@ class SciPyOptimizer(Optimizer):
             config['options'] = {k: v for k, v in config['options'].items() if k != 'disp'}
         return minimize(fun=objective1d, x0=self.get_initial().ravel(), jac=self.gradient_enabled(),
                         bounds=list(zip(self.domain.lower, self.domain.upper)), **config)
+
+
+class _LockStep(object):
+    """Rendezvous for k optimiser threads: every active thread posts its next point, the last one to arrive evaluates the
+    whole batch with ONE objective call and hands each thread its row.  A run that finishes leaves the rendezvous."""
+
+    def __init__(self, batch_fn, nruns):
+        self._fn = batch_fn
+        self._cv = threading.Condition()
+        self._active = nruns
+        self._pending = {}
+        self._results = {}
+        self._error = None
+        self.batches = 0
+        self.rows = 0
+
+    def _flush(self):
+        ids = sorted(self._pending)
+        try:
+            f, g = self._fn(np.vstack([self._pending[i] for i in ids]))
+            for row, i in enumerate(ids):
+                self._results[i] = (float(np.ravel(f[row])[0]), np.array(g[row], dtype=np.float64))
+        except BaseException as exc:           # wake everybody up, every run re-raises
+            self._error = exc
+        self._pending.clear()
+        self.batches += 1
+        self.rows += len(ids)
+        self._cv.notify_all()
+
+    def evaluate(self, run, x):
+        with self._cv:
+            self._pending[run] = np.atleast_2d(x)
+            if len(self._pending) == self._active:
+                self._flush()
+            while run not in self._results and self._error is None:
+                self._cv.wait()
+            if self._error is not None:
+                raise self._error
+            return self._results.pop(run)
+
+    def leave(self, run):
+        with self._cv:
+            self._active -= 1
+            if self._pending and len(self._pending) == self._active:
+                self._flush()
+
+
+class MultiStartOptimizer(Optimizer):
+    """Monte-Carlo stage + batched multi-start polish (no counterpart class in the reference, whose
+    StagedOptimizer([MCOptimizer, SciPyOptimizer]) polishes the single best MC point with N = 1 objective calls).
+
+    The ``nstarts`` best of ``nsamples`` random points each seed an L-BFGS-B run; the runs advance in lock step, so every
+    round of line-search evaluations is one ``evaluate_with_gradients`` call with N = (runs still active) instead of that
+    many latency-bound N = 1 calls.  Each run sees exactly the numbers it would see alone, so its trajectory is the one
+    ``SciPyOptimizer`` would produce from the same start; the result is the best run."""
+
+    def __init__(self, domain, nsamples, nstarts=8, method='L-BFGS-B', tol=None, maxiter=1000, device_rng=False):
+        super(MultiStartOptimizer, self).__init__(domain)
+        self._nsamples = nsamples
+        self._nstarts = nstarts
+        self._device_rng = device_rng            # as MCOptimizer: candidates drawn inside the scoring kernel
+        self.config = dict(tol=tol, method=method, options=dict(maxiter=maxiter))
+
+    @staticmethod
+    def _lowest(scores, k):
+        """Indices of the k lowest scores, ascending, ties by index (what a stable argsort would put first)."""
+        scores = np.ravel(scores)
+        k = max(1, min(k, scores.size))
+        if k < scores.size:
+            kth = np.partition(scores, k - 1)[k - 1]
+            cand = np.flatnonzero(scores <= kth)
+        else:
+            cand = np.arange(scores.size)
+        return cand[np.argsort(scores[cand], kind='stable')][:k]
+
+    def _starts(self, objective):
+        acq = getattr(objective, 'acquisition', None)
+        if acq is not None and self._device_rng:
+            from ._lib import random_rows
+            seed = int(np.random.randint(0, 2 ** 62))
+            scores = -acq.evaluate_random(seed, 0, self._nsamples, self.domain.lower, self.domain.upper)
+            objective.counter += self._nsamples
+            order = self._lowest(scores, self._nstarts)
+            points = np.vstack([random_rows(seed, int(i), 1, self.domain.lower, self.domain.upper) for i in order])
+            return points, np.ravel(scores)[order]
+        points = RandomDesign(self._nsamples, self.domain).generate()
+        if acq is not None:                      # value-only scoring kernel; minimise -acq (bo.py:244-245)
+            scores = -acq.evaluate(points)
+            objective.counter += points.shape[0]
+        else:
+            scores = objective(points)[0]
+        order = self._lowest(scores, self._nstarts)
+        return points[order], np.ravel(scores)[order]
+
+    def _optimize(self, objective):
+        starts, start_scores = self._starts(objective)
+        k = starts.shape[0]
+        lock = _LockStep(objective, k)
+        bounds = list(zip(self.domain.lower, self.domain.upper))
+        results, errors = [None] * k, [None] * k
+
+        def run(i):
+            try:
+                results[i] = minimize(fun=lambda x: lock.evaluate(i, x), x0=starts[i], jac=True, bounds=bounds, **self.config)
+            except BaseException as exc:
+                errors[i] = exc
+            finally:
+                lock.leave(i)
+
+        threads = [threading.Thread(target=run, args=(i,), daemon=True) for i in range(k)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for exc in errors:
+            if exc is not None:
+                raise exc
+        best = int(np.argmin([r.fun for r in results]))
+        res = results[best]
+        return OptimizeResult(x=res.x, fun=np.array([[res.fun]]), success=any(r.success for r in results),
+                              message=res.message, nit=res.nit, nstarts=k, nbatches=lock.batches,
+                              polish_rows=lock.rows, start_scores=start_scores, runs=results)
 
 
 class StagedOptimizer(Optimizer):

@@ -12,7 +12,7 @@ from gpflowopt_b200.acquisition import (AcquisitionProduct, AcquisitionSum, Expe
                                         ProbabilityOfFeasibility, ProbabilityOfImprovement)
 from gpflowopt_b200.design import FactorialDesign, RandomDesign
 from gpflowopt_b200.domain import ContinuousParameter
-from gpflowopt_b200.optim import CandidateOptimizer, MCOptimizer
+from gpflowopt_b200.optim import CandidateOptimizer, MCOptimizer, MultiStartOptimizer, SciPyOptimizer, StagedOptimizer
 from oracle import acq as oacq, gp as ogp, pareto as opareto
 from helpers import assert_parity, near_tie, oracle_gp
 
@@ -292,3 +292,25 @@ def test_min_value_entropy_search_class():                 # reference test_impl
     rv, rg = node.value_and_grad(Xcenter)
     assert_parity(gr, rg, what="MES class gradient")
     np.testing.assert_array_equal(v, s_center)
+
+
+def test_multi_start_polish_on_the_device():               # k L-BFGS-B runs on N = k gradient calls
+    from gpflowopt_b200.bo import _InverseAcquisition
+    X = _design(20)
+    ei = ExpectedImprovement(_gpr(X, parabola2d(X), gpfo.Matern52))
+    np.random.seed(3)
+    ms = MultiStartOptimizer(DOMAIN, 5000, nstarts=8).optimize(_InverseAcquisition(ei, True))
+    np.random.seed(3)
+    st = StagedOptimizer([MCOptimizer(DOMAIN, 5000), SciPyOptimizer(DOMAIN)]).optimize(_InverseAcquisition(ei, True))
+    assert ms.success and ms.x.shape == (1, 2) and ms.x in DOMAIN
+    scale = abs(float(np.ravel(st.fun)[0]))
+    assert float(np.ravel(ms.fun)[0]) <= float(np.ravel(st.fun)[0]) + 1e-9 * scale      # the staged start is start 0
+    assert ms.nbatches < ms.polish_rows and ms.nfev == 5000 + ms.polish_rows
+    v = ei.evaluate(ms.x)
+    assert abs(-v[0, 0] - float(np.ravel(ms.fun)[0])) <= 1e-12 * scale
+    # device-generated candidates: the starts are regenerated rows of the stream, their scores are the kernel's
+    np.random.seed(4)
+    md = MultiStartOptimizer(DOMAIN, 5000, nstarts=4, device_rng=True).optimize(_InverseAcquisition(ei, True))
+    assert md.success and md.x in DOMAIN and md.nstarts == 4 and np.all(np.diff(md.start_scores) >= 0)
+    assert float(np.ravel(md.fun)[0]) <= md.start_scores[0] + 1e-12
+    np.testing.assert_allclose(-ei.evaluate(np.vstack([r.x for r in md.runs]))[:, 0], [r.fun for r in md.runs], rtol=1e-12)

@@ -11,7 +11,7 @@ from gpflowopt_b200 import dist, _lib
 from gpflowopt_b200.design import EmptyDesign, FactorialDesign, RandomDesign
 from gpflowopt_b200.domain import ContinuousParameter, UnitCube
 from gpflowopt_b200.engine import ProgramBuilder
-from gpflowopt_b200.optim import CandidateOptimizer, MCOptimizer, SciPyOptimizer, StagedOptimizer
+from gpflowopt_b200.optim import CandidateOptimizer, MCOptimizer, MultiStartOptimizer, SciPyOptimizer, StagedOptimizer
 from gpflowopt_b200.transforms import LinearTransform
 
 
@@ -106,6 +106,42 @@ def test_scipy_and_staged_optimizers():                        # reference test_
     assert r.success and r.nstages == 3 and np.allclose(r.x, 0, atol=1e-3)
     r = staged.optimize(KeyboardRaiser(0, parabola2d))
     assert not r.success and r.nstages == 1 and r.nfev == 0
+
+
+def test_multi_start_lock_step_equals_independent_runs():
+    """the k polish runs advance in lock step on batched objective calls, and every run follows exactly
+    the trajectory it would follow alone (same numbers in, same L-BFGS-B decisions out)."""
+    d = _domain()
+    calls = []
+
+    def bumpy(X):
+        calls.append(X.shape[0])
+        f = np.sum(X ** 2 + 0.3 * np.sin(7.0 * X + 0.5), axis=1, keepdims=True)
+        return f, 2 * X + 2.1 * np.cos(7.0 * X + 0.5)
+
+    np.random.seed(11)
+    opt = MultiStartOptimizer(d, 200, nstarts=6, maxiter=50)
+    r = opt.optimize(bumpy)
+    assert r.success and r.x.shape == (1, 2) and r.nstarts == 6
+    assert calls[0] == 200 and max(calls[1:]) == 6 and len(calls) - 1 == r.nbatches
+    assert r.nfev == 200 + r.polish_rows == sum(calls)
+    assert r.nbatches == max(run.nfev for run in r.runs)               # lock step: as many batches as the longest run needs
+    assert r.polish_rows == sum(run.nfev for run in r.runs)
+    # the same starts, one at a time through the reference-style optimiser
+    np.random.seed(11)
+    starts = RandomDesign(200, d).generate()
+    order = np.argsort(np.ravel(bumpy(starts)[0]), kind='stable')[:6]
+    funs = []
+    for i, x0 in enumerate(starts[order]):
+        single = SciPyOptimizer(d, maxiter=50)
+        single.set_initial(x0)
+        rs = single.optimize(bumpy)
+        np.testing.assert_array_equal(rs.x.ravel(), r.runs[i].x)       # bit-identical trajectory end points
+        funs.append(float(np.ravel(rs.fun)[0]))
+    assert float(np.ravel(r.fun)[0]) == min(funs)
+    # errors inside a batched call reach the caller instead of dead-locking the other runs
+    with pytest.raises(ZeroDivisionError):
+        MultiStartOptimizer(d, 20, nstarts=3).optimize(lambda X: (bumpy(X)[0], bumpy(X)[1]) if X.shape[0] == 20 else 1 / 0)
 
 
 def test_shard_bounds_and_pair_reduce():
