@@ -12,7 +12,11 @@ struct GpHost {
     bool valid = false;
     int M = 0, Mp = 0, Mf = 0, D = 0, R = 0, kind = 0, slot0 = 0;
     double *dX = nullptr, *dell = nullptr, *dXs = nullptr, *dxn = nullptr, *dY = nullptr, *dV = nullptr;
-    double *dL = nullptr, *dLinv = nullptr, *dpacked = nullptr;
+    double *dL = nullptr, *dLinv = nullptr;
+    double* dpacked_by[2] = {nullptr, nullptr};             // forward block streams: [0] 256-row chunks, [1] the other layout in use
+    size_t cap_packed_by[2] = {0, 0};
+    bool packed_ready[2] = {false, false};
+    int packed_slot_rbc[2] = {0, 0};
     double *dalpha = nullptr, *dpacked_kinv = nullptr;      // gradient pass state, built lazily
     bool kinv_ready = false;
     double* dpacked_c[2] = {nullptr, nullptr};              // cluster layout (contract3), built lazily
@@ -27,7 +31,7 @@ struct GpHost {
     double* dpacked_rt = nullptr; size_t cap_packed_rt = 0;
     PackGeom geom_rt;
     bool rt_ready = false;
-    size_t cap_mf = 0, cap_d = 0, cap_r = 0, cap_packed = 0, cap_alpha = 0, cap_kinv = 0;
+    size_t cap_mf = 0, cap_d = 0, cap_r = 0, cap_alpha = 0, cap_kinv = 0;
     GpDev hdev;
     GpDev* ddev = nullptr;
 };
@@ -143,7 +147,7 @@ int gpfo_ctx_create(int device, gpfo_ctx** out) {
 
 static void free_gp(GpHost& g) {
     cudaFree(g.dX); cudaFree(g.dell); cudaFree(g.dXs); cudaFree(g.dxn); cudaFree(g.dY); cudaFree(g.dV);
-    cudaFree(g.dL); cudaFree(g.dLinv); cudaFree(g.dpacked); cudaFree(g.ddev);
+    cudaFree(g.dL); cudaFree(g.dLinv); cudaFree(g.dpacked_by[0]); cudaFree(g.dpacked_by[1]); cudaFree(g.ddev);
     cudaFree(g.dalpha); cudaFree(g.dpacked_kinv); cudaFree(g.dpacked_c[0]); cudaFree(g.dpacked_c[1]);
     cudaFree(g.dpacked_s); cudaFree(g.dpacked_kinv_s); cudaFree(g.dpacked_rt);
     g = GpHost();
@@ -173,7 +177,14 @@ static int effective_variant(const gpfo_ctx* ctx, int64_t N) {
     // GPFO_STRICT_ONCHIP=1) keeps the covariance strictly on chip at ~13% lower throughput.
     static const bool strict = getenv("GPFO_STRICT_ONCHIP") && atoi(getenv("GPFO_STRICT_ONCHIP")) != 0;
     if (!strict && N >= (int64_t)64 * 4 * ctx->num_sms) return 12;
-    if (N >= (int64_t)32 * ctx->num_sms) return 4;
+    if (N >= (int64_t)32 * ctx->num_sms) {
+        // a few tiles per SM: wave quantisation decides.  Cost model = waves x candidates per tile / measured efficiency
+        // (64-candidate tiles with scratch 0.73 of peak, 32-candidate tiles on chip 0.64).
+        const int64_t w64 = ((N + 63) / 64 + ctx->num_sms - 1) / ctx->num_sms;
+        const int64_t w32 = ((N + 31) / 32 + ctx->num_sms - 1) / ctx->num_sms;
+        if (!strict && (double)w64 * 64.0 / 0.73 < (double)w32 * 32.0 / 0.64) return 12;
+        return 4;
+    }
     return (N >= (int64_t)16 * ctx->num_sms) ? 5 : 6;
 }
 
@@ -201,15 +212,22 @@ static int ensure_partials(gpfo_ctx* ctx) {
     return GPFO_OK;
 }
 
+// Makes the block stream with `rbc` row blocks per chunk the GP's current one.  Both layouts in use (256- and 512-row chunks)
+// stay cached, so alternating batch sizes only re-sends the small GpDev record.
 static int repack(gpfo_ctx* ctx, GpHost& g, int rbc) {
     const PackGeom geom = make_geom(g.Mp / 8, rbc, 0);
-    const size_t need = (size_t)pg_total_blocks(geom) * 64;
-    CK(ensure(&g.dpacked, &g.cap_packed, need));
-    gpfo_pack_linv(ctx->stream, g.dLinv, g.Mf, geom, g.dpacked);
-    CK(cudaGetLastError());
+    const int slot = rbc == 32 ? 0 : 1;
+    if (!g.packed_ready[slot] || g.packed_slot_rbc[slot] != rbc) {
+        const size_t need = (size_t)pg_total_blocks(geom) * 64;
+        CK(ensure(&g.dpacked_by[slot], &g.cap_packed_by[slot], need));
+        gpfo_pack_linv(ctx->stream, g.dLinv, g.Mf, geom, g.dpacked_by[slot]);
+        CK(cudaGetLastError());
+        g.packed_ready[slot] = true;
+        g.packed_slot_rbc[slot] = rbc;
+    }
     g.packed_rbc = rbc;
     g.hdev.geom = geom;
-    g.hdev.packed = g.dpacked;
+    g.hdev.packed = g.dpacked_by[slot];
     CK(cudaMemcpyAsync(g.ddev, &g.hdev, sizeof(GpDev), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return GPFO_OK;
@@ -318,6 +336,7 @@ int gpfo_gp_set(gpfo_ctx* ctx, int gp_id, int64_t M64, int D, int R, const doubl
     g.kinv_ready = false;
     g.cluster_ready = false;
     g.rt_ready = false;
+    g.packed_ready[0] = g.packed_ready[1] = false;
     g.M = M; g.Mp = Mp; g.Mf = Mf; g.D = D; g.R = R; g.kind = kernel_kind; g.slot0 = slot0;
     memset(&g.hdev, 0, sizeof(GpDev));
     double ell[GPFO_MAX_DIM];
@@ -699,7 +718,7 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
             EvalIO gio = io;
             gio.write_moments = need_mom ? 1 : 0;
             gio.run_program = (!hv && !want_grad && g == ctx->ngps - 1) ? 1 : 0;
-            if (variant == 11 || variant == 12 || (variant >= 120 && variant <= 129)) {   // 12x: profiling builds of 12
+            if (variant == 11 || variant == 12 || variant == 13 || (variant >= 120 && variant <= 129)) {   // 12x: profiling builds of 12
                 // per-CTA K(X*,X) scratch: one slot per (training point, candidate of the tile), rounded up to whole groups
                 const size_t cols = ((size_t)ctx->gps[g].Mp + 127) / 128 * 128;
                 const size_t stride = cols * (size_t)gpfo_contract_tile(variant);
@@ -845,7 +864,7 @@ int gpfo_predict(gpfo_ctx* ctx, int gp_id, const double* X, int64_t N, int D, do
     int rc = stage_candidates(ctx, X, N, D, &dX);
     if (rc != GPFO_OK) return rc;
     int variant = effective_variant(ctx, N);
-    if (variant == 10 || variant == 12) variant = (N >= (int64_t)32 * ctx->num_sms) ? 4 : ((N >= (int64_t)16 * ctx->num_sms) ? 5 : 6);
+    if (variant == 10 || variant == 12 || variant == 13) variant = (N >= (int64_t)32 * ctx->num_sms) ? 4 : ((N >= (int64_t)16 * ctx->num_sms) ? 5 : 6);
     const int rbc = gpfo_contract_rbc(variant);
     if (g.packed_rbc != rbc) { rc = repack(ctx, g, rbc); if (rc != GPFO_OK) return rc; }
     const size_t need = (size_t)GPFO_MAX_SLOTS * N;
@@ -893,7 +912,7 @@ int gpfo_timings_get(const gpfo_ctx* ctx, gpfo_timings* out) {
 
 int gpfo_set_variant(gpfo_ctx* ctx, int variant) {
     if (!ctx) return GPFO_ERR_STATE;
-    static const int known[] = {0, 4, 5, 6, 10, 11, 12, 41, 42, 43, 121, 122, 123, 127};
+    static const int known[] = {0, 4, 5, 6, 10, 11, 12, 13, 41, 42, 43, 121, 122, 123, 125, 127};
     bool ok = false;
     for (int k : known) ok = ok || k == variant;
     if (!ok) return fail(ctx, GPFO_ERR_BAD_SHAPE, "unknown kernel variant");

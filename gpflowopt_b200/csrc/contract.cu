@@ -36,10 +36,11 @@ void gpfo_argmax_final(cudaStream_t st, const double* part_val, const long long*
 // variant table of the contraction kernel (contract2.cu); 10 = 2-CTA cluster kernel (contract3.cu, handled by the API).
 //    4: T=32, 512-row chunks, K(X*,X) regenerated per chunk (strictly on chip)      5 / 6: T=16 / T=8 (small batches)
 //   11: T=32 + per-CTA K(X*,X) scratch       12: T=64, 256-row chunks + scratch (default for large batches)
+//   13: the tiling of 12, warp-specialised (contract4.cu: 4 producer warps feed 16 DMMA warps through mbarrier stages)
 //   41-43, 121-123: ablations (no generation / no L^-1 loads / neither), 127: per-phase cycle counters -- profiling only
 struct VarInfo { int rbc, tile; };
 static VarInfo var_info(int v) {
-    if (v == 12 || (v >= 120 && v <= 129)) return {32, 64};
+    if (v == 12 || v == 13 || (v >= 120 && v <= 129)) return {32, 64};
     if (v == 5) return {64, 16};
     if (v == 6) return {64, 8};
     return {64, 32};
@@ -56,8 +57,12 @@ int gpfo_contract_grid(int variant, int64_t N, int num_sms) {
 cudaError_t gpfo_contract2_launch(cudaStream_t st, int variant, int kind, const GpDev* d_gp, const ProgramDev* d_prog,
                                   EvalIO io, int grid, int D);
 
+cudaError_t gpfo_contract_ws_launch(cudaStream_t st, int kind, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io,
+                                    int grid, int D);
+
 cudaError_t gpfo_contract_launch(cudaStream_t st, int variant, int kind, const GpDev* d_gp, const ProgramDev* d_prog,
                                  EvalIO io, int grid, int D) {
+    if (variant == 13) return gpfo_contract_ws_launch(st, kind, d_gp, d_prog, io, grid, D);
     return gpfo_contract2_launch(st, variant, kind, d_gp, d_prog, io, grid, D);
 }
 

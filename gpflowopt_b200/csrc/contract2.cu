@@ -66,7 +66,9 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     const int gen_nb = w % NB;
     const int gen_n = 8 * gen_nb + (lane >> 2);
     const int gen_jl = lane & 3;
-    const bool gen_first = ((w >> 2) & 1) == 0;          // warps w, w+4, w+8, w+12 share a scheduler: 2 + 2
+    // warps w, w+4, w+8, w+12 share a scheduler: 2 generate before their DMMA work, 2 after it.  ABL bit 256 (experiment):
+    // every warp generates first, i.e. generation runs as a burst with the DMMA pipe idle
+    const bool gen_first = (ABL & 256) ? true : ((w >> 2) & 1) == 0;
 
     constexpr bool TIM = (ABL & 64) != 0;             // profiling build: per-warp cycle counters per phase
     long long t_gen = 0, t_mma = 0, t_bar = 0, t_red = 0, t_all = 0, t_mark = 0;
@@ -563,6 +565,7 @@ cudaError_t gpfo_contract2_launch(cudaStream_t st, int variant, int kind, const 
         case 122: return launch2<16, 2, 8, 4, 10>(st, kind, d_gp, d_prog, io, grid, D);
         case 123: return launch2<16, 2, 8, 4, 11>(st, kind, d_gp, d_prog, io, grid, D);
         case 127: return launch2<16, 2, 8, 4, 8 + 64>(st, kind, d_gp, d_prog, io, grid, D);
+        case 125: return launch2<16, 2, 8, 4, 8 + 256>(st, kind, d_gp, d_prog, io, grid, D);
         case 6: return launch2<16, 4, 1, 4>(st, kind, d_gp, d_prog, io, grid, D);
         case 41: return launch2<16, 4, 4, 4, 1>(st, kind, d_gp, d_prog, io, grid, D);
         case 42: return launch2<16, 4, 4, 4, 2>(st, kind, d_gp, d_prog, io, grid, D);

@@ -3,7 +3,8 @@ import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gpflowopt_b200 import _lib, synthetic
-M, D, N = 2048, 8, 1000000
+M = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+D, N = 8, int(1000000 * min(4.0, (2048.0 / M) ** 2))
 X, Y = synthetic.training_set(M, D)
 ctx = _lib.Context(0)
 ctx.gp_set(0, X, Y, _lib.KERN_MATERN52, **synthetic.hypers(D))

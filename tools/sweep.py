@@ -51,14 +51,35 @@ def main():
         tf = N * M * (M + 1.0) / (t["hot_kernel_ms"] * 1e-3) / 1e12
         print("values  M=%5d N=%8d: factor %.1f ms, eval %.1f ms -> %.3e cand/s, %.2f TF/s (%.1f%% of peak), parity %.1e" % (
             M, N, fm, t["eval_ms"], N / (t["eval_ms"] * 1e-3), tf, 100 * tf / PEAK, rel(vals[sub], ref)), flush=True)
-        Ng = max(4096, N // 8)
+        Ng = max(40000, N // 8)
         ctx.eval(Xc[:2048], want_grads=True)
         vals, grads, _, _ = ctx.eval(Xc[:Ng], want_grads=True)
         t = ctx.timings()
         _, rg = oacq.Leaf('ei', g, fmin).value_and_grad(Xc[:200])
-        print("grads   M=%5d N=%8d: eval %.1f ms -> %.3e cand/s (%.2f TF/s of 3M^2 executed), grad parity %.1e" % (
-            M, Ng, t["eval_ms"], Ng / (t["eval_ms"] * 1e-3), Ng * 3.0 * M * M / (t["eval_ms"] * 1e-3) / 1e12,
-            rel(grads[:200], rg)), flush=True)
+        tfg = Ng * 2.0 * M * (M + 1.0) / (t["eval_ms"] * 1e-3) / 1e12          # algorithmic F_grad
+        print("grads   M=%5d N=%8d: eval %.1f ms -> %.3e cand/s, %.2f TF/s algorithmic 2M(M+1) (%.1f%% of peak, %s), grad parity %.1e" % (
+            M, Ng, t["eval_ms"], Ng / (t["eval_ms"] * 1e-3), tfg, 100 * tfg / PEAK,
+            "stored-A" if t["launches"] == 4 and Ng >= 37888 else "dense K^-1", rel(grads[:200], rg)), flush=True)
+    # ---- config #5 upper end: N = 1e8 device-generated candidates (no N x D array anywhere), M = 512 ---------------
+    M, N = 512, 10 ** 8
+    g = model(M, 8)
+    upload(ctx, 0, g, 0)
+    ctx.gp_count_set(1)
+    ctx.program_set([[_lib.OP_EI, 0, 0, 0]], [-1.5])
+    lower, upper = np.zeros(8), np.ones(8)
+    ctx.eval_random(4321, 0, 10 ** 6, lower, upper)
+    _, bv, bi = ctx.eval_random(4321, 0, N, lower, upper)
+    t = ctx.timings()
+    xbest = _lib.random_rows(4321, bi, 1, lower, upper)
+    first = 77000000
+    vals, _, _ = ctx.eval_random(4321, first, 20000, lower, upper, want_values=True)
+    rows = _lib.random_rows(4321, first, 20000, lower, upper)
+    leaf = oacq.Leaf('ei', g, -1.5)
+    print("N=1e8 device-generated, M=512: eval %.1f ms -> %.3e cand/s (%.2f TF/s, %.1f%% of peak); winner row %d regenerated on the host: "
+          "oracle value rel. diff %.1e; parity on regenerated rows %d..%d: %.1e" % (
+              t["eval_ms"], N / (t["eval_ms"] * 1e-3), N * M * (M + 1.0) / (t["eval_ms"] * 1e-3) / 1e12,
+              100 * N * M * (M + 1.0) / (t["eval_ms"] * 1e-3) / 1e12 / PEAK, bi,
+              abs(leaf.value(xbest)[0, 0] - bv) / abs(bv), first, first + 20000, rel(vals, leaf.value(rows))), flush=True)
     # ---- config #3: EI x PoF, two GPs, M = 4096, D = 16 (one GPU's shard of the 1e7 / 8-GPU job) -----------------
     M, D, N = 4096, 16, 1250000
     g1, g2 = model(M, D, constraint=True, col=0), model(M, D, constraint=True, col=1)
