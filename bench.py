@@ -125,7 +125,7 @@ def run_reference(args):
     dt = float(np.mean(times))
     value = n_sample / dt
     sample = "%d candidates per step in 4096-row chunks, Cholesky hoisted, NumPy/SciPy + OpenBLAS" % n_sample
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -133,10 +133,29 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "GPflowOpt 0.1.1 needs GPflow 0.5.0 + TensorFlow 1.x (absent, not installable): the reference arm is "
-                "the CPU oracle port of its path (oracle/), all host threads via OpenBLAS"}))
+                "the CPU oracle port of its path (oracle/), all host threads via OpenBLAS"})
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout: everything else a library prints on fd 1 (NCCL prints its version banner
+    there) is sent to stderr; emit() writes the line to the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(obj) + "\n").encode())
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -290,7 +309,7 @@ def main():
             out["cpu_baseline"] = {"value": v_cpu, "unit": UNIT, "cores": host_threads(), "kind": "port",
                                    "sample": "%d candidates (%.1f s) in 4096-row chunks, Cholesky hoisted, "
                                              "NumPy/SciPy + OpenBLAS on all host cores" % (n_cpu, dt)}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         td.destroy_process_group()
 
