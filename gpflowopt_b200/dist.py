@@ -52,6 +52,50 @@ def broadcast_points(points):
     return buf.cpu().numpy()
 
 
+def scatter_points(points):
+    """Rank 0's candidate matrix split into the contiguous row blocks of ``shard_bounds``: every rank receives only its own
+    block (N x D doubles leave rank 0 once instead of world_size times).  Returns (block, lo, n_total); under NCCL the block
+    is a CUDA tensor that is scored in place through the device-pointer entry, otherwise a NumPy array."""
+    td = _pg()
+    if td is None or td.get_world_size() == 1:
+        return points, 0, points.shape[0]
+    import torch
+    dev = _device_for_collectives(td)
+    rank, ws = td.get_rank(), td.get_world_size()
+    shape = torch.tensor(list(points.shape), dtype=torch.int64, device=dev)
+    td.broadcast(shape, src=0)
+    n, d = int(shape[0]), int(shape[1])
+    per = max(1, -(-n // ws))
+    out = torch.empty((per, d), dtype=torch.float64, device=dev)
+    chunks = None
+    if rank == 0:
+        full = torch.zeros((ws * per, d), dtype=torch.float64, device=dev)
+        full[:n] = torch.from_numpy(np.ascontiguousarray(points, dtype=np.float64)).to(dev)
+        chunks = list(full.split(per))
+    td.scatter(out, scatter_list=chunks, src=0)
+    lo, hi = shard_bounds(n, rank, ws)
+    block = out[:hi - lo]
+    return (block if block.is_cuda else block.numpy()), lo, n
+
+
+def fetch_row(block, lo, index, n_total, d):
+    """Row ``index`` of the scattered matrix on every rank (its owner broadcasts D doubles)."""
+    td = _pg()
+    if td is None or td.get_world_size() == 1:
+        return np.array(block[index - lo:index - lo + 1], dtype=np.float64)
+    import torch
+    dev = _device_for_collectives(td)
+    ws = td.get_world_size()
+    per = max(1, -(-n_total // ws))
+    owner = int(index // per)
+    row = torch.empty((1, d), dtype=torch.float64, device=dev)
+    if td.get_rank() == owner:
+        src = block[index - lo:index - lo + 1]
+        row.copy_(src if hasattr(src, 'is_cuda') else torch.from_numpy(np.ascontiguousarray(src)))
+    td.broadcast(row, src=owner)
+    return row.cpu().numpy()
+
+
 def broadcast_int(value):
     """Rank 0's integer on every rank (seed of the device candidate generator)."""
     td = _pg()

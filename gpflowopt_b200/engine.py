@@ -164,7 +164,15 @@ class Engine(object):
         return (vals, grads) if gradients else vals
 
     def argmax(self, acq, X):
-        """Best (value, index) over the candidate rows without bringing the scores back to the host."""
+        """Best (value, index) over the candidate rows without bringing the scores back to the host.  ``X`` is a host
+        array or a CUDA float64 tensor on this engine's device (torch is only the buffer owner: the rows are read in place)."""
+        if hasattr(X, 'data_ptr') and getattr(X, 'is_cuda', False):
+            import torch
+            assert X.dtype == torch.float64 and X.dim() == 2
+            X = X.contiguous()
+            torch.cuda.current_stream(X.device).synchronize()      # the library launches on its own stream
+            self.prepare(acq)
+            return self.ctx.eval_device(X.data_ptr(), X.shape[0], X.shape[1])
         X = np.atleast_2d(np.asarray(X, dtype=np.float64))
         self.prepare(acq)
         _, _, bv, bi = self.ctx.eval(X, want_values=False, want_grads=False)

@@ -116,12 +116,19 @@ class MCOptimizer(Optimizer):
             return self._optimize_device_rng(objective, acq)
         points = self._get_eval_points()
         if acq is not None:
-            # fused route: argmin of -acq == argmax of acq with the same first-occurrence tie-break
-            points = dist.broadcast_points(points)
-            best, idx = dist.sharded_argmax(acq.argmax, points)
-            objective.counter += points.shape[0]
-            return OptimizeResult(x=points[[idx], :], success=True, fun=np.array([[-best]]),
-                                  nfev=points.shape[0], message="OK")
+            # fused route: argmin of -acq == argmax of acq with the same first-occurrence tie-break.  Under
+            # torch.distributed the rows are rank 0's, every rank receives and scores only its own block
+            n_total, d = points.shape
+            block, lo, n_total = dist.scatter_points(points)
+            if block.shape[0] > 0:
+                v, i = acq.argmax(block)
+                i = i + lo if i >= 0 else -1
+            else:
+                v, i = 0.0, -1
+            best, idx = dist.reduce_pairs(*dist.allgather_pair(v, i))
+            objective.counter += n_total
+            x = dist.fetch_row(block, lo, idx, n_total, d) if idx >= 0 else np.empty((0, d))
+            return OptimizeResult(x=x, success=True, fun=np.array([[-best]]), nfev=n_total, message="OK")
         evaluations = objective(points)
         idx_best = np.argmin(evaluations, axis=0)
         return OptimizeResult(x=points[idx_best, :], success=True, fun=evaluations[idx_best, :],

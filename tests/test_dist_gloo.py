@@ -43,6 +43,24 @@ WORKER = textwrap.dedent("""
     assert i3 == 0
     v4, i4 = dist.sharded_argmax(local_argmax, pts[:0])
     assert i4 == -1
+    # scatter route used by MCOptimizer / CandidateOptimizer: every rank receives only its own row block of rank 0's matrix
+    src = synthetic.candidates(1001, 3) if td.get_rank() == 0 else np.full((7, 2), np.nan)
+    block, lo, n = dist.scatter_points(src)
+    blo, bhi = dist.shard_bounds(1001, td.get_rank(), td.get_world_size())
+    assert n == 1001 and lo == blo and block.shape == (bhi - blo, 3) and np.array_equal(block, pts[blo:bhi])
+    for idx in (0, 500, 501, 1000):
+        assert np.array_equal(dist.fetch_row(block, lo, idx, n, 3), pts[[idx]])
+    from gpflowopt_b200.optim import CandidateOptimizer
+    from gpflowopt_b200.domain import UnitCube
+    class Acq(object):                                     # stands in for a gpflowopt_b200 acquisition (fused route)
+        def argmax(self, rows):
+            return local_argmax(np.asarray(rows))
+    def inverse(x):
+        return -ei.value(np.atleast_2d(x))
+    inverse.acquisition = Acq()
+    cands = pts if td.get_rank() == 0 else pts[::-1].copy()     # only rank 0's matrix counts
+    res = CandidateOptimizer(UnitCube(3), cands).optimize(inverse)
+    assert np.array_equal(res.x, pts[[i]]) and float(res.fun[0, 0]) == -v and res.nfev == 1001
     print("rank %%d ok %%d %%r" %% (td.get_rank(), i, v))
     td.destroy_process_group()
 """) % ROOT
