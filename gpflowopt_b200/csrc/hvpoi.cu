@@ -21,7 +21,7 @@
 // GRAD: also d(Hv PoI)/d mean_j and /d var_j per candidate (closed form of SURVEY Appendix A item 10), fed through the
 // forward-mode program evaluation; writes the per-slot coefficients the contraction kernel's gradient mode consumes.
 template <int R, bool GRAD>
-__global__ void __launch_bounds__(HV_THREADS)
+__global__ void __launch_bounds__(HV_THREADS, GRAD ? 1 : 2)
 hvpoi_kernel(const ProgramDev* __restrict__ prog, CellsDev cells, EvalIO io, int slot_first) {
     extern __shared__ __align__(16) double sm[];
     const int n_ext = cells.n_ext;
