@@ -434,6 +434,7 @@ def test_large_candidate_batch_device_resident(ctx):
     gen = torch.Generator(device="cuda").manual_seed(7)
     Xd = torch.rand((N, 4), dtype=torch.float64, device="cuda", generator=gen)
     vd = torch.empty(N, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()                  # the library launches on its own stream: torch's generator must be done
     bv, bi = ctx.eval_device(Xd.data_ptr(), N, 4, vd.data_ptr())
     torch.cuda.synchronize()
     assert int(torch.argmax(vd)) == bi and float(vd[bi]) == bv
