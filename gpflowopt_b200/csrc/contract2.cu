@@ -554,18 +554,22 @@ static cudaError_t launch2(cudaStream_t st, int kind, const GpDev* d_gp, const P
     }
 }
 
+// Ring depth of the 64-candidate tiling (variant 12 and its gradient-pass relatives).  Measured at M = 2048: S = 3: 27.23,
+// 4: 26.95, 5: 27.34, 6: 27.33, 7: 27.36 TF/s -- five stages of 1 KB per warp
+constexpr int S12 = 5;
+
 // variants: see the table in contract.cu
 cudaError_t gpfo_contract2_launch(cudaStream_t st, int variant, int kind, const GpDev* d_gp, const ProgramDev* d_prog,
                                   EvalIO io, int grid, int D) {
     switch (variant) {
         case 5: return launch2<16, 4, 2, 4>(st, kind, d_gp, d_prog, io, grid, D);
         case 11: return launch2<16, 4, 4, 4, 8>(st, kind, d_gp, d_prog, io, grid, D);
-        case 12: return launch2<16, 2, 8, 4, 8>(st, kind, d_gp, d_prog, io, grid, D);
-        case 121: return launch2<16, 2, 8, 4, 9>(st, kind, d_gp, d_prog, io, grid, D);
-        case 122: return launch2<16, 2, 8, 4, 10>(st, kind, d_gp, d_prog, io, grid, D);
-        case 123: return launch2<16, 2, 8, 4, 11>(st, kind, d_gp, d_prog, io, grid, D);
-        case 127: return launch2<16, 2, 8, 4, 8 + 64>(st, kind, d_gp, d_prog, io, grid, D);
-        case 125: return launch2<16, 2, 8, 4, 8 + 256>(st, kind, d_gp, d_prog, io, grid, D);
+        case 12: return launch2<16, 2, 8, S12, 8>(st, kind, d_gp, d_prog, io, grid, D);
+        case 121: return launch2<16, 2, 8, S12, 9>(st, kind, d_gp, d_prog, io, grid, D);
+        case 122: return launch2<16, 2, 8, S12, 10>(st, kind, d_gp, d_prog, io, grid, D);
+        case 123: return launch2<16, 2, 8, S12, 11>(st, kind, d_gp, d_prog, io, grid, D);
+        case 127: return launch2<16, 2, 8, S12, 8 + 64>(st, kind, d_gp, d_prog, io, grid, D);
+        case 125: return launch2<16, 2, 8, S12, 8 + 256>(st, kind, d_gp, d_prog, io, grid, D);
         case 6: return launch2<16, 4, 1, 4>(st, kind, d_gp, d_prog, io, grid, D);
         case 41: return launch2<16, 4, 4, 4, 1>(st, kind, d_gp, d_prog, io, grid, D);
         case 42: return launch2<16, 4, 4, 4, 2>(st, kind, d_gp, d_prog, io, grid, D);
@@ -602,18 +606,18 @@ cudaError_t gpfo_contract_grad_split_launch(cudaStream_t st, int kind, const GpD
 // also parks A per tile; backward = the same tiles over the reversed transposed stream, all groups read back, M^2 flop.
 int gpfo_contract_bwd_rbc() { return 32; }
 int gpfo_contract_bwd_tile() { return 64; }
-long long gpfo_contract_astore_stride(int nrb) { return (long long)((nrb + KPC - 1) / KPC) * Contract2Cfg<16, 2, 8, 4>::GROUP_SLOTS; }
+long long gpfo_contract_astore_stride(int nrb) { return (long long)((nrb + KPC - 1) / KPC) * Contract2Cfg<16, 2, 8, S12>::GROUP_SLOTS; }
 size_t gpfo_contract_bwd_smem(int D) {
-    using C = Contract2Cfg<16, 2, 8, 4>;
+    using C = Contract2Cfg<16, 2, 8, S12>;
     return ((size_t)16 * C::RING_DOUBLES_PER_WARP + 3 * C::GROUP_SLOTS + (size_t)D * C::T + C::T + C::T * (1 + RMAX) +
             2 * ((C::T + 31) / 32) + 34 + C::T * RMAX + C::T + C::T * (1 + (size_t)D)) * sizeof(double);
 }
 cudaError_t gpfo_contract_astore_launch(cudaStream_t st, int kind, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io,
                                         int grid, int D) {
-    return launch2<16, 2, 8, 4, 8 + 128>(st, kind, d_gp, d_prog, io, grid, D);
+    return launch2<16, 2, 8, S12, 8 + 128>(st, kind, d_gp, d_prog, io, grid, D);
 }
 cudaError_t gpfo_contract_bwd_launch(cudaStream_t st, int kind, const GpDev* d_gp, EvalIO io, int grid, int D) {
-    return launch2<16, 2, 8, 4, 32>(st, kind, d_gp, nullptr, io, grid, D);
+    return launch2<16, 2, 8, S12, 32>(st, kind, d_gp, nullptr, io, grid, D);
 }
 
 // gradient pass launcher (dense K^-1 stream; T = 32 candidates per tile, 512-row chunks)
