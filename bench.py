@@ -35,7 +35,7 @@ METRIC = "acq candidate evals/sec (M=2048,D=8,fp64)"
 # taken from profiles/r01_final_contract2_v12.metrics.csv (27.7 GB read + 16.3 GB written: the per-CTA K(X*,X) scratch of
 # variant 12 is written back to HBM and partly re-read from it -- an earlier capture of the same kernel saw 44.7 GB read, the
 # split between L2 hits and HBM varies; the strictly on-chip variant 4 moves 36.5 MB per launch)
-NCU_DRAM_BYTES_PER_LAUNCH = 27688032000 + 16292329000      # profiles/r01_final_contract2_v12.metrics.csv (read + write)
+NCU_DRAM_BYTES_PER_LAUNCH = 27688939000 + 16286433000      # profiles/r01_final_contract2_v12.metrics.csv (read + write)
 UNIT = "candidates/s"
 
 
