@@ -179,11 +179,11 @@ static int effective_variant(const gpfo_ctx* ctx, int64_t N) {
     if (!strict && N >= (int64_t)64 * 4 * ctx->num_sms) return 12;
     if (N >= (int64_t)32 * ctx->num_sms) {
         // a few tiles per SM: wave quantisation decides.  Cost model = waves x candidates per tile / measured efficiency
-        // (64-candidate tiles with scratch 0.73 of peak, 32-candidate tiles on chip 0.64).
+        // (64-candidate tiles with scratch 0.73 of peak, 32-candidate tiles with scratch 0.70, on chip 0.64).
+        if (strict) return 4;
         const int64_t w64 = ((N + 63) / 64 + ctx->num_sms - 1) / ctx->num_sms;
         const int64_t w32 = ((N + 31) / 32 + ctx->num_sms - 1) / ctx->num_sms;
-        if (!strict && (double)w64 * 64.0 / 0.73 < (double)w32 * 32.0 / 0.64) return 12;
-        return 4;
+        return ((double)w64 * 64.0 / 0.73 < (double)w32 * 32.0 / 0.70) ? 12 : 11;
     }
     return (N >= (int64_t)16 * ctx->num_sms) ? 5 : 6;
 }
@@ -864,7 +864,7 @@ int gpfo_predict(gpfo_ctx* ctx, int gp_id, const double* X, int64_t N, int D, do
     int rc = stage_candidates(ctx, X, N, D, &dX);
     if (rc != GPFO_OK) return rc;
     int variant = effective_variant(ctx, N);
-    if (variant == 10 || variant == 12 || variant == 13) variant = (N >= (int64_t)32 * ctx->num_sms) ? 4 : ((N >= (int64_t)16 * ctx->num_sms) ? 5 : 6);
+    if (variant == 10 || variant == 11 || variant == 12 || variant == 13) variant = (N >= (int64_t)32 * ctx->num_sms) ? 4 : ((N >= (int64_t)16 * ctx->num_sms) ? 5 : 6);
     const int rbc = gpfo_contract_rbc(variant);
     if (g.packed_rbc != rbc) { rc = repack(ctx, g, rbc); if (rc != GPFO_OK) return rc; }
     const size_t need = (size_t)GPFO_MAX_SLOTS * N;

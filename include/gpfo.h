@@ -159,7 +159,7 @@ int gpfo_timings_get(const gpfo_ctx* ctx, gpfo_timings* out);
  * 8/16/32-candidate tiles for mid-size batches, 64-candidate tiles + K(X*,X) scratch for large ones; large gradient batches
  * take the stored-A pass).  Explicit values (4, 5, 6, 11, 12: tile widths; 10, 13: experimental cluster / warp-specialised
  * kernels; 41-43, 121-127: profiling builds) pin one kernel; see the table in csrc/contract.cu and DESIGN.md 4.1 / 8.
- * Environment switches read per call: GPFO_STRICT_ONCHIP=1 (never park K(X*,X) in global memory), GPFO_GRAD_DENSE=1
+ * Environment switches: GPFO_STRICT_ONCHIP=1 (read once: never park K(X*,X) in global memory); per call GPFO_GRAD_DENSE=1
  * (gradient pass over the dense K^-1 stream for every batch size), GPFO_ASTORE_BUDGET_MB (bound of the stored-A scratch). */
 int gpfo_set_variant(gpfo_ctx* ctx, int variant);
 
