@@ -172,20 +172,24 @@ int gpfo_ctx_destroy(gpfo_ctx* ctx) {
 
 static int effective_variant(const gpfo_ctx* ctx, int64_t N) {
     if (ctx->variant >= 1) return ctx->variant;
-    // automatic (v2 kernel): the widest candidate tile that still gives every SM a few tiles.  The 64-candidate variant
-    // parks K(X*,X) of the tile in a per-CTA global scratch (variant 12); `strict_onchip` (gpfo_set_variant(ctx, 4) or
-    // GPFO_STRICT_ONCHIP=1) keeps the covariance strictly on chip at ~13% lower throughput.
+    // automatic: 64-candidate tiles with the K(X*,X) tile parked in a per-CTA global scratch (variant 12) for large
+    // batches; `strict_onchip` (gpfo_set_variant(ctx, 4) or GPFO_STRICT_ONCHIP=1) keeps the covariance strictly on chip
+    // at ~13% lower throughput.  Below four waves of 64-candidate tiles wave quantisation decides: cost = waves of tiles x
+    // measured time of one wave relative to the others (M = 2048: 0.29 / 0.50 / 0.77 (0.85 on chip) / 1.46 ms for
+    // T = 8 / 16 / 32 / 64); ties go to the wider tile.
     static const bool strict = getenv("GPFO_STRICT_ONCHIP") && atoi(getenv("GPFO_STRICT_ONCHIP")) != 0;
     if (!strict && N >= (int64_t)64 * 4 * ctx->num_sms) return 12;
-    if (N >= (int64_t)32 * ctx->num_sms) {
-        // a few tiles per SM: wave quantisation decides.  Cost model = waves x candidates per tile / measured efficiency
-        // (64-candidate tiles with scratch 0.73 of peak, 32-candidate tiles with scratch 0.70, on chip 0.64).
-        if (strict) return 4;
-        const int64_t w64 = ((N + 63) / 64 + ctx->num_sms - 1) / ctx->num_sms;
-        const int64_t w32 = ((N + 31) / 32 + ctx->num_sms - 1) / ctx->num_sms;
-        return ((double)w64 * 64.0 / 0.73 < (double)w32 * 32.0 / 0.70) ? 12 : 11;
+    const int var[4] = {6, 5, strict ? 4 : 11, 12};
+    const int tile[4] = {8, 16, 32, 64};
+    const double wave_cost[4] = {0.29, 0.50, strict ? 0.85 : 0.77, 1.46};
+    int best = 0;
+    double best_cost = 0.0;
+    for (int k = 0; k < (strict ? 3 : 4); ++k) {
+        const int64_t tiles = (N + tile[k] - 1) / tile[k];
+        const double cost = (double)((tiles + ctx->num_sms - 1) / ctx->num_sms) * wave_cost[k];
+        if (k == 0 || cost <= best_cost) { best = k; best_cost = cost; }
     }
-    return (N >= (int64_t)16 * ctx->num_sms) ? 5 : 6;
+    return var[best];
 }
 
 static PackGeom make_geom(int nrb, int rbc, int dense) {
