@@ -512,15 +512,29 @@ static int ensure_parts(gpfo_ctx* ctx, int n) {
     return GPFO_OK;
 }
 
-int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_values, double* out_grads,
-              double* best_value, int64_t* best_index) {
-    if (!ctx) return GPFO_ERR_STATE;
-    cudaSetDevice(ctx->device);
+// What one gpfo_eval call launches, decided once up front.
+struct EvalPlan {
+    int64_t N;
+    int D, variant, grid, hv_grid, pg_grid, slot_first;
+    bool use_cluster, hv, want_grad, need_mom, generate;
+};
+
+// Two device buffers of the same size that grow together ([slot][N] moment / coefficient arrays).
+static int ensure_pair(gpfo_ctx* ctx, double** a, double** b, size_t* cap, size_t need) {
+    if (*cap >= need) return GPFO_OK;
+    cudaFree(*a); cudaFree(*b);
+    *a = *b = nullptr; *cap = 0;
+    CK(cudaMalloc((void**)a, need * sizeof(double)));
+    CK(cudaMalloc((void**)b, need * sizeof(double)));
+    *cap = need;
+    return GPFO_OK;
+}
+
+// State checks of gpfo_eval: program, models, moment slots, cell tables.
+static int check_eval_state(gpfo_ctx* ctx, int D, bool want_grad) {
     if (!ctx->prog_set) return fail(ctx, GPFO_ERR_STATE, "gpfo_eval before gpfo_program_set");
     if (ctx->ngps < 1) return fail(ctx, GPFO_ERR_STATE, "gpfo_eval before gpfo_gp_set");
-    if (N < 0) return fail(ctx, GPFO_ERR_BAD_SHAPE, "N < 0");
-    // which slots are produced by the registered GPs?
-    bool have[GPFO_MAX_SLOTS] = {false};
+    bool have[GPFO_MAX_SLOTS] = {false};               // which slots are produced by the registered GPs?
     for (int g = 0; g < ctx->ngps; ++g) {
         const GpHost& gp = ctx->gps[g];
         if (!gp.valid) return fail(ctx, GPFO_ERR_STATE, "a GP below gp count was never set");
@@ -530,10 +544,199 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     for (int s = 0; s < ctx->hprog.nslots; ++s)
         if (!have[s]) return fail(ctx, GPFO_ERR_STATE, "program references a moment slot no GP produces");
     if (ctx->hprog.has_hvpoi && !ctx->cells_set) return fail(ctx, GPFO_ERR_STATE, "HVPoI program without gpfo_cells_set");
-    const bool want_grad = out_grads != nullptr;
     if (want_grad && ctx->hprog.has_hvpoi &&
         gpfo_hvpoi_smem_bytes_grad(ctx->cells.n_ext, ctx->cells.R) > 227 * 1024)
         return fail(ctx, GPFO_ERR_UNSUPPORTED, "Pareto front too large for the gradient HVPoI kernel");
+    return GPFO_OK;
+}
+
+// Large gradient batch: forward launches park A = L^-1 Kx, backward launches contract it with the reversed transposed
+// stream (2 M^2 flop per candidate and GP in total instead of 3 M^2).  A lives in a bounded scratch, so the batch is
+// processed in slabs of whole tiles: forward (all GPs) -> program partials -> backward (all GPs).
+static int launch_stored_a(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* launches_out, int* nparts_out, float* hot_ms_out) {
+    cudaStream_t st = ctx->stream;
+    const int64_t N = pl.N;
+    const int D = pl.D, slot_first = pl.slot_first;
+    const bool hv = pl.hv;
+    int launches = 0, nparts = 0, rc = GPFO_OK;
+    float hot_ms = 0.f;
+    const int Tt = gpfo_contract_bwd_tile();
+    const int64_t ntiles = (N + Tt - 1) / Tt;
+    size_t per_tile = 0;                                   // doubles of A per tile, all GPs
+    for (int g = 0; g < ctx->ngps; ++g) per_tile += (size_t)gpfo_contract_astore_stride(ctx->gps[g].Mp / 8);
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = (free_b + ctx->cap_a_scratch * sizeof(double)) / 4;
+    if (budget > ((size_t)8 << 30)) budget = (size_t)8 << 30;
+    if (const char* mb = getenv("GPFO_ASTORE_BUDGET_MB")) budget = (size_t)atoll(mb) << 20;      // tests: force several slabs
+    int64_t slab_tiles = (int64_t)(budget / (per_tile * sizeof(double)));
+    if (slab_tiles < ctx->num_sms) slab_tiles = ctx->num_sms;
+    if (slab_tiles > ntiles) slab_tiles = ntiles;
+    CK(ensure(&ctx->da_scratch, &ctx->cap_a_scratch, (size_t)slab_tiles * per_tile));
+    const int64_t nslabs = (ntiles + slab_tiles - 1) / slab_tiles;
+    const int sgrid = (int)(slab_tiles < ctx->num_sms ? slab_tiles : ctx->num_sms);
+    const int64_t slab_n = slab_tiles * Tt;
+    const int ppg = hv ? gpfo_hvpoi_grid(slab_n, ctx->num_sms) : gpfo_program_grad_grid(slab_n, ctx->num_sms);
+    rc = ensure_parts(ctx, (int)(nslabs * ppg));
+    if (rc != GPFO_OK) return rc;
+    io.part_val = ctx->dpart_val; io.part_idx = ctx->dpart_idx;
+    size_t kx_need = 0;
+    for (int g = 0; g < ctx->ngps; ++g) {
+        const size_t cols = ((size_t)ctx->gps[g].Mp + 127) / 128 * 128;
+        if (cols * Tt * (size_t)sgrid > kx_need) kx_need = cols * Tt * (size_t)sgrid;
+    }
+    CK(ensure(&ctx->dkx_scratch, &ctx->cap_kx_scratch, kx_need));
+    nparts = 0;
+    for (int64_t k = 0; k < nslabs; ++k) {
+        const int64_t n0 = k * slab_n;
+        const int64_t ns = (N - n0 < slab_n) ? N - n0 : slab_n;
+        const int64_t st_tiles = (ns + Tt - 1) / Tt;
+        const int g_s = (int)(st_tiles < sgrid ? st_tiles : sgrid);
+        EvalIO sio = io;
+        sio.X = io.X + (size_t)n0 * D; sio.N = ns; sio.idx0 = n0;
+        sio.mom_mean = io.mom_mean + n0; sio.mom_var = io.mom_var + n0;
+        sio.cmu = io.cmu + n0; sio.cva = io.cva + n0;
+        if (io.values) sio.values = io.values + n0;
+        sio.grads = io.grads + (size_t)n0 * D;
+        sio.part_val = io.part_val + nparts; sio.part_idx = io.part_idx + nparts;
+        size_t a_off = 0;
+        for (int g = 0; g < ctx->ngps; ++g) {
+            const GpHost& gh = ctx->gps[g];
+            EvalIO gio = sio;
+            gio.write_moments = 1; gio.run_program = 0;
+            gio.kx_scratch = ctx->dkx_scratch;
+            gio.kx_scratch_stride = (long long)(((size_t)gh.Mp + 127) / 128 * 128 * Tt);
+            gio.a_scratch = ctx->da_scratch + a_off;
+            gio.a_stride = gpfo_contract_astore_stride(gh.Mp / 8);
+            a_off += (size_t)slab_tiles * (size_t)gio.a_stride;
+            if (k == 0 && g == 0) CK(cudaEventRecord(ctx->ev[6], st));
+            CK(gpfo_contract_astore_launch(st, gh.kind, gh.ddev, ctx->dprog, gio, g_s, D));
+            if (k == 0 && g == 0) CK(cudaEventRecord(ctx->ev[7], st));
+            ++launches;
+        }
+        int parts_k;
+        if (hv) {
+            EvalIO hio = sio;
+            hio.run_program = 1;
+            parts_k = gpfo_hvpoi_grid(ns, ctx->num_sms);
+            CK(gpfo_hvpoi_launch(st, ctx->dprog, ctx->cells, hio, parts_k, slot_first, 1));
+        } else {
+            parts_k = gpfo_program_grad_grid(ns, ctx->num_sms);
+            CK(gpfo_program_grad_launch(st, ctx->dprog, sio, parts_k));
+        }
+        ++launches;
+        nparts += parts_k;
+        a_off = 0;
+        for (int g = 0; g < ctx->ngps; ++g) {
+            const GpHost& gh = ctx->gps[g];
+            EvalIO gio = sio;
+            gio.grad_accumulate = g > 0 ? 1 : 0;
+            gio.packed_o = gh.dpacked_rt; gio.geom_o = gh.geom_rt;
+            gio.a_scratch = ctx->da_scratch + a_off;
+            gio.a_stride = gpfo_contract_astore_stride(gh.Mp / 8);
+            a_off += (size_t)slab_tiles * (size_t)gio.a_stride;
+            CK(gpfo_contract_bwd_launch(st, gh.kind, gh.ddev, gio, g_s, D));
+            ++launches;
+        }
+    }
+    if (ctx->ngps > 1) { CK(cudaEventSynchronize(ctx->ev[7])); float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); hot_ms = ms; }
+    *launches_out = launches; *nparts_out = nparts; *hot_ms_out = hot_ms;
+    return GPFO_OK;
+}
+
+// Everything else: one forward launch per GP (row-split for few candidates), then the HVPoI / program-gradient kernel and,
+// for gradients, the dense K^-1 pass per GP.
+static int launch_standard(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* launches_out, int* nparts_out, float* hot_ms_out) {
+    cudaStream_t st = ctx->stream;
+    const int64_t N = pl.N;
+    const int D = pl.D, variant = pl.variant, grid = pl.grid, hv_grid = pl.hv_grid, pg_grid = pl.pg_grid, slot_first = pl.slot_first;
+    const bool hv = pl.hv, want_grad = pl.want_grad, need_mom = pl.need_mom, generate = pl.generate, use_cluster = pl.use_cluster;
+    int launches = 0, nparts = grid, fwd_parts = grid;
+    float hot_ms = 0.f;
+    for (int g = 0; g < ctx->ngps; ++g) {
+        EvalIO gio = io;
+        gio.write_moments = need_mom ? 1 : 0;
+        gio.run_program = (!hv && !want_grad && g == ctx->ngps - 1) ? 1 : 0;
+        if (variant == 11 || variant == 12 || variant == 13 || (variant >= 120 && variant <= 129)) {   // 12x: profiling builds of 12
+            // per-CTA K(X*,X) scratch: one slot per (training point, candidate of the tile), rounded up to whole groups
+            const size_t cols = ((size_t)ctx->gps[g].Mp + 127) / 128 * 128;
+            const size_t stride = cols * (size_t)gpfo_contract_tile(variant);
+            CK(ensure(&ctx->dkx_scratch, &ctx->cap_kx_scratch, stride * (size_t)grid));
+            gio.kx_scratch = ctx->dkx_scratch;
+            if (variant == 127) {          // profiling build: phase counters land at the start of the values buffer
+                CK(ensure(&ctx->dvalues, &ctx->cap_values, (size_t)(N > 65536 ? N : 65536)));
+                gio.debug = reinterpret_cast<long long*>(ctx->dvalues);
+                gio.values = nullptr;
+            }
+            gio.kx_scratch_stride = (long long)stride;
+        }
+        CK(cudaEventRecord(ctx->ev[6], st));
+        const int ns = generate ? 1 : split_count(ctx, N, gpfo_split_tile(), ctx->gps[g].geom_s.nchunks);
+        if (ns > 1) {
+            gio.packed_o = ctx->gps[g].dpacked_s; gio.geom_o = ctx->gps[g].geom_s;
+            gio.nsplit = ns; gio.partials = ctx->dpartials;
+            CK(gpfo_contract_split_launch(st, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, D));
+            ++launches;
+            fwd_parts = (int)((N + 127) / 128);
+        } else {
+            if (use_cluster) CK(gpfo_contract3_launch(st, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
+            else CK(gpfo_contract_launch(st, variant, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
+            fwd_parts = grid;
+        }
+        CK(cudaEventRecord(ctx->ev[7], st));
+        ++launches;
+        if (ctx->ngps > 1) {                 // per-GP timing needs a sync only when events are reused
+            CK(cudaEventSynchronize(ctx->ev[7]));
+            float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); hot_ms += ms;
+        }
+    }
+    nparts = fwd_parts;
+    if (hv) {
+        EvalIO hio = io;
+        hio.run_program = 1;
+        CK(gpfo_hvpoi_launch(st, ctx->dprog, ctx->cells, hio, hv_grid, slot_first, want_grad ? 1 : 0));
+        ++launches;
+        nparts = hv_grid;
+    } else if (want_grad) {
+        CK(gpfo_program_grad_launch(st, ctx->dprog, io, pg_grid));
+        ++launches;
+        nparts = pg_grid;
+    }
+    if (want_grad) {
+        // chain rule through each GP: W = K^-1 Kx on DMMA, then the (1+D)-wide reduction over the training points
+        const int ggrid = gpfo_contract_grad_grid(N, ctx->num_sms);
+        for (int g = 0; g < ctx->ngps; ++g) {
+            EvalIO gio = io;
+            gio.grad_accumulate = g > 0 ? 1 : 0;
+            const GpHost& gh = ctx->gps[g];
+            const int ns_small = split_count(ctx, N, gpfo_split_tile(), gh.geom_kinv_s.nchunks);
+            const int ns_wide = ns_small > 1 ? 1 : split_count(ctx, N, 32, gh.hdev.geom_kinv.nchunks);
+            if (ns_small > 1 || ns_wide > 1) {
+                gio.partials = ctx->dpartials;
+                gio.nsplit = ns_small > 1 ? ns_small : ns_wide;
+                gio.packed_o = ns_small > 1 ? gh.dpacked_kinv_s : gh.dpacked_kinv;
+                gio.geom_o = ns_small > 1 ? gh.geom_kinv_s : gh.hdev.geom_kinv;
+                CK(gpfo_contract_grad_split_launch(st, gh.kind, gh.ddev, gio, D, ns_small > 1 ? 0 : 1));
+                ++launches;
+            } else {
+                CK(gpfo_contract_grad_launch(st, gh.kind, gh.ddev, gio, ggrid, D));
+            }
+            ++launches;
+        }
+    }
+
+    *launches_out = launches; *nparts_out = nparts; *hot_ms_out = hot_ms;
+    return GPFO_OK;
+}
+
+int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_values, double* out_grads,
+              double* best_value, int64_t* best_index) {
+    if (!ctx) return GPFO_ERR_STATE;
+    cudaSetDevice(ctx->device);
+    if (N < 0) return fail(ctx, GPFO_ERR_BAD_SHAPE, "N < 0");
+    const bool want_grad = out_grads != nullptr;
+    int rc = check_eval_state(ctx, D, want_grad);
+    if (rc != GPFO_OK) return rc;
     if (N == 0) {
         if (best_index) *best_index = -1;
         if (best_value) *best_value = 0.0;
@@ -546,7 +749,6 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     if (generate && want_grad) return fail(ctx, GPFO_ERR_UNSUPPORTED, "gradients of generated candidates are not supported");
     cudaStream_t st = ctx->stream;
     const double* dX = nullptr;
-    int rc = GPFO_OK;
     if (!generate) rc = stage_candidates(ctx, Xcand, N, D, &dX);
     else ctx->tm.h2d_ms = 0.0;
     if (rc != GPFO_OK) return rc;
@@ -580,14 +782,8 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
         io.gen_seed = ctx->gen_seed; io.gen_first = ctx->gen_first;
     }
     if (need_mom) {
-        const size_t need = (size_t)GPFO_MAX_SLOTS * N;
-        if (ctx->cap_mom < need) {
-            cudaFree(ctx->dmom_mean); cudaFree(ctx->dmom_var);
-            ctx->dmom_mean = ctx->dmom_var = nullptr; ctx->cap_mom = 0;
-            CK(cudaMalloc((void**)&ctx->dmom_mean, need * sizeof(double)));
-            CK(cudaMalloc((void**)&ctx->dmom_var, need * sizeof(double)));
-            ctx->cap_mom = need;
-        }
+        rc = ensure_pair(ctx, &ctx->dmom_mean, &ctx->dmom_var, &ctx->cap_mom, (size_t)GPFO_MAX_SLOTS * N);
+        if (rc != GPFO_OK) return rc;
         io.mom_mean = ctx->dmom_mean; io.mom_var = ctx->dmom_var;
     }
     const bool dev_out = out_values && is_device_ptr(out_values);
@@ -597,14 +793,8 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     }
     const bool dev_grads = want_grad && is_device_ptr(out_grads);
     if (want_grad) {
-        const size_t need = (size_t)GPFO_MAX_SLOTS * N;
-        if (ctx->cap_coef < need) {
-            cudaFree(ctx->dcmu); cudaFree(ctx->dcva);
-            ctx->dcmu = ctx->dcva = nullptr; ctx->cap_coef = 0;
-            CK(cudaMalloc((void**)&ctx->dcmu, need * sizeof(double)));
-            CK(cudaMalloc((void**)&ctx->dcva, need * sizeof(double)));
-            ctx->cap_coef = need;
-        }
+        rc = ensure_pair(ctx, &ctx->dcmu, &ctx->dcva, &ctx->cap_coef, (size_t)GPFO_MAX_SLOTS * N);
+        if (rc != GPFO_OK) return rc;
         io.cmu = ctx->dcmu; io.cva = ctx->dcva;
         if (dev_grads) io.grads = out_grads;
         else { CK(ensure(&ctx->dgrads, &ctx->cap_grads, (size_t)N * D)); io.grads = ctx->dgrads; }
@@ -619,7 +809,7 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     if (rc != GPFO_OK) return rc;
     io.part_val = ctx->dpart_val; io.part_idx = ctx->dpart_idx;
 
-    int launches = 0, fwd_parts = grid;
+    int launches = 0;
     float hot_ms = 0.f;
     rc = ensure_partials(ctx);
     if (rc != GPFO_OK) return rc;
@@ -633,163 +823,13 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
                 if (ctx->hprog.ops[4 * i + 2] != ctx->cells.R)
                     return fail(ctx, GPFO_ERR_BAD_SHAPE, "HVPoI objective count does not match the cell tables");
             }
-    if (astore) {
-        // ---- large gradient batch: forward launches park A = L^-1 Kx, backward launches contract it with the reversed
-        // transposed stream (2 M^2 flop per candidate and GP in total instead of 3 M^2).  A lives in a bounded scratch, so
-        // the batch is processed in slabs of whole tiles: forward (all GPs) -> program partials -> backward (all GPs).
-        const int Tt = gpfo_contract_bwd_tile();
-        const int64_t ntiles = (N + Tt - 1) / Tt;
-        size_t per_tile = 0;                                   // doubles of A per tile, all GPs
-        for (int g = 0; g < ctx->ngps; ++g) per_tile += (size_t)gpfo_contract_astore_stride(ctx->gps[g].Mp / 8);
-        size_t free_b = 0, total_b = 0;
-        CK(cudaMemGetInfo(&free_b, &total_b));
-        size_t budget = (free_b + ctx->cap_a_scratch * sizeof(double)) / 4;
-        if (budget > ((size_t)8 << 30)) budget = (size_t)8 << 30;
-        if (const char* mb = getenv("GPFO_ASTORE_BUDGET_MB")) budget = (size_t)atoll(mb) << 20;      // tests: force several slabs
-        int64_t slab_tiles = (int64_t)(budget / (per_tile * sizeof(double)));
-        if (slab_tiles < ctx->num_sms) slab_tiles = ctx->num_sms;
-        if (slab_tiles > ntiles) slab_tiles = ntiles;
-        CK(ensure(&ctx->da_scratch, &ctx->cap_a_scratch, (size_t)slab_tiles * per_tile));
-        const int64_t nslabs = (ntiles + slab_tiles - 1) / slab_tiles;
-        const int sgrid = (int)(slab_tiles < ctx->num_sms ? slab_tiles : ctx->num_sms);
-        const int64_t slab_n = slab_tiles * Tt;
-        const int ppg = hv ? gpfo_hvpoi_grid(slab_n, ctx->num_sms) : gpfo_program_grad_grid(slab_n, ctx->num_sms);
-        rc = ensure_parts(ctx, (int)(nslabs * ppg));
-        if (rc != GPFO_OK) return rc;
-        io.part_val = ctx->dpart_val; io.part_idx = ctx->dpart_idx;
-        size_t kx_need = 0;
-        for (int g = 0; g < ctx->ngps; ++g) {
-            const size_t cols = ((size_t)ctx->gps[g].Mp + 127) / 128 * 128;
-            if (cols * Tt * (size_t)sgrid > kx_need) kx_need = cols * Tt * (size_t)sgrid;
-        }
-        CK(ensure(&ctx->dkx_scratch, &ctx->cap_kx_scratch, kx_need));
-        nparts = 0;
-        for (int64_t k = 0; k < nslabs; ++k) {
-            const int64_t n0 = k * slab_n;
-            const int64_t ns = (N - n0 < slab_n) ? N - n0 : slab_n;
-            const int64_t st_tiles = (ns + Tt - 1) / Tt;
-            const int g_s = (int)(st_tiles < sgrid ? st_tiles : sgrid);
-            EvalIO sio = io;
-            sio.X = io.X + (size_t)n0 * D; sio.N = ns; sio.idx0 = n0;
-            sio.mom_mean = io.mom_mean + n0; sio.mom_var = io.mom_var + n0;
-            sio.cmu = io.cmu + n0; sio.cva = io.cva + n0;
-            if (io.values) sio.values = io.values + n0;
-            sio.grads = io.grads + (size_t)n0 * D;
-            sio.part_val = io.part_val + nparts; sio.part_idx = io.part_idx + nparts;
-            size_t a_off = 0;
-            for (int g = 0; g < ctx->ngps; ++g) {
-                const GpHost& gh = ctx->gps[g];
-                EvalIO gio = sio;
-                gio.write_moments = 1; gio.run_program = 0;
-                gio.kx_scratch = ctx->dkx_scratch;
-                gio.kx_scratch_stride = (long long)(((size_t)gh.Mp + 127) / 128 * 128 * Tt);
-                gio.a_scratch = ctx->da_scratch + a_off;
-                gio.a_stride = gpfo_contract_astore_stride(gh.Mp / 8);
-                a_off += (size_t)slab_tiles * (size_t)gio.a_stride;
-                if (k == 0 && g == 0) CK(cudaEventRecord(ctx->ev[6], st));
-                CK(gpfo_contract_astore_launch(st, gh.kind, gh.ddev, ctx->dprog, gio, g_s, D));
-                if (k == 0 && g == 0) CK(cudaEventRecord(ctx->ev[7], st));
-                ++launches;
-            }
-            int parts_k;
-            if (hv) {
-                EvalIO hio = sio;
-                hio.run_program = 1;
-                parts_k = gpfo_hvpoi_grid(ns, ctx->num_sms);
-                CK(gpfo_hvpoi_launch(st, ctx->dprog, ctx->cells, hio, parts_k, slot_first, 1));
-            } else {
-                parts_k = gpfo_program_grad_grid(ns, ctx->num_sms);
-                CK(gpfo_program_grad_launch(st, ctx->dprog, sio, parts_k));
-            }
-            ++launches;
-            nparts += parts_k;
-            a_off = 0;
-            for (int g = 0; g < ctx->ngps; ++g) {
-                const GpHost& gh = ctx->gps[g];
-                EvalIO gio = sio;
-                gio.grad_accumulate = g > 0 ? 1 : 0;
-                gio.packed_o = gh.dpacked_rt; gio.geom_o = gh.geom_rt;
-                gio.a_scratch = ctx->da_scratch + a_off;
-                gio.a_stride = gpfo_contract_astore_stride(gh.Mp / 8);
-                a_off += (size_t)slab_tiles * (size_t)gio.a_stride;
-                CK(gpfo_contract_bwd_launch(st, gh.kind, gh.ddev, gio, g_s, D));
-                ++launches;
-            }
-        }
-        if (ctx->ngps > 1) { CK(cudaEventSynchronize(ctx->ev[7])); float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); hot_ms = ms; }
-    } else {
-        for (int g = 0; g < ctx->ngps; ++g) {
-            EvalIO gio = io;
-            gio.write_moments = need_mom ? 1 : 0;
-            gio.run_program = (!hv && !want_grad && g == ctx->ngps - 1) ? 1 : 0;
-            if (variant == 11 || variant == 12 || variant == 13 || (variant >= 120 && variant <= 129)) {   // 12x: profiling builds of 12
-                // per-CTA K(X*,X) scratch: one slot per (training point, candidate of the tile), rounded up to whole groups
-                const size_t cols = ((size_t)ctx->gps[g].Mp + 127) / 128 * 128;
-                const size_t stride = cols * (size_t)gpfo_contract_tile(variant);
-                CK(ensure(&ctx->dkx_scratch, &ctx->cap_kx_scratch, stride * (size_t)grid));
-                gio.kx_scratch = ctx->dkx_scratch;
-                if (variant == 127) {          // profiling build: phase counters land at the start of the values buffer
-                    CK(ensure(&ctx->dvalues, &ctx->cap_values, (size_t)(N > 65536 ? N : 65536)));
-                    gio.debug = reinterpret_cast<long long*>(ctx->dvalues);
-                    gio.values = nullptr;
-                }
-                gio.kx_scratch_stride = (long long)stride;
-            }
-            CK(cudaEventRecord(ctx->ev[6], st));
-            const int ns = generate ? 1 : split_count(ctx, N, gpfo_split_tile(), ctx->gps[g].geom_s.nchunks);
-            if (ns > 1) {
-                gio.packed_o = ctx->gps[g].dpacked_s; gio.geom_o = ctx->gps[g].geom_s;
-                gio.nsplit = ns; gio.partials = ctx->dpartials;
-                CK(gpfo_contract_split_launch(st, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, D));
-                ++launches;
-                fwd_parts = (int)((N + 127) / 128);
-            } else {
-                if (use_cluster) CK(gpfo_contract3_launch(st, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
-                else CK(gpfo_contract_launch(st, variant, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
-                fwd_parts = grid;
-            }
-            CK(cudaEventRecord(ctx->ev[7], st));
-            ++launches;
-            if (ctx->ngps > 1) {                 // per-GP timing needs a sync only when events are reused
-                CK(cudaEventSynchronize(ctx->ev[7]));
-                float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); hot_ms += ms;
-            }
-        }
-        nparts = fwd_parts;
-        if (hv) {
-            EvalIO hio = io;
-            hio.run_program = 1;
-            CK(gpfo_hvpoi_launch(st, ctx->dprog, ctx->cells, hio, hv_grid, slot_first, want_grad ? 1 : 0));
-            ++launches;
-            nparts = hv_grid;
-        } else if (want_grad) {
-            CK(gpfo_program_grad_launch(st, ctx->dprog, io, pg_grid));
-            ++launches;
-            nparts = pg_grid;
-        }
-        if (want_grad) {
-            // chain rule through each GP: W = K^-1 Kx on DMMA, then the (1+D)-wide reduction over the training points
-            const int ggrid = gpfo_contract_grad_grid(N, ctx->num_sms);
-            for (int g = 0; g < ctx->ngps; ++g) {
-                EvalIO gio = io;
-                gio.grad_accumulate = g > 0 ? 1 : 0;
-                const GpHost& gh = ctx->gps[g];
-                const int ns_small = split_count(ctx, N, gpfo_split_tile(), gh.geom_kinv_s.nchunks);
-                const int ns_wide = ns_small > 1 ? 1 : split_count(ctx, N, 32, gh.hdev.geom_kinv.nchunks);
-                if (ns_small > 1 || ns_wide > 1) {
-                    gio.partials = ctx->dpartials;
-                    gio.nsplit = ns_small > 1 ? ns_small : ns_wide;
-                    gio.packed_o = ns_small > 1 ? gh.dpacked_kinv_s : gh.dpacked_kinv;
-                    gio.geom_o = ns_small > 1 ? gh.geom_kinv_s : gh.hdev.geom_kinv;
-                    CK(gpfo_contract_grad_split_launch(st, gh.kind, gh.ddev, gio, D, ns_small > 1 ? 0 : 1));
-                    ++launches;
-                } else {
-                    CK(gpfo_contract_grad_launch(st, gh.kind, gh.ddev, gio, ggrid, D));
-                }
-                ++launches;
-            }
-        }
-    }
+    EvalPlan pl;
+    pl.N = N; pl.D = D; pl.variant = variant; pl.grid = grid; pl.hv_grid = hv_grid; pl.pg_grid = pg_grid;
+    pl.slot_first = slot_first; pl.use_cluster = use_cluster; pl.hv = hv; pl.want_grad = want_grad;
+    pl.need_mom = need_mom; pl.generate = generate;
+    rc = astore ? launch_stored_a(ctx, pl, io, &launches, &nparts, &hot_ms)
+                : launch_standard(ctx, pl, io, &launches, &nparts, &hot_ms);
+    if (rc != GPFO_OK) return rc;
     gpfo_argmax_final(st, ctx->dpart_val, ctx->dpart_idx, nparts, ctx->dbest_val, ctx->dbest_idx);
     CK(cudaGetLastError());
     ++launches;
@@ -871,14 +911,8 @@ int gpfo_predict(gpfo_ctx* ctx, int gp_id, const double* X, int64_t N, int D, do
     if (variant == 10 || variant == 11 || variant == 12 || variant == 13) variant = (N >= (int64_t)32 * ctx->num_sms) ? 4 : ((N >= (int64_t)16 * ctx->num_sms) ? 5 : 6);
     const int rbc = gpfo_contract_rbc(variant);
     if (g.packed_rbc != rbc) { rc = repack(ctx, g, rbc); if (rc != GPFO_OK) return rc; }
-    const size_t need = (size_t)GPFO_MAX_SLOTS * N;
-    if (ctx->cap_mom < need) {
-        cudaFree(ctx->dmom_mean); cudaFree(ctx->dmom_var);
-        ctx->dmom_mean = ctx->dmom_var = nullptr; ctx->cap_mom = 0;
-        CK(cudaMalloc((void**)&ctx->dmom_mean, need * sizeof(double)));
-        CK(cudaMalloc((void**)&ctx->dmom_var, need * sizeof(double)));
-        ctx->cap_mom = need;
-    }
+    rc = ensure_pair(ctx, &ctx->dmom_mean, &ctx->dmom_var, &ctx->cap_mom, (size_t)GPFO_MAX_SLOTS * N);
+    if (rc != GPFO_OK) return rc;
     const int grid = gpfo_contract_grid(variant, N, ctx->num_sms);
     rc = ensure_parts(ctx, grid);
     if (rc != GPFO_OK) return rc;
