@@ -471,8 +471,9 @@ def test_row_split_small_batches(ctx, M, D):
             v6, g6, _, i6 = ctx.eval(Xc, want_grads=True)
         finally:
             ctx.set_variant(0)
-        assert_parity(vals, v6, tol=1e-12, what="split vs un-split value")
-        assert_parity(grads, g6, tol=1e-11, what="split vs un-split grad")
+        # different summation orders (the number of row splits follows the SM count of the box): well inside the 1e-9 bar
+        assert_parity(vals, v6, tol=1e-11, what="split vs un-split value")
+        assert_parity(grads, g6, tol=1e-10, what="split vs un-split grad")
 
 
 # ------------------------------------------------------------------------------------------------------------------
