@@ -502,6 +502,14 @@ def test_stored_a_gradients_large_batch(ctx, M, D, kind):
     fmin = float(np.min(g.predict(g.input_transform.backward(g.Xs))[0])) + 0.05
     ctx.program_set([[_lib.OP_EI, 0, 0, 0]], [fmin])
     Xc = _cands(N, D, lo, up)
+    ctx.set_variant(12)            # the large-batch kernel family whatever the SM count of the box (automatic at N >= 256 SMs)
+    try:
+        _stored_a_checks(ctx, g, fmin, Xc, N)
+    finally:
+        ctx.set_variant(0)
+
+
+def _stored_a_checks(ctx, g, fmin, Xc, N):
     vals, grads, bv, bi = ctx.eval(Xc, want_grads=True)
     assert ctx.timings()["launches"] == 4                         # forward + partials + backward + argmax: one slab
     sub = np.arange(0, N, 97)
@@ -532,6 +540,7 @@ def test_stored_a_product_of_two_gps_and_hvpoi(ctx):
     try:
         Xc = _cands(N, D, lo, up)
         sub = np.arange(5, N, 101)
+        ctx.set_variant(12)
         f1 = float(np.min(g1.predict(g1.input_transform.backward(g1.Xs))[0]))
         ctx.program_set([[_lib.OP_EI, 0, 0, 0], [_lib.OP_POF, 1, 0, 1], [_lib.OP_PROD, 2, 0, 0]], [f1, 2.5])
         vals, grads, _, bi = _with_env("GPFO_ASTORE_BUDGET_MB", "8", lambda: ctx.eval(Xc, want_grads=True))
@@ -554,6 +563,7 @@ def test_stored_a_product_of_two_gps_and_hvpoi(ctx):
         assert_parity(grads[sub], rg, what="stored-A HVPoI grad")
         assert bi == int(np.argmax(vals))
     finally:
+        ctx.set_variant(0)
         ctx.gp_count_set(1)
 
 
