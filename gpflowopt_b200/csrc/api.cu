@@ -6,6 +6,8 @@
 #include "gpfo_internal.cuh"
 
 #define FB 64
+#define GPFO_STAGE_BYTES (4 * 65536)          // pinned staging: four 64 KB areas (candidates, values, gradients, best record)
+#define GPFO_STAGE_AREA 65536
 #define RMAX_KERNEL 4
 
 struct GpHost {
@@ -63,7 +65,10 @@ struct gpfo_ctx {
     double* dgen = nullptr;                                  // 2 * GPFO_MAX_DIM doubles: affine map of the device candidate generator
     bool gen_active = false; unsigned long long gen_seed = 0; long long gen_first = 0;
     double* dpart_val = nullptr; long long* dpart_idx = nullptr; int cap_parts = 0;
-    double* dbest_val = nullptr; long long* dbest_idx = nullptr;
+    double* dbest_val = nullptr; long long* dbest_idx = nullptr;   // one 16-byte record: value, index
+    // pinned host staging for small transfers (candidates in, values / gradients / best record out): pageable copies of a
+    // few KB cost ~10 us each through the driver's own staging, which is most of a latency-bound N = 1 call
+    char* hstage = nullptr;
     int* dflag = nullptr;
     cudaEvent_t ev[8];
     gpfo_timings tm;
@@ -137,8 +142,9 @@ int gpfo_ctx_create(int device, gpfo_ctx** out) {
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&ctx->dprog, sizeof(ProgramDev)) == cudaSuccess;
-    ok = ok && cudaMalloc((void**)&ctx->dbest_val, sizeof(double)) == cudaSuccess;
-    ok = ok && cudaMalloc((void**)&ctx->dbest_idx, sizeof(long long)) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&ctx->dbest_val, 16) == cudaSuccess;
+    if (ok) ctx->dbest_idx = reinterpret_cast<long long*>(ctx->dbest_val + 1);
+    ok = ok && cudaMallocHost((void**)&ctx->hstage, GPFO_STAGE_BYTES) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&ctx->dflag, sizeof(int)) == cudaSuccess;
     if (!ok) { delete ctx; return GPFO_ERR_CUDA; }
     *out = ctx;
@@ -162,7 +168,7 @@ int gpfo_ctx_destroy(gpfo_ctx* ctx) {
     cudaFree(ctx->dXc); cudaFree(ctx->dvalues); cudaFree(ctx->dmom_mean); cudaFree(ctx->dmom_var);
     cudaFree(ctx->dcmu); cudaFree(ctx->dcva); cudaFree(ctx->dgrads); cudaFree(ctx->dkx_scratch); cudaFree(ctx->dgen);
     cudaFree(ctx->dpartials); cudaFree(ctx->da_scratch);
-    cudaFree(ctx->dpart_val); cudaFree(ctx->dpart_idx); cudaFree(ctx->dbest_val); cudaFree(ctx->dbest_idx);
+    cudaFree(ctx->dpart_val); cudaFree(ctx->dpart_idx); cudaFree(ctx->dbest_val); cudaFreeHost(ctx->hstage);
     cudaFree(ctx->dflag);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->stream);
@@ -496,7 +502,10 @@ static int stage_candidates(gpfo_ctx* ctx, const double* X, int64_t N, int D, co
     if (is_device_ptr(X)) { *dX = X; ctx->tm.h2d_ms = 0.0; return GPFO_OK; }
     CK(ensure(&ctx->dXc, &ctx->cap_xc, (size_t)N * D));
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-    CK(cudaMemcpyAsync(ctx->dXc, X, (size_t)N * D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const size_t bytes = (size_t)N * D * sizeof(double);
+    const void* src = X;
+    if (bytes <= GPFO_STAGE_AREA) { memcpy(ctx->hstage, X, bytes); src = ctx->hstage; }
+    CK(cudaMemcpyAsync(ctx->dXc, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     *dX = ctx->dXc;
     return GPFO_OK;
@@ -835,16 +844,24 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     ++launches;
     CK(cudaEventRecord(ctx->ev[5], st));
     // results
-    double hbest = 0.0;
-    long long hidx = -1;
+    const size_t vbytes = (size_t)N * sizeof(double), gbytes = (size_t)N * D * sizeof(double);
+    char* const hv_stage = ctx->hstage + GPFO_STAGE_AREA, *const hg_stage = ctx->hstage + 2 * GPFO_STAGE_AREA;
+    char* const hb_stage = ctx->hstage + 3 * GPFO_STAGE_AREA;
+    const bool stage_v = out_values && !dev_out && vbytes <= GPFO_STAGE_AREA;
+    const bool stage_g = want_grad && !dev_grads && gbytes <= GPFO_STAGE_AREA;
     if (out_values && !dev_out)
-        CK(cudaMemcpyAsync(out_values, ctx->dvalues, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(stage_v ? (void*)hv_stage : (void*)out_values, ctx->dvalues, vbytes, cudaMemcpyDeviceToHost, st));
     if (want_grad && !dev_grads)
-        CK(cudaMemcpyAsync(out_grads, ctx->dgrads, (size_t)N * D * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&hbest, ctx->dbest_val, sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&hidx, ctx->dbest_idx, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(stage_g ? (void*)hg_stage : (void*)out_grads, ctx->dgrads, gbytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hb_stage, ctx->dbest_val, 16, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev[1], st));
     CK(cudaStreamSynchronize(st));
+    if (stage_v) memcpy(out_values, hv_stage, vbytes);
+    if (stage_g) memcpy(out_grads, hg_stage, gbytes);
+    double hbest;
+    long long hidx;
+    memcpy(&hbest, hb_stage, sizeof(double));
+    memcpy(&hidx, hb_stage + 8, sizeof(long long));
     if (best_value) *best_value = hbest;
     if (best_index) *best_index = (int64_t)hidx;
     float ms = 0.f;
