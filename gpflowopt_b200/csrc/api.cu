@@ -1,4 +1,5 @@
 // C-ABI of libgpfo.so (see include/gpfo.h).  One ctx = one device + one stream; not thread-safe.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -217,8 +218,24 @@ static int split_count(const gpfo_ctx* ctx, int64_t N, int T, int nchunks) {
     return ns < nchunks ? ns : nchunks;
 }
 
+// Dense gradient pass (32-candidate tiles): CTAs per tile chosen so that whole waves are filled -- each CTA contracts 1/ns of
+// the rows, so the cost is waves(tiles * ns) / ns, plus a few percent per split for the partial sums and the finish kernel.
+static int grad_split_wide(const gpfo_ctx* ctx, int64_t N, int nchunks) {
+    if (ctx->variant != 0) return 1;
+    const char* off = getenv("GPFO_GRAD_NO_WAVE_SPLIT");
+    const int64_t ntiles = (N + 31) / 32;
+    if (off && atoi(off) != 0) return (ntiles * 2 > ctx->num_sms || nchunks < 2) ? 1 : (int)std::min<int64_t>(ctx->num_sms / ntiles, nchunks);
+    int best = 1;
+    double best_cost = (double)((ntiles + ctx->num_sms - 1) / ctx->num_sms);
+    for (int ns = 2; ns <= nchunks && ns <= 16 && ntiles * ns <= (int64_t)4 * ctx->num_sms; ++ns) {
+        const double cost = (double)((ntiles * ns + ctx->num_sms - 1) / ctx->num_sms) / ns * (1.0 + 0.03 * (ns - 1));
+        if (cost < best_cost) { best = ns; best_cost = cost; }
+    }
+    return best;
+}
+
 static int ensure_partials(gpfo_ctx* ctx) {
-    CK(ensure(&ctx->dpartials, &ctx->cap_partials, (size_t)ctx->num_sms * 32 * (1 + GPFO_MAX_DIM)));
+    CK(ensure(&ctx->dpartials, &ctx->cap_partials, (size_t)4 * ctx->num_sms * 32 * (1 + GPFO_MAX_DIM)));
     return GPFO_OK;
 }
 
@@ -719,7 +736,7 @@ static int launch_standard(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
             gio.grad_accumulate = g > 0 ? 1 : 0;
             const GpHost& gh = ctx->gps[g];
             const int ns_small = split_count(ctx, N, gpfo_split_tile(), gh.geom_kinv_s.nchunks);
-            const int ns_wide = ns_small > 1 ? 1 : split_count(ctx, N, 32, gh.hdev.geom_kinv.nchunks);
+            const int ns_wide = ns_small > 1 ? 1 : grad_split_wide(ctx, N, gh.hdev.geom_kinv.nchunks);
             if (ns_small > 1 || ns_wide > 1) {
                 gio.partials = ctx->dpartials;
                 gio.nsplit = ns_small > 1 ? ns_small : ns_wide;
