@@ -683,7 +683,7 @@ static int launch_standard(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
         EvalIO gio = io;
         gio.write_moments = need_mom ? 1 : 0;
         gio.run_program = (!hv && !want_grad && g == ctx->ngps - 1) ? 1 : 0;
-        if (variant == 11 || variant == 12 || variant == 13 || (variant >= 120 && variant <= 129)) {   // 12x: profiling builds of 12
+        if (variant == 11 || variant == 12 || variant == 13 || variant == 14 || (variant >= 120 && variant <= 129)) {   // 12x: profiling builds of 12
             // per-CTA K(X*,X) scratch: one slot per (training point, candidate of the tile), rounded up to whole groups
             const size_t cols = ((size_t)ctx->gps[g].Mp + 127) / 128 * 128;
             const size_t stride = cols * (size_t)gpfo_contract_tile(variant);
@@ -942,7 +942,7 @@ int gpfo_predict(gpfo_ctx* ctx, int gp_id, const double* X, int64_t N, int D, do
     int rc = stage_candidates(ctx, X, N, D, &dX);
     if (rc != GPFO_OK) return rc;
     int variant = effective_variant(ctx, N);
-    if (variant == 10 || variant == 11 || variant == 12 || variant == 13) variant = (N >= (int64_t)32 * ctx->num_sms) ? 4 : ((N >= (int64_t)16 * ctx->num_sms) ? 5 : 6);
+    if (variant == 10 || variant == 11 || variant == 12 || variant == 13 || variant == 14) variant = (N >= (int64_t)32 * ctx->num_sms) ? 4 : ((N >= (int64_t)16 * ctx->num_sms) ? 5 : 6);
     const int rbc = gpfo_contract_rbc(variant);
     if (g.packed_rbc != rbc) { rc = repack(ctx, g, rbc); if (rc != GPFO_OK) return rc; }
     rc = ensure_pair(ctx, &ctx->dmom_mean, &ctx->dmom_var, &ctx->cap_mom, (size_t)GPFO_MAX_SLOTS * N);
@@ -984,7 +984,7 @@ int gpfo_timings_get(const gpfo_ctx* ctx, gpfo_timings* out) {
 
 int gpfo_set_variant(gpfo_ctx* ctx, int variant) {
     if (!ctx) return GPFO_ERR_STATE;
-    static const int known[] = {0, 4, 5, 6, 10, 11, 12, 13, 41, 42, 43, 121, 122, 123, 125, 127};
+    static const int known[] = {0, 4, 5, 6, 10, 11, 12, 13, 14, 41, 42, 43, 121, 122, 123, 125, 127};
     bool ok = false;
     for (int k : known) ok = ok || k == variant;
     if (!ok) return fail(ctx, GPFO_ERR_BAD_SHAPE, "unknown kernel variant");

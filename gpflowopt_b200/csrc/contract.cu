@@ -36,11 +36,12 @@ void gpfo_argmax_final(cudaStream_t st, const double* part_val, const long long*
 // variant table of the contraction kernel (contract2.cu); 10 = 2-CTA cluster kernel (contract3.cu, handled by the API).
 //    4: T=32, 512-row chunks, K(X*,X) regenerated per chunk (strictly on chip)      5 / 6: T=16 / T=8 (small batches)
 //   11: T=32 + per-CTA K(X*,X) scratch       12: T=64, 256-row chunks + scratch (default for large batches)
+//   14: 12 with the scratch re-reads as 1-D bulk copies (cp.async.bulk / UBLKCP + mbarrier): same speed, not default
 //   13: the tiling of 12, warp-specialised (contract4.cu: 4 producer warps feed 16 DMMA warps through mbarrier stages)
 //   41-43, 121-123: ablations (no generation / no L^-1 loads / neither), 127: per-phase cycle counters -- profiling only
 struct VarInfo { int rbc, tile; };
 static VarInfo var_info(int v) {
-    if (v == 12 || v == 13 || (v >= 120 && v <= 129)) return {32, 64};
+    if (v == 12 || v == 13 || v == 14 || (v >= 120 && v <= 129)) return {32, 64};
     if (v == 5) return {64, 16};
     if (v == 6) return {64, 8};
     return {64, 32};

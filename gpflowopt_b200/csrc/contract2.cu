@@ -42,6 +42,10 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     double* gcm = tab32 + 34;                                        // [T][RMAX]  (d acq/d mean_ro) / out_scale_ro
     double* gcv = gcm + T * RMAX;                                    // [T]        -2 sum_ro (d acq/d var_ro) / out_scale_ro^2
     double* gsum = gcv + T;                                          // [T][1+D]   sum_i u_in [1, Xs_i]
+    // ABL bit 1024 = BULK: groups re-read from the scratch arrive by one 1-D bulk copy (cp.async.bulk, the TMA engine;
+    // SASS UBLKCP) issued by thread 0 and signalled on an mbarrier per group buffer, instead of four LDGSTS per thread
+    constexpr bool BULK = (ABL & 1024) != 0;
+    unsigned long long* kxbar = reinterpret_cast<unsigned long long*>(GRADM ? gsum + T * (1 + D) : gcm);   // [KXB]
     static_assert(!GRADM || NW * C::RING_DOUBLES_PER_WARP + KXB * C::GROUP_SLOTS >= 8 * C::RBC * T,
                   "the u buffer of the gradient pass reuses the ring and the group buffers");
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -75,6 +79,10 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     if (TIM) t_all = clock64();
     if (tid < EW) { sbest[2 * tid] = 0.0; reinterpret_cast<long long*>(sbest)[2 * tid + 1] = -1; }
     if (tid < 32) tab32[tid] = exp2(tid * (1.0 / 32.0));
+    const unsigned kxbar_s = (unsigned)__cvta_generic_to_shared(kxbar);
+    unsigned kx_phase = 0;                               // bit b: parity of the next completion of group buffer b's mbarrier
+    if (BULK && tid == 0)
+        for (int b2 = 0; b2 < KXB; ++b2) mbar_init(kxbar_s + 8 * b2, 1);
     __syncthreads();
 
     const int64_t ntiles = (io.N + T - 1) / T;
@@ -196,6 +204,8 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                     dst[(ksl * NB + gen_nb) * 32 + lane] = out;
                     if (SCR) __stcg(scratch + (size_t)g * C::GROUP_SLOTS + (ksl * NB + gen_nb) * 32 + lane, out);
                 }
+                // the scratch is re-read through the async proxy: order this thread's generic writes before it
+                if (BULK) asm volatile("fence.proxy.async;" ::: "memory");
             };
 
             // scratch mode, re-read chunks: asynchronous copy of a whole group scratch -> shared, issued TWO groups ahead
@@ -203,6 +213,18 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             auto copy_group = [&](int g) {
                 const double* __restrict__ src = scratch + (size_t)g * C::GROUP_SLOTS;
                 const unsigned dst = (unsigned)__cvta_generic_to_shared(kx + (g % KXB) * C::GROUP_SLOTS);
+                if (BULK) {
+                    if (tid == 0) {
+                        const unsigned bar = kxbar_s + 8 * (g % KXB);
+                        constexpr unsigned bytes = C::GROUP_SLOTS * sizeof(double);
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}"
+                                     ::"r"(bar), "r"(bytes) : "memory");
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+                    }
+                    return;
+                }
 #pragma unroll
                 for (int q = 0; q < C::GROUP_SLOTS / (2 * C::THREADS); ++q) {
                     const int ch = tid + q * C::THREADS;                 // 16-byte chunk index
@@ -258,7 +280,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             if (nold > 0) {
                 copy_group(0);
                 if (nold > 1) copy_group(1);
-                cp_async_wait<0>();
+                if (!BULK) cp_async_wait<0>();
             } else if (!BWD) {
                 gen_group(0, kx);
             }
@@ -271,13 +293,18 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 // (A split arrive/wait barrier on an mbarrier was measured here: it moves waiting time from the barrier
                 // into pipe contention, 26.8 vs 27.2 TFLOP/s, so the plain CTA barrier stays.)
                 if (SCR && g + 2 < nold) copy_group(g + 2);
+                if (BULK && g < nold) {               // this group was bulk-copied: wait for its bytes
+                    unsigned par = (kx_phase >> (g % KXB)) & 1u;
+                    mbar_wait(kxbar_s + 8 * (g % KXB), par);
+                    kx_phase ^= 1u << (g % KXB);
+                }
                 if (SCR && g + 1 < nold) {            // next group comes from the scratch (already in flight)
                     if (TIM) t_mark = clock64();
                     mma_group(g);
                     if (TIM) t_mma += clock64() - t_mark;
                     // it was committed a whole iteration ago; only a very short group can leave it pending
                     const int kcount = (kp_end < (g + 1) * KPC ? kp_end : (g + 1) * KPC) - g * KPC;
-                    if (kcount < S) cp_async_wait<0>();
+                    if (!BULK && kcount < S) cp_async_wait<0>();
                 } else if (gen_first) {
                     if (TIM) t_mark = clock64();
                     if (!BWD && more) gen_group(g + 1, nxt);
@@ -536,7 +563,7 @@ static cudaError_t launch2_kind(cudaStream_t st, const GpDev* d_gp, const Progra
     using C = Contract2Cfg<NW, RBW, NB, S>;
     const size_t smem = ((size_t)NW * C::RING_DOUBLES_PER_WARP + ((ABL & (8 | 32)) ? 3 : 2) * C::GROUP_SLOTS +
                          (size_t)D * C::T + C::T + C::T * (1 + RMAX) + 2 * ((C::T + 31) / 32) + 34 +
-                         ((ABL & (4 | 32)) ? C::T * RMAX + C::T + C::T * (1 + (size_t)D) : 0)) * sizeof(double);
+                         ((ABL & (4 | 32)) ? C::T * RMAX + C::T + C::T * (1 + (size_t)D) : 0) + ((ABL & 1024) ? 4 : 0)) * sizeof(double);
     auto kern = contract2_kernel<NW, RBW, NB, S, KIND, ABL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -570,6 +597,7 @@ cudaError_t gpfo_contract2_launch(cudaStream_t st, int variant, int kind, const 
         case 123: return launch2<16, 2, 8, S12, 11>(st, kind, d_gp, d_prog, io, grid, D);
         case 127: return launch2<16, 2, 8, S12, 8 + 64>(st, kind, d_gp, d_prog, io, grid, D);
         case 125: return launch2<16, 2, 8, S12, 8 + 256>(st, kind, d_gp, d_prog, io, grid, D);
+        case 14: return launch2<16, 2, 8, S12, 8 + 1024>(st, kind, d_gp, d_prog, io, grid, D);
         case 6: return launch2<16, 4, 1, 4>(st, kind, d_gp, d_prog, io, grid, D);
         case 41: return launch2<16, 4, 4, 4, 1>(st, kind, d_gp, d_prog, io, grid, D);
         case 42: return launch2<16, 4, 4, 4, 2>(st, kind, d_gp, d_prog, io, grid, D);

@@ -69,7 +69,7 @@ def test_multi_output_gp(ctx):
     assert_parity(var, vo, scale=g.variance, what="var")
 
 
-@pytest.mark.parametrize("variant", [13, 12, 11, 10, 4, 5, 6])
+@pytest.mark.parametrize("variant", [14, 13, 12, 11, 10, 4, 5, 6])
 @pytest.mark.parametrize("leaf,param", [("ei", None), ("poi", None), ("pof", 0.15), ("lcb", 2.0)])
 def test_leaf_acquisitions(ctx, variant, leaf, param):
     g, lo, up = _model(300, 5, "matern52", scaled=True)
@@ -219,7 +219,7 @@ def test_hvpoi_reference_fixture(ctx):
         ctx.gp_count_set(1)
 
 
-@pytest.mark.parametrize("variant", [13, 12, 11, 10, 4])
+@pytest.mark.parametrize("variant", [14, 13, 12, 11, 10, 4])
 def test_multi_chunk_variants_agree_with_oracle(ctx, variant):
     """M = 1100 spans several row chunks in every layout (256/512-row chunks, 1024-row cluster chunks, partial last chunk):
     the scratch variants (11, 12), the 2-CTA cluster variant (10) and the on-chip variant (4) all meet the oracle."""
