@@ -15,8 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "build")
 LIB = os.path.join(HERE, "libgpfo.so")
-SOURCES = ["api.cu", "factor.cu", "contract.cu", "contract2.cu", "contract3.cu", "contract4.cu", "hvpoi.cu", "grad.cu", "pareto_host.cu"]
-HEADERS = [os.path.join(CSRC, "gpfo_internal.cuh"), os.path.join(CSRC, "contract_common.cuh"), os.path.join(HERE, "..", "include", "gpfo.h")]
+SOURCES = ["api.cu", "factor.cu", "contract.cu", "contract2.cu", "contract2_aux.cu", "contract2_prof.cu", "contract3.cu", "contract4.cu", "hvpoi.cu", "grad.cu", "pareto_host.cu"]
+HEADERS = [os.path.join(CSRC, "gpfo_internal.cuh"), os.path.join(CSRC, "contract_common.cuh"), os.path.join(CSRC, "contract2_kernel.cuh"), os.path.join(HERE, "..", "include", "gpfo.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "--expt-extended-lambda"]
 
