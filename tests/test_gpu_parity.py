@@ -616,3 +616,68 @@ def test_mes_leaf_values_and_gradients(ctx, kind):
     assert np.any((gam < -20.0) & (gam > -37.0)) and np.any((m0 - samples[5]) / np.sqrt(v0) > 8.0)     # segments were hit
     with pytest.raises(_lib.GpfoError):
         ctx.program_set([[_lib.OP_MES, 0, 5, 2]], [0.0] * 6)       # sample range runs past params
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE configs at their full per-GPU sizes: oracle parity on a row subset + size-independent properties
+# (a slice scored alone reproduces its rows of the whole batch bit for bit; arg-max == arg-max of the returned scores;
+# the fused arg-max call without scores returns the same record)
+# ------------------------------------------------------------------------------------------------------------------
+def test_config3_full_size_constrained_ei(ctx):
+    """configs[2]: EI x PoF, 2 GPs, M = 4096, D = 16, one GPU's 1/8 share of the 1e7 candidates."""
+    M, D, N = 4096, 16, 1250000
+    X, Y2 = synthetic.training_set(M, D, constraint=True)
+    h = synthetic.hypers(D)
+    g1 = oracle_gp(X, Y2[:, [0]], ogp.MATERN52, h)
+    g2 = oracle_gp(X, Y2[:, [1]], ogp.MATERN52, h)
+    for i, g in enumerate((g1, g2)):
+        upload_oracle_gp(ctx, i, g, slot0=i)
+    ctx.gp_count_set(2)
+    try:
+        ctx.program_set([[_lib.OP_EI, 0, 0, 0], [_lib.OP_POF, 1, 0, 1], [_lib.OP_PROD, 2, 0, 0]], [-1.0, 0.0])
+        Xc = synthetic.candidates(N, D)
+        vals, _, bv, bi = ctx.eval(Xc)
+        sub = np.random.RandomState(2).choice(N, 400, replace=False)
+        sub[0] = bi
+        ref = oacq.Agg('prod', [oacq.Leaf('ei', g1, -1.0), oacq.Leaf('pof', g2, 0.0)]).value(Xc[sub])
+        assert_parity(vals[sub], ref, what="config 3 subset")
+        assert bi == int(np.argmax(vals)) and bv == vals[bi, 0]
+        _, _, bv2, bi2 = ctx.eval(Xc, want_values=False)
+        assert (bv2, bi2) == (bv, bi)
+        lo_, hi_ = 777777, 777777 + 9472                      # a slice scored alone (different tile width, same numbers)
+        part, _, _, _ = ctx.eval(Xc[lo_:hi_])
+        assert_parity(part, vals[lo_:hi_], tol=1e-11, what="config 3 slice vs whole")
+    finally:
+        ctx.gp_count_set(1)
+
+
+def test_config4_full_size_hvpoi(ctx):
+    """configs[3]: HVPoI, 3 objectives, M = 1024 per GP, 1e6 candidates, Pareto front of ~200 points."""
+    from gpflowopt_b200 import pareto as gpareto
+    M, D, R, N = 1024, 4, 3, 1000000
+    X = synthetic.candidates(M, D, seed=5)
+    F = synthetic.dtlz2_objectives(X, R)
+    h = synthetic.hypers(D, 1e-3)
+    gps = [oracle_gp(X, F[:, [j]], ogp.MATERN52, h) for j in range(R)]
+    for j, g in enumerate(gps):
+        upload_oracle_gp(ctx, j, g, slot0=j)
+    ctx.gp_count_set(R)
+    try:
+        Fm = np.hstack([ctx.predict(j, X, 1)[0] for j in range(R)])
+        p = gpareto.Pareto(np.zeros((1, R)))
+        p.update(Fm)
+        hv = oacq.HVPoI(gps, np.asarray(p.front), np.asarray(p.bounds.lb), np.asarray(p.bounds.ub))
+        assert 150 <= p.front.shape[0] <= 260
+        mlb, mub = gpareto.merge_cells(hv.pf_ext(), hv.lb, hv.ub)          # what HVProbabilityOfImprovement uploads
+        ctx.cells_set(hv.pf_ext(), mlb, mub)
+        ctx.program_set([[_lib.OP_HVPOI, 0, R, 0]], [])
+        Xc = synthetic.candidates(N, D)
+        vals, _, bv, bi = ctx.eval(Xc)
+        sub = np.random.RandomState(3).choice(N, 200, replace=False)
+        sub[0] = bi
+        assert_parity(vals[sub], hv.value(Xc[sub]), what="config 4 subset (reference cell tables on the oracle side)")
+        assert bi == int(np.argmax(vals)) and bv == vals[bi, 0]
+        part, _, _, _ = ctx.eval(Xc[123456:123456 + 40000])
+        assert_parity(part, vals[123456:123456 + 40000], tol=1e-11, what="config 4 slice vs whole")
+    finally:
+        ctx.gp_count_set(1)
