@@ -19,6 +19,29 @@ from ..gpr import GPR
 from ..scaling import DataScaler
 
 
+def _best_restart(model, restarts):
+    """First run from the current state, the others from ``model.randomize()``; failed runs are reported and skipped."""
+    finished = []
+    for attempt in range(1, restarts + 1):
+        if attempt > 1:
+            model.randomize()
+        try:
+            finished.append(model.optimize())
+        except Exception:                                   # pragma: no cover
+            print("Warning: optimization restart {0}/{1} failed".format(attempt, restarts))
+    if not finished:
+        raise RuntimeError("All model hyperparameter optimization restarts failed, exiting.")
+    return min(finished, key=lambda run: run.fun)
+
+
+def _join(kind, left, right):
+    """``left (+|*) right`` with operands of the same aggregation kind flattened into one node."""
+    flat = []
+    for node in (left, right):
+        flat.extend(node.operands if isinstance(node, kind) else [node])
+    return kind(flat)
+
+
 def setup_required(method):
     """Runs model optimisation and ``_setup`` of the whole tree first if the root is flagged
     (gpflowopt/acquisition/acquisition.py:32-54)."""
@@ -68,45 +91,34 @@ class Acquisition(object):
 
     # ---- reference API -----------------------------------------------------------------------------------
     def _optimize_models(self):
-        """gpflowopt/acquisition/acquisition.py:92-122.  Hyper-parameter learning itself is the model's business
-        (``GPR.optimize`` keeps the given hyper-parameters); the restart / best-run protocol is preserved."""
-        if self.optimize_restarts == 0:
-            return
-        for model in self.models:
-            runs = []
-            for i in range(self.optimize_restarts):
-                if i > 0:
-                    model.randomize()
-                try:
-                    runs.append(model.optimize())
-                except Exception as e:                      # pragma: no cover
-                    print("Warning: optimization restart {0}/{1} failed".format(i + 1, self.optimize_restarts))
-            if not runs:
-                raise RuntimeError("All model hyperparameter optimization restarts failed, exiting.")
-            best_idx = int(np.argmin([r.fun for r in runs]))
-            model.set_state(runs[best_idx].x)
+        """Refits every model ``optimize_restarts`` times and keeps the best run of each (protocol of
+        gpflowopt/acquisition/acquisition.py:92-122; the fit itself is the model's business -- ``GPR.optimize`` keeps the
+        given hyper-parameters)."""
+        for model in (self.models if self.optimize_restarts > 0 else ()):
+            model.set_state(_best_restart(model, self.optimize_restarts).x)
 
     def build_acquisition(self, Xcand):
         raise NotImplementedError
 
     def enable_scaling(self, domain):
-        n_inputs = self.data[0].shape[1]
-        assert domain.size == n_inputs
-        for m in self.models:
-            m.input_transform = domain >> UnitCube(n_inputs)
-            m.normalize_output = True
+        """Inputs of every model are mapped from ``domain`` to the unit cube and outputs are standardised."""
+        d = self.data[0].shape[1]
+        assert d == domain.size
+        to_cube = domain >> UnitCube(d)
+        for scaler in self.models:
+            scaler.input_transform = to_cube
+            scaler.normalize_output = True
         self.highest_parent._needs_setup = True
 
     def set_data(self, X, Y):
-        num_outputs_sum = 0
-        for model in self.models:
-            num_outputs = model.Y.shape[1]
-            Ypart = Y[:, num_outputs_sum:num_outputs_sum + num_outputs]
-            num_outputs_sum += num_outputs
-            model.X = X
-            model.Y = Ypart
+        """New training data for all models; model k takes its own columns of Y.  Returns the number of columns used."""
+        widths = [scaler.Y.shape[1] for scaler in self.models]
+        ends = np.cumsum(widths)
+        for scaler, end, width in zip(self.models, ends, widths):
+            scaler.X = X
+            scaler.Y = Y[:, end - width:end]
         self.highest_parent._needs_setup = True
-        return num_outputs_sum
+        return int(ends[-1]) if widths else 0
 
     @property
     def models(self):
@@ -164,14 +176,10 @@ class Acquisition(object):
         return self._get_engine().evaluate_random(self, seed, first_row, n, lower, upper)
 
     def __add__(self, other):
-        if isinstance(other, AcquisitionSum):
-            return AcquisitionSum([self] + other.operands)
-        return AcquisitionSum([self, other])
+        return _join(AcquisitionSum, self, other)
 
     def __mul__(self, other):
-        if isinstance(other, AcquisitionProduct):
-            return AcquisitionProduct([self] + other.operands)
-        return AcquisitionProduct([self, other])
+        return _join(AcquisitionProduct, self, other)
 
 
 class AcquisitionAggregation(Acquisition):
@@ -199,31 +207,32 @@ class AcquisitionAggregation(Acquisition):
             oper.enable_scaling(domain)
 
     def set_data(self, X, Y):
-        offset = 0
-        for operand in self.operands:
-            offset += operand.set_data(X, Y[:, offset:])
-        return offset
+        used = 0
+        for node in self.operands:              # every operand consumes its columns from the left
+            used += node.set_data(X, Y[:, used:])
+        return used
 
     def _setup_constraints(self):
-        for oper in self.operands:
-            if oper.constraint_indices().size > 0:
-                oper._setup_constraints()
+        for node in self.operands:
+            if node.constraint_indices().size:
+                node._setup_constraints()
 
     def _setup_objectives(self):
-        for oper in self.operands:
-            oper._setup_objectives()
+        for node in self.operands:
+            node._setup_objectives()
 
     def _setup(self):
-        self._setup_constraints()        # first: objectives may depend on the constraint acquisitions
+        # constraint acquisitions first: the incumbent of an objective acquisition is taken over the points they accept
+        self._setup_constraints()
         self._setup_objectives()
 
     def constraint_indices(self):
-        offset = [0]
-        idx = []
-        for operand in self.operands:
-            idx.append(operand.constraint_indices())
-            offset.append(operand.data[1].shape[1])
-        return np.hstack([i + o for i, o in zip(idx, offset[:-1])]).astype(int)
+        """Constraint columns of the concatenated output matrix (operand-local indices shifted by the operand's offset)."""
+        shifted, start = [], 0
+        for node in self.operands:
+            shifted.append(node.constraint_indices() + start)
+            start += node.data[1].shape[1]
+        return np.concatenate(shifted).astype(int)
 
     def feasible_data_index(self):
         return np.all(np.vstack([o.feasible_data_index() for o in self.operands]), axis=0)
@@ -239,20 +248,10 @@ class AcquisitionSum(AcquisitionAggregation):
     def __init__(self, operands):
         super(AcquisitionSum, self).__init__(operands, 'sum')
 
-    def __add__(self, other):
-        if isinstance(other, AcquisitionSum):
-            return AcquisitionSum(self.operands + other.operands)
-        return AcquisitionSum(self.operands + [other])
-
 
 class AcquisitionProduct(AcquisitionAggregation):
     def __init__(self, operands):
         super(AcquisitionProduct, self).__init__(operands, 'prod')
-
-    def __mul__(self, other):
-        if isinstance(other, AcquisitionProduct):
-            return AcquisitionProduct(self.operands + other.operands)
-        return AcquisitionProduct(self.operands + [other])
 
 
 class MCMCAcquistion(AcquisitionSum):

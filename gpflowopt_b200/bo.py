@@ -59,22 +59,59 @@ class _InverseAcquisition(object):
         return -self.acquisition.evaluate(x), np.zeros((x.shape[0], 0))
 
 
+def _summarise(acquisition, success, message):
+    """What a run reports (reference behaviour, gpflowopt/bo.py:156-203): among the evaluated points that satisfy every
+    constraint model -- or all of them, flagged unsuccessful, if none does -- the single best one (one objective), the
+    non-dominated set (several objectives) or the whole feasible set (constraints only)."""
+    X, Y = acquisition.data
+    feasible = acquisition.feasible_data_index()
+    if feasible.any():
+        X, Y = X[feasible], Y[feasible]
+    else:
+        success, message = False, "No evaluations satisfied all the constraints"
+    objectives = Y[:, acquisition.objective_indices()]
+    constraints = Y[:, acquisition.constraint_indices()]
+    n_obj = objectives.shape[1]
+    if n_obj == 0:
+        keep = np.arange(constraints.shape[0])
+    elif n_obj == 1:
+        keep = np.argmin(objectives)
+    else:
+        keep = non_dominated_sort(objectives)[1] == 0
+    return OptimizeResult(x=X[keep, :], fun=objectives[keep, :], constraints=constraints[keep, :], success=success,
+                          message=message)
+
+
+def _progress_line(iteration, summary, step):
+    """One line per iteration in verbose mode: running minima of objectives and constraints, then any failure messages."""
+    parts = []
+    for label, block in (("fmin", summary.fun), ("constraints", summary.constraints)):
+        if block.shape[0] > 0 and block.shape[1] > 0:
+            lows = np.atleast_1d(np.min(block, axis=0))
+            parts.append("%s [%s]" % (label, ", ".join("{:.3}".format(v) for v in lows)))
+    parts.extend(r.message for r in (summary, step) if not r.success)
+    return "iter #{0:>3} - {1}".format(iteration, " - ".join(str(p) for p in parts))
+
+
 class BayesianOptimizer(Optimizer):
+    """Sequential model-based optimisation loop (public surface of gpflowopt/bo.py:55-305): evaluate the initial design, then
+    ``n_iter`` times { refresh the models, maximise the acquisition with ``optimizer``, evaluate the objectives there }."""
+
     def __init__(self, domain, acquisition, optimizer=None, initial=None, scaling=True, hyper_draws=None,
                  callback=jitchol_callback, verbose=False):
-        assert isinstance(acquisition, Acquisition)
-        assert hyper_draws is None or hyper_draws > 0
-        assert optimizer is None or isinstance(optimizer, Optimizer)
-        assert initial is None or isinstance(initial, Design)
+        for ok in (isinstance(acquisition, Acquisition), hyper_draws is None or hyper_draws > 0,
+                   optimizer is None or isinstance(optimizer, Optimizer), initial is None or isinstance(initial, Design)):
+            assert ok
         super(BayesianOptimizer, self).__init__(domain, exclude_gradient=True)
         self._scaling = scaling
-        if self._scaling:
+        if scaling:
             acquisition.enable_scaling(domain)
-        self.acquisition = acquisition if hyper_draws is None else MCMCAcquistion(acquisition, hyper_draws)
-        self.optimizer = optimizer or SciPyOptimizer(domain)
+        if hyper_draws is not None:
+            acquisition = MCMCAcquistion(acquisition, hyper_draws)
+        self.acquisition = acquisition
+        self.optimizer = SciPyOptimizer(domain) if optimizer is None else optimizer
         self.optimizer.domain = domain
-        initial = initial or EmptyDesign(domain)
-        self.set_initial(initial.generate())
+        self.set_initial((initial if initial is not None else EmptyDesign(domain)).generate())
         self._model_callback = callback
         self.verbose = verbose
 
@@ -84,48 +121,30 @@ class BayesianOptimizer(Optimizer):
 
     @domain.setter
     def domain(self, dom):
-        assert self._domain.size == dom.size
+        assert dom.size == self._domain.size
         self._domain = dom
         self.set_initial(dom.value)
         if self._scaling:
             self.acquisition.enable_scaling(dom)
 
     def _update_model_data(self, newX, newY):
-        assert self.acquisition.data[0].shape[1] == newX.shape[-1]
-        assert self.acquisition.data[1].shape[1] == newY.shape[-1]
-        assert newX.shape[0] == newY.shape[0]
-        if newX.size == 0:
-            return
-        X = np.vstack((self.acquisition.data[0], newX))
-        Y = np.vstack((self.acquisition.data[1], newY))
-        self.acquisition.set_data(X, Y)
+        """Appends evaluations to the data every model of the acquisition is trained on."""
+        oldX, oldY = self.acquisition.data
+        assert newX.shape[-1] == oldX.shape[1] and newY.shape[-1] == oldY.shape[1] and newX.shape[0] == newY.shape[0]
+        if newX.size > 0:
+            self.acquisition.set_data(np.vstack((oldX, newX)), np.vstack((oldY, newY)))
 
     def _evaluate_objectives(self, X, fxs):
-        if X.size > 0:
-            evaluations = np.hstack([f(X) for f in fxs])
-            assert evaluations.shape[1] == self.acquisition.data[1].shape[1]
-            return evaluations, np.zeros((X.shape[0], 0))
-        return np.empty((0, self.acquisition.data[1].shape[1])), np.zeros((0, 0))
+        """All objective / constraint callables at X, side by side; the (empty) second item is the gradient slot."""
+        n_out = self.acquisition.data[1].shape[1]
+        if X.size == 0:
+            return np.empty((0, n_out)), np.zeros((0, 0))
+        columns = np.hstack([f(X) for f in fxs])
+        assert columns.shape[1] == n_out
+        return columns, np.zeros((X.shape[0], 0))
 
     def _create_bo_result(self, success, message):
-        """Best feasible point / Pareto set / feasible set, as in gpflowopt/bo.py:156-203."""
-        X, Y = self.acquisition.data
-        valid = self.acquisition.feasible_data_index()
-        if np.any(valid):
-            X, Y = X[valid, :], Y[valid, :]
-        else:
-            success = False
-            message = "No evaluations satisfied all the constraints"
-        Yo = Y[:, self.acquisition.objective_indices()]
-        Yc = Y[:, self.acquisition.constraint_indices()]
-        if Yo.shape[1] == 1:
-            idx = np.argmin(Yo)
-        elif Yo.shape[1] > 1:
-            _, dom = non_dominated_sort(Yo)
-            idx = dom == 0
-        else:
-            idx = np.arange(Yc.shape[0])
-        return OptimizeResult(x=X[idx, :], success=success, fun=Yo[idx, :], constraints=Yc[idx, :], message=message)
+        return _summarise(self.acquisition, success, message)
 
     def optimize(self, objectivefx, n_iter=20):
         fxs = np.atleast_1d(objectivefx)
@@ -133,37 +152,31 @@ class BayesianOptimizer(Optimizer):
 
     def _optimize(self, fx, n_iter):
         assert isinstance(fx, ObjectiveWrapper)
-        initial = self.get_initial()
-        values = fx(initial)
-        self._update_model_data(initial, values)
-        self.set_initial(EmptyDesign(self.domain).generate())
-        inverse_acquisition = _InverseAcquisition(self.acquisition, self.optimizer.gradient_enabled())
-        for i in range(n_iter):
+        start = self.get_initial()
+        self._update_model_data(start, fx(start))
+        self.set_initial(EmptyDesign(self.domain).generate())          # the initial design is consumed once
+        # the optimiser minimises -acquisition; gradients are only asked for when it can use them
+        target = _InverseAcquisition(self.acquisition, self.optimizer.gradient_enabled())
+        iteration = 0
+        while iteration < n_iter:
             with self.silent():
-                if self._model_callback and self.acquisition._needs_setup:
-                    self._model_callback([m.wrapped for m in self.acquisition.models])
-                result = self.optimizer.optimize(inverse_acquisition)
-                self._update_model_data(result.x, fx(result.x))
+                if self._model_callback is not None and self.acquisition._needs_setup:
+                    self._model_callback([scaler.wrapped for scaler in self.acquisition.models])
+                step = self.optimizer.optimize(target)
+                self._update_model_data(step.x, fx(step.x))
             if self.verbose:
                 with self.silent():
-                    bo_result = self._create_bo_result(True, 'Monitor')
-                metrics = []
-                if bo_result.fun.shape[0] > 0:
-                    funs = np.atleast_1d(np.min(bo_result.fun, axis=0))
-                    metrics.append('fmin [' + ', '.join('{:.3}'.format(f) for f in funs) + ']')
-                if bo_result.constraints.shape[0] > 0 and bo_result.constraints.shape[1] > 0:
-                    cons = np.atleast_1d(np.min(bo_result.constraints, axis=0))
-                    metrics.append('constraints [' + ', '.join('{:.3}'.format(c) for c in cons) + ']')
-                metrics += [r.message for r in [bo_result, result] if not r.success]
-                print('iter #{0:>3} - {1}'.format(i, ' - '.join(str(m) for m in metrics)))
-        return self._create_bo_result(True, "OK")
+                    summary = _summarise(self.acquisition, True, 'Monitor')
+                print(_progress_line(iteration, summary, step))
+            iteration += 1
+        return _summarise(self.acquisition, True, "OK")
 
     @contextmanager
     def failsafe(self):
-        """Dumps the evaluated data to failed_bopt_<id>.npz when the wrapped block raises (gpflowopt/bo.py:290-305)."""
+        """Saves the evaluated data to failed_bopt_<id>.npz when the wrapped block raises (gpflowopt/bo.py:290-305)."""
         try:
             yield
-        except Exception as e:
+        except Exception as exc:
             X, Y = self.acquisition.data
-            np.savez('failed_bopt_{0}'.format(id(e)), X=X, Y=Y)
+            np.savez('failed_bopt_{0}'.format(id(exc)), X=X, Y=Y)
             raise
