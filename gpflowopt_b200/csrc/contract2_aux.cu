@@ -67,7 +67,7 @@ int gpfo_split_tile() { return 8; }
 cudaError_t gpfo_contract_split_launch(cudaStream_t st, int kind, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io,
                                        int D) {
     const int64_t ntiles = (io.N + 7) / 8;
-    cudaError_t e = launch2<16, 1, 1, 4, 16>(st, kind, d_gp, d_prog, io, (int)(ntiles * io.nsplit), D);
+    cudaError_t e = launch2<16, 1, 1, 4, 16 + 2048>(st, kind, d_gp, d_prog, io, (int)(ntiles * io.nsplit), D);
     if (e != cudaSuccess) return e;
     split_final_kernel<<<(unsigned)((io.N + 127) / 128), 128, 0, st>>>(d_gp, d_prog, io, 8);
     return cudaGetLastError();
@@ -78,7 +78,7 @@ cudaError_t gpfo_contract_grad_split_launch(cudaStream_t st, int kind, const GpD
     const int64_t ntiles = (io.N + T - 1) / T;
     const int grid = (int)(ntiles * io.nsplit);
     cudaError_t e = wide ? launch2<16, 4, 4, 4, 4 + 16>(st, kind, d_gp, nullptr, io, grid, D)
-                         : launch2<16, 1, 1, 4, 4 + 16>(st, kind, d_gp, nullptr, io, grid, D);
+                         : launch2<16, 1, 1, 4, 4 + 16 + 2048>(st, kind, d_gp, nullptr, io, grid, D);
     if (e != cudaSuccess) return e;
     split_final_grad_kernel<<<(unsigned)((io.N * D + 127) / 128), 128, 0, st>>>(d_gp, io, T, D);
     return cudaGetLastError();

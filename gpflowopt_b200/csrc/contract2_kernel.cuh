@@ -26,7 +26,12 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     extern __shared__ __align__(16) double smem[];
     const int D = gpp->D;
     double* ring = smem;                                             // [NW][S][RBW][64]
-    constexpr int KXB = (ABL & (8 | 32)) ? 3 : 2;                    // K(X*,X) group buffers (3 in scratch mode, see below)
+    // ABL bit 2048 = PANEL (latency form for the row-split launches of a handful of candidates): all column groups of a
+    // panel of up to 32 groups (2048 training points) are generated first, into 32 group buffers, then contracted without a
+    // barrier per group -- a call is then a few barriers long instead of one generate -> DMMA -> barrier round per group
+    constexpr bool PANEL = (ABL & 2048) != 0;
+    constexpr int PANEL_GROUPS = 32;
+    constexpr int KXB = PANEL ? PANEL_GROUPS : ((ABL & (8 | 32)) ? 3 : 2);   // K(X*,X) group buffers (3 in scratch mode)
     double* kx = ring + (size_t)NW * C::RING_DOUBLES_PER_WARP;       // [KXB][GROUP_SLOTS]
     double* xc = kx + KXB * C::GROUP_SLOTS;                          // [D][T]
     double* x2 = xc + (size_t)D * T;                                 // [T]
@@ -264,7 +269,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 rd_stage = (rd_stage == (S - 1) * RBW * 64) ? 0 : rd_stage + RBW * 64;
             };
             auto mma_group = [&](int g) {
-                const double* __restrict__ kb = kx + (g % KXB) * C::GROUP_SLOTS + lane;
+                const double* __restrict__ kb = kx + (g % KXB) * C::GROUP_SLOTS + lane;      // PANEL: KXB = groups per panel
                 const int k0 = g * KPC;
                 const int k1 = (k0 + KPC < kp_end) ? k0 + KPC : kp_end;
                 if (nr == C::RBC && k1 <= kd0) {       // whole group in the dense part of a full chunk
@@ -280,6 +285,19 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             const int ngroups = (kp_end + KPC - 1) / KPC;
             // groups left of the diagonal were generated by earlier chunks (backward pass: every group is a stored one)
             const int nold = BWD ? ngroups : (SCR ? kd0 / KPC : 0);
+            if (PANEL) {
+#pragma unroll
+                for (int s = 0; s < S - 1; ++s) issue();
+                for (int g0 = 0; g0 < ngroups; g0 += PANEL_GROUPS) {
+                    const int g1 = g0 + PANEL_GROUPS < ngroups ? g0 + PANEL_GROUPS : ngroups;
+                    __syncthreads();                                  // the previous panel (or chunk) has been consumed
+#pragma unroll 4
+                    for (int g = g0; g < g1; ++g) gen_group(g, kx + (g % KXB) * C::GROUP_SLOTS);
+                    __syncthreads();
+                    for (int g = g0; g < g1; ++g) mma_group(g);
+                }
+                __syncthreads();
+            } else {
             if (nold > 0) {
                 copy_group(0);
                 if (nold > 1) copy_group(1);
@@ -328,6 +346,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                     t_bar += clock64() - t_mark;
                 }
             }
+            }   // !PANEL
             cp_async_wait<0>();
 
             if (GRADM) {
@@ -507,12 +526,18 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
 template <int NW, int RBW, int NB, int S, int KIND, int ABL>
 static inline cudaError_t launch2_kind(cudaStream_t st, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io, int grid, int D) {
     using C = Contract2Cfg<NW, RBW, NB, S>;
-    const size_t smem = ((size_t)NW * C::RING_DOUBLES_PER_WARP + ((ABL & (8 | 32)) ? 3 : 2) * C::GROUP_SLOTS +
+    const size_t smem = ((size_t)NW * C::RING_DOUBLES_PER_WARP + ((ABL & 2048) ? 32 : ((ABL & (8 | 32)) ? 3 : 2)) * C::GROUP_SLOTS +
                          (size_t)D * C::T + C::T + C::T * (1 + RMAX) + 2 * ((C::T + 31) / 32) + 34 +
                          ((ABL & (4 | 32)) ? C::T * RMAX + C::T + C::T * (1 + (size_t)D) : 0) + ((ABL & 1024) ? 4 : 0)) * sizeof(double);
     auto kern = contract2_kernel<NW, RBW, NB, S, KIND, ABL>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    static size_t smem_set[16] = {0};              // per instantiation and device: the opt-in is sticky, raise it only when needed
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16 || smem_set[dev] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 16) smem_set[dev] = smem;
+    }
     kern<<<grid, C::THREADS, smem, st>>>(d_gp, d_prog, io);
     return cudaGetLastError();
 }
