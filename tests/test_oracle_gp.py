@@ -315,3 +315,31 @@ def test_mc_optimize_first_occurrence():
     Xc2[45] = Xc2[best]
     x, f, idx, _ = oacq.mc_optimize(ei, Xc2)
     assert idx == min(best, 45) and f[0, 0] == -scores[best, 0]
+
+
+def test_domain_maps_and_membership_against_reference_generated_vectors():
+    """tests/golden/domain_golden.npz holds outputs of the reference's own gpflowopt/domain.py (Domain.__rshift__ coefficients
+    and Domain.__contains__ verdicts, generated by tests/golden/gen_domain_golden.py): the oracle's and the product's host
+    classes must reproduce them bit for bit -- this pins the input transform of SURVEY 8a row B."""
+    import os
+    from helpers import GOLDEN
+    from gpflowopt_b200.domain import ContinuousParameter
+    g = np.load(os.path.join(GOLDEN, "domain_golden.npz"))
+
+    def box(lo, up):
+        return np.sum([ContinuousParameter("p%d" % i, l, u) for i, (l, u) in enumerate(zip(lo, up))])
+
+    for k in range(int(g["n_pairs"])):
+        lo1, up1, lo2, up2 = g["pair%d_bounds" % k]
+        A, b = g["pair%d_A" % k], g["pair%d_b" % k]
+        t_oracle = ogp.domain_transform(lo1, up1, lo2, up2)
+        np.testing.assert_array_equal(t_oracle.A, A)
+        np.testing.assert_array_equal(t_oracle.b, b)
+        t_product = box(lo1, up1) >> box(lo2, up2)
+        np.testing.assert_array_equal(t_product.A, A)
+        np.testing.assert_array_equal(t_product.b, b)
+    dom = box(*g["contains_bounds"])
+    verdicts = [bool(p[None, :] in dom) for p in g["contains_probes"]]
+    assert verdicts == [bool(v) for v in g["contains_rows"]]
+    assert (g["contains_probes"][:3] in dom) == bool(g["contains_all"])
+    assert (np.zeros((2, 3)) in dom) == bool(g["contains_wrong_width"])
