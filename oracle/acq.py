@@ -4,6 +4,10 @@ TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.  PARITY UNPINNED at 1e-9 for
 forms (tf.contrib.distributions.Normal is TF1, absent here); pinned only loosely by
 testing/data/vlmop.npz (decimal=2) and the ordinal tests in testing/unit/test_implementations.py.
 
+Pinned above the TF layer: tests/golden/acq_golden.npz holds the results of the reference's own build_acquisition methods
+executed on fixed moments (NumPy stand-ins for the TF primitives, tests/golden/gen_acq_golden.py); the compositions below
+reproduce them bit for bit (tests/test_oracle_gp.py::test_acquisition_compositions_against_reference_executed_graphs).
+
 Restated reference sites (relative to /root/reference):
   * ExpectedImprovement.build_acquisition      gpflowopt/acquisition/ei.py:70-79  (fmin: ei.py:63-68)
   * ProbabilityOfImprovement.build_acquisition gpflowopt/acquisition/poi.py:63-67
@@ -102,7 +106,10 @@ class MES:
 
     def value(self, X):
         mean, var = self.gp.predict(X)
-        gamma, pdf, cdf = self._terms(mean[:, [0]], var[:, [0]])
+        return self._value(mean[:, [0]], var[:, [0]])
+
+    def _value(self, mean, var):
+        gamma, pdf, cdf = self._terms(mean, var)
         return np.sum(gamma * pdf / (2.0 * cdf) - log_ndtr(gamma), axis=1, keepdims=True) / self.samples.size
 
     def value_and_grad(self, X):

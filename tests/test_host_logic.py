@@ -189,3 +189,48 @@ def test_device_candidate_stream_host_regeneration(libgpfo):
     u = (a - lower) / (upper - lower)
     assert abs(u.mean() - 0.5) < 0.02 and abs(u.var() - 1.0 / 12.0) < 0.01          # uniform first moments
     assert abs(np.corrcoef(u[:-1, 0], u[1:, 0])[0, 1]) < 0.08                        # no obvious serial correlation
+
+
+def test_mes_gumbel_sampling_against_reference_generated_samples():
+    """tests/golden/mes_golden.npz holds the y* samples the reference's own MinValueEntropySearch._setup (mes.py:63-94) draws
+    for an analytic surrogate model and a fixed NumPy seed (tests/golden/gen_mes_golden.py).  The host-side restatement in
+    gpflowopt_b200/acquisition/mes.py consumes the random stream in the same order and must reproduce them."""
+    import importlib.util
+    import os
+    import types
+    from gpflowopt_b200.acquisition.mes import MinValueEntropySearch
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("gen_mes_golden", os.path.join(here, "golden", "gen_mes_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)                          # only for surrogate_moments (no reference access at import)
+    g = np.load(os.path.join(here, "golden", "mes_golden.npz"))
+    for k in range(int(g["n_cases"])):
+        X = g["case%d_X" % k]
+        holder = lambda a: types.SimpleNamespace(value=a, shape=a.shape)
+        model = types.SimpleNamespace(predict_f=gen.surrogate_moments, X=holder(X), Y=holder(gen.surrogate_moments(X)[0]))
+        acq = object.__new__(MinValueEntropySearch)       # the class without its device-backed constructor
+        acq._models, acq._parent, acq._engine, acq._needs_setup, acq.optimize_restarts = [model], None, None, False, 0
+        acq.gridsize, acq.num_samples = int(g["case%d_gridsize" % k]), int(g["case%d_num_samples" % k])
+        acq._domain = np.sum([ContinuousParameter("x%d" % i, l, u)
+                              for i, (l, u) in enumerate(zip(g["case%d_lower" % k], g["case%d_upper" % k]))])
+        np.random.seed(int(g["case%d_seed" % k]))
+        acq._setup()
+        np.testing.assert_allclose(acq.samples, g["case%d_samples" % k], rtol=1e-13, atol=0)
+
+
+def test_bo_result_assembly_against_reference_generated_results():
+    """tests/golden/bo_golden.npz: outputs of the reference's own BayesianOptimizer._create_bo_result (bo.py:156-203) on five
+    evaluation records (single objective, Pareto set, constrained, nothing feasible, constraints only), generated by
+    tests/golden/gen_bo_golden.py.  The restatement in gpflowopt_b200/bo.py must return the same arrays and flags."""
+    import os
+    import types
+    from gpflowopt_b200.bo import _summarise
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bo_golden.npz"))
+    for n in g["names"]:
+        rec = types.SimpleNamespace(data=(g["%s_X" % n], g["%s_Y" % n]), feasible_data_index=lambda n=n: g["%s_feasible" % n],
+                                    objective_indices=lambda n=n: g["%s_obj" % n], constraint_indices=lambda n=n: g["%s_con" % n])
+        r = _summarise(rec, True, "OK")
+        np.testing.assert_array_equal(np.atleast_2d(r.x), g["%s_x" % n])
+        np.testing.assert_array_equal(np.atleast_2d(r.fun), g["%s_fun" % n])
+        np.testing.assert_array_equal(np.atleast_2d(r.constraints), g["%s_constraints" % n])
+        assert bool(r.success) == bool(g["%s_success" % n]) and str(r.message) == str(g["%s_message" % n])

@@ -343,3 +343,29 @@ def test_domain_maps_and_membership_against_reference_generated_vectors():
     assert verdicts == [bool(v) for v in g["contains_rows"]]
     assert (g["contains_probes"][:3] in dom) == bool(g["contains_all"])
     assert (np.zeros((2, 3)) in dom) == bool(g["contains_wrong_width"])
+
+
+def test_acquisition_compositions_against_reference_executed_graphs():
+    """tests/golden/acq_golden.npz: the reference's own ``build_acquisition`` methods (EI, PoI, PoF, LCB, MES, HVPoI) executed
+    on fixed predictive moments with NumPy stand-ins for the TensorFlow primitives (tests/golden/gen_acq_golden.py).  The
+    oracle's compositions must give the same numbers: this pins clamps, operand order, gather indices and reductions at the
+    GPflowOpt level (the TF-internal ndtr / prob forms are the oracle's own on both sides)."""
+    import os
+    from helpers import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "acq_golden.npz"))
+    mean, var = g["mean"], g["var"]
+    leaf = lambda kind, p: oacq.Leaf(kind, None, p)._value(mean, var)
+    np.testing.assert_array_equal(leaf('ei', g["fmin"][0]), g["ei"])
+    np.testing.assert_array_equal(leaf('poi', g["fmin"][0]), g["poi"])
+    np.testing.assert_array_equal(leaf('pof', float(g["threshold"])), g["pof"])
+    np.testing.assert_array_equal(leaf('lcb', float(g["sigma"])), g["lcb"])
+    with np.errstate(all="ignore"):
+        mes = oacq.MES(None, g["samples"])._value(mean, var)
+    np.testing.assert_array_equal(np.isnan(mes), np.isnan(g["mes"]))
+    ok = np.isfinite(g["mes"])
+    np.testing.assert_array_equal(mes[ok], g["mes"][ok])
+    hv = oacq.HVPoI([], g["hv_front"], g["hv_lb"], g["hv_ub"], reference=g["hv_reference"])
+    with np.errstate(invalid="ignore"):
+        got = hv._value_from_moments(g["hv_mean"], np.maximum(g["hv_var"], oacq.STABILITY))
+    np.testing.assert_allclose(got, g["hvpoi"], rtol=1e-13, atol=1e-300)
+    assert np.max(g["hvpoi"]) > 0
