@@ -369,3 +369,36 @@ def test_acquisition_compositions_against_reference_executed_graphs():
         got = hv._value_from_moments(g["hv_mean"], np.maximum(g["hv_var"], oacq.STABILITY))
     np.testing.assert_allclose(got, g["hvpoi"], rtol=1e-13, atol=1e-300)
     assert np.max(g["hvpoi"]) > 0
+
+
+def test_transforms_against_reference_executed_graph_builders():
+    """tests/golden/transform_golden.npz: the reference's own LinearTransform.build_forward / build_backward /
+    build_backward_variance, ``~LinearTransform(std, mean)`` and ``Domain >> UnitCube`` executed on fixed data
+    (tests/golden/gen_transform_golden.py).  The oracle's literal restatement reproduces them bit for bit; the O(N) variance
+    form and the product's host class agree to rounding (one division instead of two triangular solves)."""
+    import os
+    from helpers import GOLDEN
+    from gpflowopt_b200.transforms import LinearTransform
+    g = np.load(os.path.join(GOLDEN, "transform_golden.npz"))
+    for k in range(int(g["n_cases"])):
+        c = lambda name: g["c%d_%s" % (k, name)]
+        t_in = ogp.domain_transform(c("lower"), c("upper"), np.zeros(c("lower").size), np.ones(c("lower").size))
+        np.testing.assert_array_equal(t_in.A, c("in_A"))
+        np.testing.assert_array_equal(t_in.b, c("in_b"))
+        np.testing.assert_array_equal(t_in.forward(c("X")), c("X_scaled"))
+        np.testing.assert_array_equal(t_in.backward(c("X_scaled")), c("X_back"))
+        Y = c("Y")
+        t_out = ogp.Linear(Y.std(axis=0), Y.mean(axis=0)).invert()
+        np.testing.assert_array_equal(t_out.A, c("out_A"))
+        np.testing.assert_array_equal(t_out.b, c("out_b"))
+        np.testing.assert_array_equal(t_out.forward(Y), c("Y_scaled"))
+        np.testing.assert_array_equal(t_out.backward(c("f_scaled")), c("mean"))
+        np.testing.assert_array_equal(t_out.backward_variance_literal(c("v_scaled")), c("var"))
+        np.testing.assert_allclose(t_out.backward_variance(c("v_scaled")), c("var"), rtol=4e-16)
+        # the product's host-side class (diagonal maps; its forward is what feeds gpfo_gp_set)
+        p_out = ~LinearTransform(Y.std(axis=0), Y.mean(axis=0))
+        np.testing.assert_array_equal(p_out.A, c("out_A"))
+        np.testing.assert_array_equal(p_out.b, c("out_b"))
+        np.testing.assert_array_equal(p_out.forward(Y), c("Y_scaled"))
+        np.testing.assert_allclose(p_out.backward(c("f_scaled")), c("mean"), rtol=1e-15)
+        np.testing.assert_allclose(p_out.backward_variance(c("v_scaled")), c("var"), rtol=1e-15)
