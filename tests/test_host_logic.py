@@ -234,3 +234,30 @@ def test_bo_result_assembly_against_reference_generated_results():
         np.testing.assert_array_equal(np.atleast_2d(r.fun), g["%s_fun" % n])
         np.testing.assert_array_equal(np.atleast_2d(r.constraints), g["%s_constraints" % n])
         assert bool(r.success) == bool(g["%s_success" % n]) and str(r.message) == str(g["%s_message" % n])
+
+
+def test_optimisers_against_reference_generated_results():
+    """tests/golden/optim_golden.npz: results of the reference's own MCOptimizer / CandidateOptimizer / StagedOptimizer
+    (gpflowopt/optim.py, row I) for seeded runs, a cross-row tie, a domain change and Ctrl-C at two places
+    (tests/golden/gen_optim_golden.py).  The same script through gpflowopt_b200.optim must give identical results."""
+    import importlib.util
+    import os
+    from gpflowopt_b200 import optim as product_optim
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("gen_optim_golden", os.path.join(here, "golden", "gen_optim_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+
+    def make_domain(lo, up):
+        return np.sum([ContinuousParameter("x%d" % i, l, u) for i, (l, u) in enumerate(zip(lo, up))])
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = gen.flatten(gen.run_all(product_optim, make_domain))
+    want = np.load(os.path.join(here, "golden", "optim_golden.npz"))
+    assert sorted(got) == sorted(want.files)
+    for key in want.files:
+        if key.endswith("_message"):
+            assert str(got[key]) == str(want[key]), key
+        else:
+            np.testing.assert_array_equal(np.asarray(got[key]), np.asarray(want[key]), err_msg=key)
