@@ -227,12 +227,12 @@ class AcquisitionAggregation(Acquisition):
         self._setup_objectives()
 
     def constraint_indices(self):
-        """Constraint columns of the concatenated output matrix (operand-local indices shifted by the operand's offset)."""
-        shifted, start = [], 0
-        for node in self.operands:
-            shifted.append(node.constraint_indices() + start)
-            start += node.data[1].shape[1]
-        return np.concatenate(shifted).astype(int)
+        """Constraint columns of the concatenated output matrix.  As in the reference (acquisition.py:349-355, pinned by
+        tests/golden/tree_golden.npz) operand k's local indices are shifted by the width of operand k-1 -- equal to the
+        cumulative offset for the usual two-operand trees, and kept as is for three or more so that results stay identical."""
+        widths = [node.data[1].shape[1] for node in self.operands]
+        shifts = [0] + widths[:-1]
+        return np.concatenate([node.constraint_indices() + shift for node, shift in zip(self.operands, shifts)]).astype(int)
 
     def feasible_data_index(self):
         return np.all(np.vstack([o.feasible_data_index() for o in self.operands]), axis=0)

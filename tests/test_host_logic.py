@@ -261,3 +261,28 @@ def test_optimisers_against_reference_generated_results():
             assert str(got[key]) == str(want[key]), key
         else:
             np.testing.assert_array_equal(np.asarray(got[key]), np.asarray(want[key]), err_msg=key)
+
+
+def test_aggregation_bookkeeping_against_reference_generated_records():
+    """tests/golden/tree_golden.npz: the reference's own AcquisitionAggregation.set_data / _setup / constraint_indices /
+    feasible_data_index run on recording stand-in operands (tests/golden/gen_tree_golden.py); the same script on
+    gpflowopt_b200's class must leave the same call log and return the same arrays (including the reference's
+    previous-operand shift of constraint columns for three or more operands)."""
+    import importlib.util
+    import os
+    from gpflowopt_b200.acquisition.acquisition import AcquisitionAggregation
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("gen_tree_golden", os.path.join(here, "golden", "gen_tree_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+
+    def make_aggregation(ops):
+        agg = object.__new__(AcquisitionAggregation)
+        agg.operands, agg._oper, agg._parent, agg._needs_setup, agg._engine = list(ops), 'sum', None, False, None
+        return agg
+
+    got = gen.script(make_aggregation)
+    want = np.load(os.path.join(here, "golden", "tree_golden.npz"))
+    assert sorted(got) == sorted(want.files)
+    for key in want.files:
+        np.testing.assert_array_equal(np.asarray(got[key]), np.asarray(want[key]), err_msg=key)
