@@ -13,6 +13,7 @@ from functools import wraps
 
 import numpy as np
 
+from .._lib import NotPositiveDefiniteError
 from ..domain import UnitCube
 from ..engine import Engine
 from ..gpr import GPR
@@ -27,7 +28,7 @@ def _best_restart(model, restarts):
             model.randomize()
         try:
             finished.append(model.optimize())
-        except Exception:                                   # pragma: no cover
+        except NotPositiveDefiniteError:                    # the reference catches tf.errors.InvalidArgumentError (Cholesky)
             print("Warning: optimization restart {0}/{1} failed".format(attempt, restarts))
     if not finished:
         raise RuntimeError("All model hyperparameter optimization restarts failed, exiting.")

@@ -286,3 +286,29 @@ def test_aggregation_bookkeeping_against_reference_generated_records():
     assert sorted(got) == sorted(want.files)
     for key in want.files:
         np.testing.assert_array_equal(np.asarray(got[key]), np.asarray(want[key]), err_msg=key)
+
+
+def test_leaf_bookkeeping_against_reference_generated_records():
+    """tests/golden/leaf_golden.npz: the reference's own Acquisition._optimize_models (restart protocol: first run from the
+    current state, the others randomised, Cholesky failures skipped, best run -- first on ties -- restored, all failing
+    raises) and set_data (per-model column blocks, setup flag) run on recording stand-in models
+    (tests/golden/gen_leaf_golden.py); gpflowopt_b200's class must leave the same call log."""
+    import importlib.util
+    import os
+    from gpflowopt_b200.acquisition.acquisition import Acquisition
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("gen_leaf_golden", os.path.join(here, "golden", "gen_leaf_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+
+    def make_leaf(models, restarts):
+        leaf = object.__new__(Acquisition)
+        leaf._models, leaf.optimize_restarts, leaf._needs_setup, leaf._parent, leaf._engine = models, restarts, True, None, None
+        return leaf
+
+    failure = lambda message: _lib.NotPositiveDefiniteError(_lib.ERR_NOT_SPD, message)
+    got = gen.script(make_leaf, failure, None)
+    want = np.load(os.path.join(here, "golden", "leaf_golden.npz"))
+    assert sorted(got) == sorted(want.files)
+    for key in want.files:
+        np.testing.assert_array_equal(np.asarray(got[key]), np.asarray(want[key]), err_msg=key)
