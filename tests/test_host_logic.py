@@ -312,3 +312,31 @@ def test_leaf_bookkeeping_against_reference_generated_records():
     assert sorted(got) == sorted(want.files)
     for key in want.files:
         np.testing.assert_array_equal(np.asarray(got[key]), np.asarray(want[key]), err_msg=key)
+
+
+def test_bo_loop_against_reference_generated_record():
+    """tests/golden/boloop_golden.npz: the reference's own BayesianOptimizer.optimize (initial design, then n_iter times
+    model callback -> inner optimiser on the negated acquisition -> objective evaluation -> set_data) run on recording
+    stand-ins (tests/golden/gen_boloop_golden.py); gpflowopt_b200's loop must leave the same call log and result."""
+    import importlib.util
+    import os
+    from gpflowopt_b200.bo import BayesianOptimizer
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("gen_boloop_golden", os.path.join(here, "golden", "gen_boloop_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+
+    def make_domain(lo, up):
+        return np.sum([ContinuousParameter("x%d" % i, l, u) for i, (l, u) in enumerate(zip(lo, up))])
+
+    def make_bo(dom, acq, inner, callback, initial):
+        bo = object.__new__(BayesianOptimizer)
+        bo._domain, bo._initial, bo._wrapper_args = dom, initial, dict(exclude_gradient=True)
+        bo.acquisition, bo.optimizer, bo._model_callback, bo.verbose, bo._scaling = acq, inner, callback, False, False
+        return bo
+
+    got = gen.script(make_bo, make_domain)
+    want = np.load(os.path.join(here, "golden", "boloop_golden.npz"))
+    assert sorted(got) == sorted(want.files)
+    for key in want.files:
+        np.testing.assert_array_equal(np.asarray(got[key]), np.asarray(want[key]), err_msg=key)
