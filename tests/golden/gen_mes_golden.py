@@ -53,14 +53,18 @@ def _install_stubs():
     def AutoFlow(*specs):
         return lambda fn: fn
 
+    class ParamList(list):
+        sorted_params = property(lambda self: list(self))
+
     tf = types.ModuleType("tensorflow")
     tf.int32, tf.int64, tf.float64, tf.float32 = "int32", "int64", "float64", "float32"
     tf.matmul, tf.transpose = np.matmul, np.transpose
+    tf.reduce_sum, tf.reduce_prod = "reduce_sum", "reduce_prod"       # only stored as the aggregation's tag
     tf.errors = types.SimpleNamespace(InvalidArgumentError=RuntimeError)
     gpflow = types.ModuleType("gpflow")
     param = types.ModuleType("gpflow.param")
     for name, obj in dict(Parameterized=Parameterized, DataHolder=DataHolder, AutoFlow=AutoFlow, Parentable=Parentable,
-                          ParamList=list, Param=DataHolder).items():
+                          ParamList=ParamList, Param=DataHolder).items():
         setattr(param, name, obj)
     model = types.ModuleType("gpflow.model")
     model.Model = type("Model", (Parameterized,), {})

@@ -63,6 +63,18 @@ def script(make_aggregation):
     return out
 
 
+def operator_script(make_leaf):
+    """Shapes of the trees the + and * operators build (flattening of equal aggregations, acquisition.py:269-293, 377-393)."""
+    a, b, c, d = (make_leaf(tag) for tag in "abcd")
+
+    def show(node):
+        if hasattr(node, "operands"):
+            return "%s(%s)" % (type(node).__name__, ", ".join(show(x) for x in node.operands))
+        return node.tag
+    exprs = ("a+b", "(a+b)+c", "a+(b+c)", "a*b*c", "(a+b)*c", "a+(b*c)", "(a*b)+(c*d)", "(a+b)*(c+d)", "a*(b*c)", "(a+b)+(c+d)")
+    return np.array(["%s -> %s" % (e, show(eval(e))) for e in exprs])
+
+
 def main():
     spec = importlib.util.spec_from_file_location("gen_optim_golden", os.path.join(HERE, "gen_optim_golden.py"))
     helper = importlib.util.module_from_spec(spec)
@@ -80,6 +92,14 @@ def main():
         return agg
 
     out = script(make_aggregation)
+
+    def make_leaf(tag):
+        leaf = object.__new__(type("Leaf", (base.Acquisition,), {}))
+        object.__setattr__(leaf, "tag", tag)
+        object.__setattr__(leaf, "_parent", None)
+        return leaf
+    out["operators"] = operator_script(make_leaf)
+    print(out["operators"])
     np.savez(os.path.join(HERE, "tree_golden.npz"), **out)
     for k in sorted(out):
         if "constraint_indices" in k or "return" in k:

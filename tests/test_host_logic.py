@@ -270,7 +270,7 @@ def test_aggregation_bookkeeping_against_reference_generated_records():
     previous-operand shift of constraint columns for three or more operands)."""
     import importlib.util
     import os
-    from gpflowopt_b200.acquisition.acquisition import AcquisitionAggregation
+    from gpflowopt_b200.acquisition.acquisition import Acquisition, AcquisitionAggregation
     here = os.path.dirname(os.path.abspath(__file__))
     spec = importlib.util.spec_from_file_location("gen_tree_golden", os.path.join(here, "golden", "gen_tree_golden.py"))
     gen = importlib.util.module_from_spec(spec)
@@ -282,6 +282,12 @@ def test_aggregation_bookkeeping_against_reference_generated_records():
         return agg
 
     got = gen.script(make_aggregation)
+
+    def make_leaf(tag):
+        leaf = object.__new__(type("Leaf", (Acquisition,), {}))
+        leaf.tag, leaf._parent, leaf._needs_setup, leaf._engine, leaf._models = tag, None, True, None, []
+        return leaf
+    got["operators"] = gen.operator_script(make_leaf)
     want = np.load(os.path.join(here, "golden", "tree_golden.npz"))
     assert sorted(got) == sorted(want.files)
     for key in want.files:
