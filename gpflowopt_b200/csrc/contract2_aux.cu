@@ -1,5 +1,6 @@
 // Contraction kernel v2, the launches around the production forward pass: row-split launches and their finish kernels,
 // the stored-A gradient pass (forward with A parked, backward over the reversed transposed stream) and the dense K^-1 pass.
+#include <cstdlib>
 #include "contract2_kernel.cuh"
 
 // Row-split finish, forward: sums the per-split partials of every candidate in split order, then the usual epilogue

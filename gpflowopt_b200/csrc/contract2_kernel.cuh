@@ -367,11 +367,13 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                             const int n = 8 * nb + 2 * (lane & 3) + c;
                             double u = 0.0;
                             if (rbl < nr) {
+                                double coef = gcv[n] * acc[r][nb][c];
+                                for (int ro = 0; ro < R; ++ro) coef = fma(gcm[n * RMAX + ro], __ldg(gp.alpha + (size_t)gi * R + ro), coef);
+                                // (regenerating dk/dr^2 here instead of storing it in the forward pass costs ~1 ms of a 43 ms
+                                // backward launch at M = 2048: measured by ablation, not worth a second scratch)
                                 double dot = 0.0;
                                 for (int d = 0; d < D; ++d) dot = fma(__ldg(Xs + (size_t)gi * D + d), xc[d * T + n], dot);
                                 const double r2 = (-2.0 * dot + __ldg(xn + gi)) + x2[n];
-                                double coef = gcv[n] * acc[r][nb][c];
-                                for (int ro = 0; ro < R; ++ro) coef = fma(gcm[n * RMAX + ro], __ldg(gp.alpha + (size_t)gi * R + ro), coef);
                                 u = coef * dk_dr2_branchless<KIND>(variance, r2, tab32);
                             }
                             ubuf[il * T + n] = u;
@@ -380,11 +382,26 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 __syncthreads();
                 for (int e = tid; e < T * (1 + D); e += C::THREADS) {     // thread (n, dd): fixed row order
                     const int n = e / (1 + D), dd = e - n * (1 + D);
-                    double a = gsum[e];
-                    if (dd == 0) for (int il = 0; il < 8 * nr; ++il) a += ubuf[il * T + n];
-                    else for (int il = 0; il < 8 * nr; ++il)
-                        a = fma(ubuf[il * T + n], __ldg(Xs + (size_t)(BWD ? rev - (8 * row0 + il) : 8 * row0 + il) * D + dd - 1), a);
-                    gsum[e] = a;
+                    // eight interleaved partial sums (rows il = 8q + k): the DFMA chain, not the loads, bounds this loop
+                    double a[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) a[k] = 0.0;
+                    a[0] = gsum[e];
+                    const int rows = 8 * nr;                              // a multiple of 8
+                    if (dd == 0) {
+                        for (int il = 0; il < rows; il += 8) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) a[k] += ubuf[(il + k) * T + n];
+                        }
+                    } else {
+                        const int step = BWD ? -D : D;
+                        const double* xp = Xs + (size_t)(BWD ? rev - 8 * row0 : 8 * row0) * D + dd - 1;
+                        for (int il = 0; il < rows; il += 8, xp += 8 * step) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) a[k] = fma(ubuf[(il + k) * T + n], __ldg(xp + k * step), a[k]);
+                        }
+                    }
+                    gsum[e] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
                 }
                 __syncthreads();
                 continue;
