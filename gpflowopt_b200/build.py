@@ -15,10 +15,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "build")
 LIB = os.path.join(HERE, "libgpfo.so")
-SOURCES = ["api.cu", "factor.cu", "contract.cu", "contract2.cu", "contract2_aux.cu", "contract2_prof.cu", "contract3.cu", "contract4.cu", "hvpoi.cu", "grad.cu", "pareto_host.cu"]
-HEADERS = [os.path.join(CSRC, "gpfo_internal.cuh"), os.path.join(CSRC, "contract_common.cuh"), os.path.join(CSRC, "contract2_kernel.cuh"), os.path.join(HERE, "..", "include", "gpfo.h")]
+SOURCES = ["api.cu", "factor.cu", "contract.cu", "contract2.cu", "contract2_aux.cu", "contract5.cu", "hvpoi.cu", "grad.cu", "pareto_host.cu"]
+# Kernels that were measured and rejected (2-CTA cluster, warp-specialised, bulk-copy re-reads) and the profiling builds
+# (ablations, phase counters) are compiled only with GPFO_BUILD_EXPERIMENTS=1; the production library holds reachable code only.
+EXPERIMENT_SOURCES = ["contract2_prof.cu", "contract3.cu", "contract4.cu"]
+EXPERIMENTS = os.environ.get("GPFO_BUILD_EXPERIMENTS", "0") not in ("", "0")
+HEADERS = [os.path.join(CSRC, "gpfo_internal.cuh"), os.path.join(CSRC, "contract_common.cuh"), os.path.join(CSRC, "contract2_kernel.cuh"),
+           os.path.join(CSRC, "contract5_kernel.cuh"), os.path.join(HERE, "..", "include", "gpfo.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "--expt-extended-lambda"]
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "--expt-extended-lambda"] + (["-DGPFO_BUILD_EXPERIMENTS=1"] if EXPERIMENTS else [])
+STAMP = os.path.join(OBJ, ".flavour")
 
 
 def _nvcc():
@@ -46,7 +52,12 @@ def _compile(args):
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
-    sources = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    flavour = "experiments" if EXPERIMENTS else "production"
+    if not os.path.exists(STAMP) or open(STAMP).read() != flavour:     # objects of the other flavour are stale
+        force = True
+        with open(STAMP, "w") as f:
+            f.write(flavour)
+    sources = [s for s in SOURCES + (EXPERIMENT_SOURCES if EXPERIMENTS else []) if os.path.exists(os.path.join(CSRC, s))]
     jobs = []
     for s in sources:
         src = os.path.join(CSRC, s)

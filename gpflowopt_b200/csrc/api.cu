@@ -16,15 +16,17 @@ struct GpHost {
     int M = 0, Mp = 0, Mf = 0, D = 0, R = 0, kind = 0, slot0 = 0;
     double *dX = nullptr, *dell = nullptr, *dXs = nullptr, *dxn = nullptr, *dY = nullptr, *dV = nullptr;
     double *dL = nullptr, *dLinv = nullptr;
-    double* dpacked_by[2] = {nullptr, nullptr};             // forward block streams: [0] 256-row chunks, [1] the other layout in use
-    size_t cap_packed_by[2] = {0, 0};
-    bool packed_ready[2] = {false, false};
-    int packed_slot_rbc[2] = {0, 0};
+    double* dpacked_by[3] = {nullptr, nullptr, nullptr};    // forward block streams: [0] 256-, [1] 512-, [2] 1024-row chunks (or other)
+    size_t cap_packed_by[3] = {0, 0, 0};
+    bool packed_ready[3] = {false, false, false};
+    int packed_slot_rbc[3] = {0, 0, 0};
     double *dalpha = nullptr, *dpacked_kinv = nullptr;      // gradient pass state, built lazily
     bool kinv_ready = false;
+#ifdef GPFO_BUILD_EXPERIMENTS
     double* dpacked_c[2] = {nullptr, nullptr};              // cluster layout (contract3), built lazily
     size_t cap_packed_c[2] = {0, 0};
     bool cluster_ready = false;
+#endif
     int packed_rbc = 0;
     // small-chunk copies of both block streams for the row-split launches (few candidates)
     double *dpacked_s = nullptr, *dpacked_kinv_s = nullptr;
@@ -154,8 +156,11 @@ int gpfo_ctx_create(int device, gpfo_ctx** out) {
 
 static void free_gp(GpHost& g) {
     cudaFree(g.dX); cudaFree(g.dell); cudaFree(g.dXs); cudaFree(g.dxn); cudaFree(g.dY); cudaFree(g.dV);
-    cudaFree(g.dL); cudaFree(g.dLinv); cudaFree(g.dpacked_by[0]); cudaFree(g.dpacked_by[1]); cudaFree(g.ddev);
-    cudaFree(g.dalpha); cudaFree(g.dpacked_kinv); cudaFree(g.dpacked_c[0]); cudaFree(g.dpacked_c[1]);
+    cudaFree(g.dL); cudaFree(g.dLinv); cudaFree(g.dpacked_by[0]); cudaFree(g.dpacked_by[1]); cudaFree(g.dpacked_by[2]); cudaFree(g.ddev);
+    cudaFree(g.dalpha); cudaFree(g.dpacked_kinv);
+#ifdef GPFO_BUILD_EXPERIMENTS
+    cudaFree(g.dpacked_c[0]); cudaFree(g.dpacked_c[1]);
+#endif
     cudaFree(g.dpacked_s); cudaFree(g.dpacked_kinv_s); cudaFree(g.dpacked_rt);
     g = GpHost();
 }
@@ -243,7 +248,7 @@ static int ensure_partials(gpfo_ctx* ctx) {
 // stay cached, so alternating batch sizes only re-sends the small GpDev record.
 static int repack(gpfo_ctx* ctx, GpHost& g, int rbc) {
     const PackGeom geom = make_geom(g.Mp / 8, rbc, 0);
-    const int slot = rbc == 32 ? 0 : 1;
+    const int slot = rbc == 32 ? 0 : (rbc == 64 ? 1 : 2);
     if (!g.packed_ready[slot] || g.packed_slot_rbc[slot] != rbc) {
         const size_t need = (size_t)pg_total_blocks(geom) * 64;
         CK(ensure(&g.dpacked_by[slot], &g.cap_packed_by[slot], need));
@@ -260,6 +265,7 @@ static int repack(gpfo_ctx* ctx, GpHost& g, int rbc) {
     return GPFO_OK;
 }
 
+#ifdef GPFO_BUILD_EXPERIMENTS
 // Cluster-layout block streams of L^-1 for the 2-CTA kernel (variant 10), built on first use.
 static int ensure_cluster_pack(gpfo_ctx* ctx, GpHost& g) {
     if (g.cluster_ready) return GPFO_OK;
@@ -278,6 +284,7 @@ static int ensure_cluster_pack(gpfo_ctx* ctx, GpHost& g) {
     g.cluster_ready = true;
     return GPFO_OK;
 }
+#endif  // GPFO_BUILD_EXPERIMENTS
 
 // Gradient-pass state of one GP: alpha = L^-T V and the dense block stream of K^-1 = L^-T L^-1 (built on first use).
 static int ensure_kinv(gpfo_ctx* ctx, GpHost& g) {
@@ -361,9 +368,11 @@ int gpfo_gp_set(gpfo_ctx* ctx, int gp_id, int64_t M64, int D, int R, const doubl
     }
     g.valid = false;
     g.kinv_ready = false;
+#ifdef GPFO_BUILD_EXPERIMENTS
     g.cluster_ready = false;
+#endif
     g.rt_ready = false;
-    g.packed_ready[0] = g.packed_ready[1] = false;
+    g.packed_ready[0] = g.packed_ready[1] = g.packed_ready[2] = false;
     g.M = M; g.Mp = Mp; g.Mf = Mf; g.D = D; g.R = R; g.kind = kernel_kind; g.slot0 = slot0;
     memset(&g.hdev, 0, sizeof(GpDev));
     double ell[GPFO_MAX_DIM];
@@ -696,6 +705,9 @@ static int launch_standard(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
             }
             gio.kx_scratch_stride = (long long)stride;
         }
+        if (variant == 20 || variant == 21) {   // v5 reads its block stream and layout from the launch record
+            gio.packed_o = ctx->gps[g].hdev.packed; gio.geom_o = ctx->gps[g].hdev.geom;
+        }
         CK(cudaEventRecord(ctx->ev[6], st));
         const int ns = generate ? 1 : split_count(ctx, N, gpfo_split_tile(), ctx->gps[g].geom_s.nchunks);
         if (ns > 1) {
@@ -705,8 +717,11 @@ static int launch_standard(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
             ++launches;
             fwd_parts = (int)((N + 127) / 128);
         } else {
+#ifdef GPFO_BUILD_EXPERIMENTS
             if (use_cluster) CK(gpfo_contract3_launch(st, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
-            else CK(gpfo_contract_launch(st, variant, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
+            else
+#endif
+            CK(gpfo_contract_launch(st, variant, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
             fwd_parts = grid;
         }
         CK(cudaEventRecord(ctx->ev[7], st));
@@ -782,11 +797,16 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
 
     int variant = effective_variant(ctx, N);
     if (generate && variant == 10) variant = 12;
+    if ((variant == 20 || variant == 21) && (want_grad || D > gpfo_contract5_max_dim(variant)))
+        variant = 12;     // the gradient pass parks A in the 64-candidate tile layout; very wide inputs exceed v5's shared memory
     const bool use_cluster = variant == 10;
     const int rbc = gpfo_contract_rbc(variant);
     for (int g = 0; g < ctx->ngps; ++g) {
+#ifdef GPFO_BUILD_EXPERIMENTS
         if (use_cluster) rc = ensure_cluster_pack(ctx, ctx->gps[g]);
-        else if (ctx->gps[g].packed_rbc != rbc) rc = repack(ctx, ctx->gps[g], rbc);
+        else
+#endif
+        if (ctx->gps[g].packed_rbc != rbc) rc = repack(ctx, ctx->gps[g], rbc);
         if (rc != GPFO_OK) return rc;
     }
 
@@ -825,7 +845,11 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
         if (dev_grads) io.grads = out_grads;
         else { CK(ensure(&ctx->dgrads, &ctx->cap_grads, (size_t)N * D)); io.grads = ctx->dgrads; }
     }
+#ifdef GPFO_BUILD_EXPERIMENTS
     const int grid = use_cluster ? gpfo_contract3_clusters(N, ctx->num_sms) : gpfo_contract_grid(variant, N, ctx->num_sms);
+#else
+    const int grid = gpfo_contract_grid(variant, N, ctx->num_sms);
+#endif
     const int hv_grid = gpfo_hvpoi_grid(N, ctx->num_sms);
     const int pg_grid = gpfo_program_grad_grid(N, ctx->num_sms);
     int max_parts = grid > hv_grid ? grid : hv_grid;
@@ -942,6 +966,7 @@ int gpfo_predict(gpfo_ctx* ctx, int gp_id, const double* X, int64_t N, int D, do
     int rc = stage_candidates(ctx, X, N, D, &dX);
     if (rc != GPFO_OK) return rc;
     int variant = effective_variant(ctx, N);
+    if ((variant == 20 || variant == 21) && D > gpfo_contract5_max_dim(variant)) variant = 12;
     if (variant == 10 || variant == 11 || variant == 12 || variant == 13 || variant == 14) variant = (N >= (int64_t)32 * ctx->num_sms) ? 4 : ((N >= (int64_t)16 * ctx->num_sms) ? 5 : 6);
     const int rbc = gpfo_contract_rbc(variant);
     if (g.packed_rbc != rbc) { rc = repack(ctx, g, rbc); if (rc != GPFO_OK) return rc; }
@@ -955,6 +980,7 @@ int gpfo_predict(gpfo_ctx* ctx, int gp_id, const double* X, int64_t N, int D, do
     io.X = dX; io.N = N; io.mstride = N; io.mom_mean = ctx->dmom_mean; io.mom_var = ctx->dmom_var;
     io.part_val = ctx->dpart_val; io.part_idx = ctx->dpart_idx;
     io.write_moments = 1; io.run_program = 0;
+    if (variant == 20 || variant == 21) { io.packed_o = g.hdev.packed; io.geom_o = g.hdev.geom; }
     const int ns = split_count(ctx, N, gpfo_split_tile(), g.geom_s.nchunks);
     if (ns > 1) {
         rc = ensure_partials(ctx);
@@ -984,7 +1010,11 @@ int gpfo_timings_get(const gpfo_ctx* ctx, gpfo_timings* out) {
 
 int gpfo_set_variant(gpfo_ctx* ctx, int variant) {
     if (!ctx) return GPFO_ERR_STATE;
-    static const int known[] = {0, 4, 5, 6, 10, 11, 12, 13, 14, 41, 42, 43, 121, 122, 123, 125, 127};
+#ifdef GPFO_BUILD_EXPERIMENTS
+    static const int known[] = {0, 4, 5, 6, 10, 11, 12, 13, 14, 20, 21, 41, 42, 43, 121, 122, 123, 125, 127};
+#else
+    static const int known[] = {0, 4, 5, 6, 11, 12, 20, 21};
+#endif
     bool ok = false;
     for (int k : known) ok = ok || k == variant;
     if (!ok) return fail(ctx, GPFO_ERR_BAD_SHAPE, "unknown kernel variant");

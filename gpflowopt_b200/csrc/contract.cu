@@ -38,9 +38,14 @@ void gpfo_argmax_final(cudaStream_t st, const double* part_val, const long long*
 //   11: T=32 + per-CTA K(X*,X) scratch       12: T=64, 256-row chunks + scratch (default for large batches)
 //   14: 12 with the scratch re-reads as 1-D bulk copies (cp.async.bulk / UBLKCP + mbarrier): same speed, not default
 //   13: the tiling of 12, warp-specialised (contract4.cu: 4 producer warps feed 16 DMMA warps through mbarrier stages)
+//   20: v5, 16 candidates x 1024-row chunks, resident K(X*,X) panel in shared memory, no scratch (contract5_kernel.cuh)
+//   21: v5, 32 candidates x 512-row chunks
 //   41-43, 121-123: ablations (no generation / no L^-1 loads / neither), 127: per-phase cycle counters -- profiling only
+//   (10, 13, 14, 4x and 12x exist only in builds with GPFO_BUILD_EXPERIMENTS=1)
 struct VarInfo { int rbc, tile; };
 static VarInfo var_info(int v) {
+    if (v == 20) return {128, 16};
+    if (v == 21) return {64, 32};
     if (v == 12 || v == 13 || v == 14 || (v >= 120 && v <= 129)) return {32, 64};
     if (v == 5) return {64, 16};
     if (v == 6) return {64, 8};
@@ -58,12 +63,21 @@ int gpfo_contract_grid(int variant, int64_t N, int num_sms) {
 cudaError_t gpfo_contract2_launch(cudaStream_t st, int variant, int kind, const GpDev* d_gp, const ProgramDev* d_prog,
                                   EvalIO io, int grid, int D);
 
+cudaError_t gpfo_contract5_launch(cudaStream_t st, int variant, int kind, const GpDev* d_gp, const ProgramDev* d_prog,
+                                  EvalIO io, int grid, int D);
+#ifdef GPFO_BUILD_EXPERIMENTS
 cudaError_t gpfo_contract_ws_launch(cudaStream_t st, int kind, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io,
                                     int grid, int D);
+#endif
 
 cudaError_t gpfo_contract_launch(cudaStream_t st, int variant, int kind, const GpDev* d_gp, const ProgramDev* d_prog,
                                  EvalIO io, int grid, int D) {
+    if (variant == 20 || variant == 21) return gpfo_contract5_launch(st, variant, kind, d_gp, d_prog, io, grid, D);
+#ifdef GPFO_BUILD_EXPERIMENTS
     if (variant == 13) return gpfo_contract_ws_launch(st, kind, d_gp, d_prog, io, grid, D);
+#else
+    if (variant == 13) return cudaErrorInvalidValue;
+#endif
     return gpfo_contract2_launch(st, variant, kind, d_gp, d_prog, io, grid, D);
 }
 

@@ -1,0 +1,17 @@
+// Contraction kernel v5 (resident K(X*,X) panel, no global scratch): launches.  Kernel: contract5_kernel.cuh.
+#include "contract5_kernel.cuh"
+
+// variants: 20 = 16 candidates x 1024-row chunks, 21 = 32 candidates x 512-row chunks (ring: 2 quads of row blocks per warp)
+cudaError_t gpfo_contract5_launch(cudaStream_t st, int variant, int kind, const GpDev* d_gp, const ProgramDev* d_prog,
+                                  EvalIO io, int grid, int D) {
+    if (variant == 21) return launch5<4, 4, 2>(st, kind, d_gp, d_prog, io, grid, D);
+    return launch5<8, 2, 2>(st, kind, d_gp, d_prog, io, grid, D);
+}
+
+// largest input dimension the shared-memory budget of a variant allows (two streaming buffers at least)
+int gpfo_contract5_max_dim(int variant) {
+    int D = GPFO_MAX_DIM;
+    if (variant == 21) { while (D > 0 && Contract5Cfg<4, 4, 2>::smem_bytes(D, 2) > (size_t)227 * 1024) --D; }
+    else { while (D > 0 && Contract5Cfg<8, 2, 2>::smem_bytes(D, 2) > (size_t)227 * 1024) --D; }
+    return D;
+}

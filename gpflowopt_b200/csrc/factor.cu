@@ -409,6 +409,7 @@ void gpfo_reverse_transpose(cudaStream_t st, const double* src, int ld, int n, d
     reverse_transpose_kernel<<<grd, blk, 0, st>>>(src, ld, n, dst);
 }
 
+#ifdef GPFO_BUILD_EXPERIMENTS
 // ---- cluster layout (see ClusterGeom) -----------------------------------------------------------------------------
 void gpfo_cluster_geom(int nrb, int rbc, ClusterGeom* g, long long total[2]) {
     g->nrb = nrb;
@@ -453,3 +454,4 @@ void gpfo_pack_linv_cluster(cudaStream_t st, const double* dLinv, int ld, const 
             pack_linv_cluster_kernel<<<(unsigned)pairs, 64, 0, st>>>(dLinv, ld, g, p, c, nr, c ? dpacked1 : dpacked0);
         }
 }
+#endif  // GPFO_BUILD_EXPERIMENTS

@@ -53,6 +53,7 @@ GPFO_HD int64_t pg_total_blocks(const PackGeom& g) {
     return pg_chunk_base(g, p) + (int64_t)p * g.rbc * nr + (int64_t)nr * (nr + 1) / 2;
 }
 
+#ifdef GPFO_BUILD_EXPERIMENTS
 // ------------------------------------------------------------------------------------------------
 // Cluster layout (contract3.cu): a pair of CTAs (one thread-block cluster) shares one candidate tile.  Rows are cut
 // into cluster chunks of 2*rbc row blocks; CTA rank c owns the row blocks of parity c (local block q <-> global block
@@ -82,6 +83,8 @@ GPFO_HD int cg_lo(int kd, int c) {
     return t > 0 ? (t >> 1) : 0;
 }
 
+#endif  // GPFO_BUILD_EXPERIMENTS
+
 // ------------------------------------------------------------------------------------------------
 // Device-side description of one GP and of the acquisition program
 // ------------------------------------------------------------------------------------------------
@@ -95,8 +98,10 @@ struct GpDev {
     const double* V;            // Mp x R, L^-1 Y (rows >= M are zero)
     const double* packed;       // block stream of L^-1
     PackGeom geom;
+#ifdef GPFO_BUILD_EXPERIMENTS
     const double* packed_c[2];  // cluster layout: one block stream of L^-1 per CTA rank
     ClusterGeom cgeom;
+#endif
     const double* alpha;        // Mp x R, K^-1 Y = L^-T V            (gradient pass only)
     const double* packed_kinv;  // dense block stream of K^-1         (gradient pass only)
     PackGeom geom_kinv;
@@ -335,6 +340,7 @@ int gpfo_factor_device(cudaStream_t st, int M, int Mf, int D, int R, int kind, d
                        double* dLinv /*Mf x Mf*/, const double* dY /*Mf x R*/, double* dV /*Mf x R*/,
                        int* dflag, std::string* err);
 void gpfo_pack_linv(cudaStream_t st, const double* dLinv, int ld, PackGeom g, double* dpacked);
+#ifdef GPFO_BUILD_EXPERIMENTS
 void gpfo_cluster_geom(int nrb, int rbc, ClusterGeom* g, long long total[2]);
 void gpfo_pack_linv_cluster(cudaStream_t st, const double* dLinv, int ld, const ClusterGeom& g, double* dpacked0,
                             double* dpacked1);
@@ -343,6 +349,9 @@ cudaError_t gpfo_contract3_launch(cudaStream_t st, int kind, const GpDev* d_gp, 
                                   int nclusters, int D);
 int gpfo_contract3_rbc();
 int gpfo_contract3_clusters(int64_t N, int num_sms);
+#endif
+// contract5.cu (resident-panel kernel)
+int gpfo_contract5_max_dim(int variant);
 // Kinv = Linv^T Linv (Mf x Mf, full symmetric) and alpha = Linv^T V, for the gradient pass
 void gpfo_kinv_alpha(cudaStream_t st, const double* dLinv, int Mf, const double* dV, int R, double* dKinv, double* dalpha);
 void gpfo_prepare_inputs(cudaStream_t st, const double* dX, int M, int Mp, int D, const double* d_ell,
