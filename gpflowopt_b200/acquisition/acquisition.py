@@ -82,10 +82,15 @@ class Acquisition(object):
         child._parent = self
         self.highest_parent._needs_setup = True
 
+    def _all_models(self):
+        """Every model the device needs for this (sub)tree.  Equals ``models`` except below an MCMCAcquistion, whose
+        ``models`` -- as in the reference -- shows the first copy only."""
+        return self.models
+
     def _get_engine(self):
         root = self.highest_parent
         if root._engine is None or root._engine.ctx is None:
-            adopted = [m._engine for m in root.models if getattr(m, '_engine', None) is not None
+            adopted = [m._engine for m in root._all_models() if getattr(m, '_engine', None) is not None
                        and m._engine.ctx is not None]
             root._engine = adopted[0] if adopted else Engine()
         return root._engine
@@ -203,6 +208,9 @@ class AcquisitionAggregation(Acquisition):
     def models(self):
         return [model for acq in self.operands for model in acq.models]
 
+    def _all_models(self):
+        return [model for acq in self.operands for model in acq._all_models()]
+
     def enable_scaling(self, domain):
         for oper in self.operands:
             oper.enable_scaling(domain)
@@ -239,7 +247,12 @@ class AcquisitionAggregation(Acquisition):
         return np.all(np.vstack([o.feasible_data_index() for o in self.operands]), axis=0)
 
     def build_acquisition(self, Xcand):
-        return Xcand.reduce(self._oper, [operand.build_acquisition(Xcand) for operand in self.operands])
+        # folded left to right (a b + c + ...): the same summation order as one k-ary reduce, but the program's stack stays
+        # two deep whatever the number of operands (the device stack holds 8 values)
+        node = self.operands[0].build_acquisition(Xcand)
+        for operand in self.operands[1:]:
+            node = Xcand.reduce(self._oper, [node, operand.build_acquisition(Xcand)])
+        return node
 
     def __getitem__(self, item):
         return self.operands[item]
@@ -289,6 +302,25 @@ class MCMCAcquistion(AcquisitionSum):
 
     def _optimize_models(self):
         self.operands[0]._optimize_models()
+
+    @property
+    def models(self):
+        """Only the models of the first operand; the copies stay hidden (gpflowopt/acquisition/acquisition.py:434-437), so
+        ``data`` and the objective / constraint indices keep the width of ONE acquisition."""
+        return self.operands[0].models
+
+    def _all_models(self):
+        return [model for acq in self.operands for model in acq._all_models()]
+
+    def enable_scaling(self, domain):
+        for operand in self.operands:
+            operand.enable_scaling(domain)
+
+    def constraint_indices(self):
+        return self.operands[0].constraint_indices()
+
+    def feasible_data_index(self):
+        return self.operands[0].feasible_data_index()
 
     def set_data(self, X, Y):
         for operand in self.operands:

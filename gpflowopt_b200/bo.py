@@ -27,19 +27,23 @@ from .scaling import DataScaler
 
 
 def jitchol_callback(models):
-    """Increase the likelihood variance in case of Cholesky failures (gpflowopt/bo.py:30-52)."""
+    """Increase the likelihood variance in case of Cholesky failures (gpflowopt/bo.py:30-52).
+
+    ``models`` are GPRs or the DataScalers around them.  Handing over the acquisition's own DataScalers (what
+    BayesianOptimizer does) makes the probe factorisation the one the following evaluation re-uses: same engine, same
+    device state, nothing is factorised twice."""
     for m in np.atleast_1d(models):
         scaler = m if isinstance(m, DataScaler) else None
         gpr = m.wrapped if scaler is not None else m
         if not isinstance(gpr, GPR):
             continue
         base = gpr.likelihood.variance
-        eKdiag = gpr.kern.variance + base                  # mean diagonal of K for a stationary kernel
+        eKdiag = gpr.kern.variance                         # mean(diag(K_symm)) of a stationary kernel, no noise (bo.py:45)
         probe = scaler if scaler is not None else DataScaler(gpr)
         for e in [0] + [10 ** ex for ex in range(-6, -1)]:
             try:
                 gpr.likelihood.variance = base + e * eKdiag
-                probe.predict_f(gpr.X.value[:1] if scaler is None else scaler.X.value[:1])   # forces a factorisation
+                probe.predict_f(probe.X.value[:1])         # forces a factorisation
                 break
             except NotPositiveDefiniteError:               # pragma: no cover
                 gpr.likelihood.variance = base
@@ -51,6 +55,11 @@ class _InverseAcquisition(object):
     def __init__(self, acquisition, with_gradient):
         self.acquisition = acquisition
         self.with_gradient = with_gradient
+
+    def bind_gradient(self, with_gradient):
+        """The objective as one optimiser stage wants it (called by Optimizer.optimize): gradient-based stages get
+        (-value, -gradient), gradient-free ones the value-only kernel.  Inside a StagedOptimizer every stage binds its own."""
+        return self if with_gradient == self.with_gradient else _InverseAcquisition(self.acquisition, with_gradient)
 
     def __call__(self, x):
         x = np.atleast_2d(x)
@@ -161,15 +170,18 @@ class BayesianOptimizer(Optimizer):
         while iteration < n_iter:
             with self.silent():
                 if self._model_callback is not None and self.acquisition._needs_setup:
-                    self._model_callback([scaler.wrapped for scaler in self.acquisition.models])
+                    models = self.acquisition.models
+                    # the default callback probes through the acquisition's own scalers (shared engine); a user callback
+                    # receives the wrapped models, as in the reference (bo.py:250-251)
+                    self._model_callback(models if self._model_callback is jitchol_callback else [m.wrapped for m in models])
                 step = self.optimizer.optimize(target)
                 self._update_model_data(step.x, fx(step.x))
             if self.verbose:
                 with self.silent():
-                    summary = _summarise(self.acquisition, True, 'Monitor')
+                    summary = self._create_bo_result(True, 'Monitor')
                 print(_progress_line(iteration, summary, step))
             iteration += 1
-        return _summarise(self.acquisition, True, "OK")
+        return self._create_bo_result(True, "OK")
 
     @contextmanager
     def failsafe(self):

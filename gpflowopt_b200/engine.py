@@ -143,7 +143,7 @@ class Engine(object):
     def prepare(self, acq):
         """Uploads everything ``acq`` (a node of the tree owning this engine) needs; returns nothing."""
         root = acq.highest_parent
-        slot_of = self.sync_models(root.models)
+        slot_of = self.sync_models(root._all_models())
         b = ProgramBuilder(slot_of)
         acq.build_acquisition(b)
         key = (tuple(b.ops), tuple(b.params))

@@ -5,6 +5,8 @@ These classes hold numbers only.  All arithmetic (kernel matrix, Cholesky, predi
 through libgpfo; hyper-parameter learning (GPflow's Model.optimize / HMC) is outside this path, so
 ``optimize()`` keeps the hyper-parameters it was given.
 """
+import warnings
+
 import numpy as np
 from scipy.optimize import OptimizeResult
 
@@ -101,8 +103,18 @@ class GPR(_Versioned):
     def state_version(self):
         return (self.version, self.kern.version, self.likelihood.version)
 
-    # hyper-parameter learning is not part of this path
+    # Hyper-parameter learning (GPflow's Model.optimize / HMC) is not part of this path (SURVEY.md section 2, rows 1 and 14;
+    # out of scope per section 8).  optimize() keeps the hyper-parameters it was given and says so once per process: a
+    # BO loop built on these holders scores candidates under FIXED hyper-parameters unless the caller assigns new ones
+    # (kern.variance / kern.lengthscales / likelihood.variance, or set_state) between iterations.
+    _warned_fixed = False
+
     def optimize(self, **kwargs):
+        if not GPR._warned_fixed:
+            GPR._warned_fixed = True
+            warnings.warn("gpflowopt_b200.GPR.optimize() does not fit hyper-parameters (model training is outside the "
+                          "accelerated path); the values assigned to the model are kept.  Assign fitted values yourself or "
+                          "construct the acquisition with optimize_restarts=0 to silence this.", UserWarning, stacklevel=2)
         return OptimizeResult(x=self.get_free_state(), fun=0.0, success=True, message="hyper-parameters kept")
 
     def randomize(self):

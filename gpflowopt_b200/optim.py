@@ -1,4 +1,5 @@
-"""Acquisition optimisers: mirror of gpflowopt/optim.py with the candidate scoring + argmin of
+"""Acquisition optimisers: mirror of gpflowopt/optim.py (GPflowOpt 0.1.1, Apache-2.0; the Optimizer / MCOptimizer /
+SciPyOptimizer / StagedOptimizer surface and messages follow it so results stay identical, see tests/golden/optim_golden.npz) with the candidate scoring + argmin of
 MCOptimizer / CandidateOptimizer fused on the device when the objective is a gpflowopt_b200 acquisition.
 
 An objective handed to ``Optimizer.optimize`` may carry an ``acquisition`` attribute (see
@@ -38,6 +39,8 @@ class Optimizer(object):
 
     def optimize(self, objectivefx, **kwargs):
         """Minimises ``objectivefx`` over the domain; Ctrl-C returns the last good point (optim.py:63-85)."""
+        if hasattr(objectivefx, 'bind_gradient'):          # acquisition objectives adapt to what this stage consumes
+            objectivefx = objectivefx.bind_gradient(self.gradient_enabled())
         objective = ObjectiveWrapper(objectivefx, **self._wrapper_args)
         objective.acquisition = getattr(objectivefx, 'acquisition', None)
         try:
@@ -107,8 +110,16 @@ class MCOptimizer(Optimizer):
             v, i = 0.0, -1
         best, idx = dist.reduce_pairs(*dist.allgather_pair(v, i))
         objective.counter += n
+        if idx < 0:
+            return self._no_finite_score(n)
         x = random_rows(seed, idx, 1, lower, upper)
         return OptimizeResult(x=x, success=True, fun=np.array([[-best]]), nfev=n, message="OK", seed=seed, index=idx)
+
+    def _no_finite_score(self, n):
+        """Every candidate scored NaN (or there were none): nothing to return.  (np.argmin would hand back row 0 with a NaN
+        score; here the stage reports failure so that callers do not evaluate the objective on an empty array.)"""
+        return OptimizeResult(x=np.empty((0, self.domain.size)), success=False, fun=np.array([[np.nan]]), nfev=n,
+                              message="No candidate received a finite acquisition score.")
 
     def _optimize(self, objective):
         acq = getattr(objective, 'acquisition', None)
@@ -127,7 +138,9 @@ class MCOptimizer(Optimizer):
                 v, i = 0.0, -1
             best, idx = dist.reduce_pairs(*dist.allgather_pair(v, i))
             objective.counter += n_total
-            x = dist.fetch_row(block, lo, idx, n_total, d) if idx >= 0 else np.empty((0, d))
+            if idx < 0:
+                return self._no_finite_score(n_total)
+            x = dist.fetch_row(block, lo, idx, n_total, d)
             return OptimizeResult(x=x, success=True, fun=np.array([[-best]]), nfev=n_total, message="OK")
         evaluations = objective(points)
         idx_best = np.argmin(evaluations, axis=0)
@@ -172,12 +185,19 @@ class SciPyOptimizer(Optimizer):
         self.config = dict(tol=tol, method=method, options=dict(disp=False, maxiter=maxiter))
 
     def _optimize(self, objective):
+        want_jac = self.gradient_enabled()
+
         def objective1d(X):
-            return tuple(arr.ravel() for arr in objective(X))
+            f, g = (arr.ravel() for arr in objective(X))
+            if want_jac and g.size != np.size(X):
+                # an empty gradient makes L-BFGS-B report convergence at the start point without taking a step
+                raise ValueError("SciPyOptimizer needs the gradient: the objective returned %d of %d components"
+                                 % (g.size, np.size(X)))
+            return f, g
         config = dict(self.config)
         if not config['options'].get('disp'):          # recent SciPy warns about an explicit disp=False
             config['options'] = {k: v for k, v in config['options'].items() if k != 'disp'}
-        return minimize(fun=objective1d, x0=self.get_initial().ravel(), jac=self.gradient_enabled(),
+        return minimize(fun=objective1d, x0=self.get_initial().ravel(), jac=want_jac,
                         bounds=list(zip(self.domain.lower, self.domain.upper)), **config)
 
 

@@ -142,3 +142,98 @@ def test_unsupported_models_are_refused():
     from gpflowopt_b200.transforms import LinearTransform
     with pytest.raises(ValueError):
         LinearTransform(np.array([[1.0, 0.3], [0.0, 1.0]]), [0.0, 0.0]).diagonal()
+
+
+# ---- round-2 regressions: gradients reach the SciPy stage of a staged optimiser, MCMC copies stay hidden, --------
+# ---- k-ary aggregations keep the device stack shallow, all-NaN scores fail the Monte-Carlo stage -----------------------------
+def _domain2():
+    return ContinuousParameter("a", -1, 1) + ContinuousParameter("b", -1, 1)
+
+
+def test_staged_optimizer_polish_stage_receives_gradients(fake):
+    """BayesianOptimizer(optimizer=StagedOptimizer([MCOptimizer, SciPyOptimizer])): the staged optimiser as a whole is
+    'gradient-free' (one stage is), but its SciPy stage must still be fed evaluate_with_gradients -- as the reference's
+    inverse_acquisition always does (gpflowopt/bo.py:244-245).  An empty gradient makes L-BFGS-B stop at its start."""
+    from gpflowopt_b200 import BayesianOptimizer
+    from gpflowopt_b200.optim import MCOptimizer, SciPyOptimizer, StagedOptimizer
+    X, Yo, _ = _data()
+    dom = _domain2()
+    acq = ExpectedImprovement(_gpr(X, Yo))
+    acq.optimize_restarts = 0
+    bo = BayesianOptimizer(dom, acq, optimizer=StagedOptimizer([MCOptimizer(dom, 50), SciPyOptimizer(dom)]), callback=None)
+    np.random.seed(0)
+    bo.optimize(lambda x: np.sum(np.atleast_2d(x) ** 2, axis=1, keepdims=True), n_iter=1)
+    evals = [c for c in acq._get_engine().ctx.calls if c[0] == "eval"]
+    assert ("eval", (50, 2), False, False) in evals                     # MC stage: fused argmax, no values, no gradients
+    polish = [c for c in evals if c[1] == (1, 2)]
+    assert polish and all(c[3] for c in polish)                         # every N = 1 polish call asks for gradients
+
+
+def test_scipy_optimizer_refuses_an_empty_gradient():
+    from gpflowopt_b200.optim import SciPyOptimizer
+    opt = SciPyOptimizer(_domain2())
+    with pytest.raises(ValueError, match="needs the gradient"):
+        opt.optimize(lambda x: (np.sum(x ** 2, axis=1, keepdims=True), np.zeros((x.shape[0], 0))))
+
+
+def test_mcmc_acquisition_hides_its_copies_and_runs_in_bo(fake):
+    """MCMCAcquistion(acq, k): ``models`` / ``data`` show the first copy only (gpflowopt/acquisition/acquisition.py:434-437) so
+    BayesianOptimizer(hyper_draws=k) sees ONE output column; the device still receives k GP states, and the program is
+    folded pairwise (stack depth 2), so k = 10 draws fit the 8-deep device stack."""
+    from gpflowopt_b200 import BayesianOptimizer
+    from gpflowopt_b200.acquisition import MCMCAcquistion
+    from gpflowopt_b200.optim import MCOptimizer
+    X, Yo, _ = _data()
+    dom = _domain2()
+    k = 10
+    bo = BayesianOptimizer(dom, LowerConfidenceBound(_gpr(X, Yo), 2.0), optimizer=MCOptimizer(dom, 40), hyper_draws=k,
+                           callback=None)
+    mc = bo.acquisition
+    assert isinstance(mc, MCMCAcquistion) and len(mc.operands) == k
+    assert len(mc.models) == 1 and len(mc._all_models()) == k
+    assert mc.data[1].shape == (12, 1)
+    np.testing.assert_array_equal(mc.objective_indices(), [0])
+    np.random.seed(0)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        r = bo.optimize(lambda x: np.sum(np.atleast_2d(x) ** 2, axis=1, keepdims=True), n_iter=2)
+    assert r.success and mc.data[0].shape[0] == 14 and all(o.data[0].shape[0] == 14 for o in mc.operands)
+    ctx = mc._get_engine().ctx
+    assert sorted({c[1] for c in ctx.calls if c[0] == "gp_set"}) == list(range(k))
+    prog = [c for c in ctx.calls if c[0] == "program_set"][-1][1]
+    depth = peak = 0
+    for op in prog:
+        if op[0] in (_lib.OP_SUM, _lib.OP_PROD):
+            depth -= op[1] - 1
+        elif op[0] != _lib.OP_SCALE:
+            depth += 1
+        peak = max(peak, depth)
+    assert depth == 1 and peak == 2 and prog[-1][0] == _lib.OP_SCALE
+    assert sum(1 for op in prog if op[0] == _lib.OP_LCB) == k
+
+
+def test_many_operand_sum_is_folded_left_to_right(fake):
+    X, Yo, _ = _data()
+    leaves = [LowerConfidenceBound(_gpr(X, Yo + i), 1.0 + i) for i in range(4)]
+    tree = leaves[0] + leaves[1] + leaves[2] + leaves[3]
+    assert isinstance(tree, AcquisitionSum) and len(tree.operands) == 4
+    tree.evaluate(np.zeros((2, 2)))
+    prog = [c for c in tree._get_engine().ctx.calls if c[0] == "program_set"][-1][1]
+    kinds = [op[0] for op in prog]
+    assert kinds == [_lib.OP_LCB, _lib.OP_LCB, _lib.OP_SUM, _lib.OP_LCB, _lib.OP_SUM, _lib.OP_LCB, _lib.OP_SUM]
+    assert all(op[1] == 2 for op in prog if op[0] == _lib.OP_SUM)
+
+
+def test_mc_optimizer_reports_failure_when_no_score_is_finite(fake, monkeypatch):
+    from gpflowopt_b200.optim import MCOptimizer
+    X, Yo, _ = _data()
+    dom = _domain2()
+    acq = ExpectedImprovement(_gpr(X, Yo))
+    monkeypatch.setattr(FakeContext, "eval", lambda self, X, want_values=True, want_grads=False: (None, None, 0.0, -1))
+
+    def target(x):
+        return -acq.evaluate(x), np.zeros((x.shape[0], 0))
+    target.acquisition = acq
+    r = MCOptimizer(dom, 30).optimize(target)
+    assert not r.success and r.x.shape == (0, 2) and "finite" in r.message
