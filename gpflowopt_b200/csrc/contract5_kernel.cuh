@@ -227,43 +227,112 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 }
             };
 
-            // one column block: B fragments from the group, A fragments from the ring, RBW * 2 * NB DMMAs.
-            // CUR_FULL: every row block of this warp is active in column block kp (dense column of a full chunk);
-            // NEXT_FULL: the same holds for the column block the ring is refilled for (kp + KA): no predicates at all.
-            // Otherwise row block r of this warp is active iff r_lo <= r < r_hi (warp-uniform bounds).
-            auto mma_kp = [&](const double* __restrict__ kbk, int kp, auto cur_tag, auto next_tag) {
-                constexpr bool CUR_FULL = decltype(cur_tag)::value, NEXT_FULL = decltype(next_tag)::value;
+            // One column block: B fragments from the group, A fragments from the ring, up to RBW * 2 * NB DMMAs.
+            // Row block r of this warp (global row block r * NW + w of the chunk) is active in column block kp iff
+            // r_lo(kp) <= r < r_hi, r_lo(kp) = ceil((kp - row0 - w) / NW) clamped at 0: warp-uniform, zero left of the diagonal,
+            // and constant over 16 consecutive diagonal column blocks.
+            //
+            // mma_static<RLO, NEXT_DENSE>: FULL chunks (r_hi == RBW).  Rows RLO .. RBW-1 are active, rows below RLO do not
+            // exist in the instruction stream.  (A predicated-off DMMA still occupies the FP64 tensor pipe for its 16 cycles
+            // -- measured: 1.5 x the useful pipe time with `@P DMMA` in the triangles, profiles/r02_v5_first_*.csv -- so the
+            // triangles are specialised at compile time and dispatched by a warp-uniform switch instead.)
+            // NEXT_DENSE: the column block the ring is refilled for is dense as well: unconditional copies.
+            auto mma_static = [&](const double* __restrict__ kbk, auto rlo_tag, auto next_tag) {
+                constexpr int RLO = decltype(rlo_tag)::value;
+                constexpr bool NEXT_DENSE = decltype(next_tag)::value;
+                double bf[2][NB];
+                if (RLO < RBW) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int nb = 0; nb < NB; ++nb) bf[h][nb] = kbk[(h * NB + nb) * 32];
+                }
+                // first row block the NEXT column block (kp_next) keeps: RLO or RLO + 1; none at all past the chunk's end
+                bool has_next = true, keep_first = true;
+                if (!NEXT_DENSE) {
+                    has_next = kp_next < kp_end;
+                    keep_first = (kp_next - row0 - w) <= RLO * NW;                 // ceil((kp_next - row0 - w) / NW) <= RLO
+                }
+#pragma unroll
+                for (int qd = 0; qd < QPC; ++qd) {
+                    if ((qd + 1) * RQ <= RLO) {           // no row block of this quad is left: keep the group count in step
+                        cp_async_commit();
+                        ring_step();
+                        continue;
+                    }
+                    cp_async_wait<QD - 1>();              // this thread's copies of the quad have landed
+                    const unsigned slot = myring_s + ring_off * 8;
+                    double2 a[RQ];
+#pragma unroll
+                    for (int i = 0; i < RQ; ++i)
+                        if (qd * RQ + i >= RLO) a[i] = lds128(slot + i * 512);
+                    // refill the slot just read for column block kp + KA (the loads above precede these asynchronous
+                    // writes in program order; their data returns long before a copy can land)
+#pragma unroll
+                    for (int i = 0; i < RQ; ++i) {
+                        const int r = qd * RQ + i;
+                        if (r > RLO) { if (NEXT_DENSE || has_next) cp_async16(slot + i * 512, src_next + r * (NW * 64)); }
+                        else if (r == RLO) { if (NEXT_DENSE || (has_next && keep_first)) cp_async16(slot + i * 512, src_next + r * (NW * 64)); }
+                    }
+                    cp_async_commit();
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int i = 0; i < RQ; ++i)
+                            if (qd * RQ + i >= RLO) {
+#pragma unroll
+                                for (int nb = 0; nb < NB; ++nb)
+                                    dmma884v(acc[qd * RQ + i][nb][0], acc[qd * RQ + i][nb][1], h == 0 ? a[i].x : a[i].y, bf[h][nb]);
+                            }
+                    ring_step();
+                }
+                advance_next();
+            };
+            auto mma_diag = [&](const double* __restrict__ kbk, int kp) {      // full chunk, diagonal column block: dispatch on r_lo
+                const int t = kp - row0 - w + (NW - 1);
+                const int r_lo = t > 0 ? t / NW : 0;
+                switch (r_lo) {
+                    case 0: mma_static(kbk, std::integral_constant<int, 0>(), std::false_type()); break;
+                    case 1: mma_static(kbk, std::integral_constant<int, (1 < RBW ? 1 : RBW)>(), std::false_type()); break;
+                    case 2: mma_static(kbk, std::integral_constant<int, (2 < RBW ? 2 : RBW)>(), std::false_type()); break;
+                    case 3: mma_static(kbk, std::integral_constant<int, (3 < RBW ? 3 : RBW)>(), std::false_type()); break;
+                    case 4: mma_static(kbk, std::integral_constant<int, (4 < RBW ? 4 : RBW)>(), std::false_type()); break;
+                    case 5: mma_static(kbk, std::integral_constant<int, (5 < RBW ? 5 : RBW)>(), std::false_type()); break;
+                    case 6: mma_static(kbk, std::integral_constant<int, (6 < RBW ? 6 : RBW)>(), std::false_type()); break;
+                    case 7: mma_static(kbk, std::integral_constant<int, (7 < RBW ? 7 : RBW)>(), std::false_type()); break;
+                    default: mma_static(kbk, std::integral_constant<int, RBW>(), std::false_type()); break;
+                }
+            };
+            // ragged last chunk (r_hi < RBW for some warps): generic bounds, predicated (slower; at most one chunk per tile)
+            auto mma_ragged = [&](const double* __restrict__ kbk, int kp) {
                 double bf[2][NB];
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
 #pragma unroll
                     for (int nb = 0; nb < NB; ++nb) bf[h][nb] = kbk[(h * NB + nb) * 32];
-                // active row blocks of this warp: r * NW + w >= kp - row0  <=>  r >= ceil((kp - row0 - w) / NW)
-                int r_lo = 0, n_lo = 0;
-                if (!CUR_FULL) { const int t = kp - row0 - w + (NW - 1); r_lo = t > 0 ? t / NW : 0; }
-                if (!NEXT_FULL) { const int t = kp_next - row0 - w + (NW - 1); n_lo = kp_next < kp_end ? (t > 0 ? t / NW : 0) : RBW; }
+                int r_lo, n_lo;
+                { const int t = kp - row0 - w + (NW - 1); r_lo = t > 0 ? t / NW : 0; }
+                { const int t = kp_next - row0 - w + (NW - 1); n_lo = kp_next < kp_end ? (t > 0 ? t / NW : 0) : RBW; }
 #pragma unroll
                 for (int qd = 0; qd < QPC; ++qd) {
-                    cp_async_wait<QD - 1>();              // this thread's copies of the quad have landed
+                    cp_async_wait<QD - 1>();
                     const unsigned slot = myring_s + ring_off * 8;
                     double2 a[RQ];
 #pragma unroll
                     for (int i = 0; i < RQ; ++i) {
-                        if (CUR_FULL || (qd * RQ + i >= r_lo && qd * RQ + i < r_hi)) a[i] = lds128(slot + i * 512);
+                        if (qd * RQ + i >= r_lo && qd * RQ + i < r_hi) a[i] = lds128(slot + i * 512);
                         else a[i] = make_double2(0.0, 0.0);
                     }
-                    // refill the slot just read for column block kp + KA (the loads above are ordered before these
-                    // asynchronous writes by the volatile asm order; their data returns long before a copy can land)
 #pragma unroll
                     for (int i = 0; i < RQ; ++i)
-                        if (NEXT_FULL || (qd * RQ + i >= n_lo && qd * RQ + i < r_hi))
+                        if (qd * RQ + i >= n_lo && qd * RQ + i < r_hi)
                             cp_async16(slot + i * 512, src_next + (qd * RQ + i) * (NW * 64));
                     cp_async_commit();
 #pragma unroll
                     for (int h = 0; h < 2; ++h)
 #pragma unroll
                         for (int i = 0; i < RQ; ++i) {
-                            if (CUR_FULL || (qd * RQ + i >= r_lo && qd * RQ + i < r_hi)) {
+                            if (qd * RQ + i >= r_lo && qd * RQ + i < r_hi) {
 #pragma unroll
                                 for (int nb = 0; nb < NB; ++nb)
                                     dmma884v(acc[qd * RQ + i][nb][0], acc[qd * RQ + i][nb][1], h == 0 ? a[i].x : a[i].y, bf[h][nb]);
@@ -305,13 +374,14 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 const int k1 = (k0 + GK < kp_end) ? k0 + GK : kp_end;
                 if (full_chunk && k1 + KA <= row0) {  // group and its refills in the dense part of a full chunk: no predicates
 #pragma unroll 1
-                    for (int kp = k0; kp < k1; ++kp) mma_kp(kb + (kp - k0) * (2 * NB * 32), kp, std::true_type(), std::true_type());
-                } else if (full_chunk && k1 <= row0) {
+                    for (int kp = k0; kp < k1; ++kp)
+                        mma_static(kb + (kp - k0) * (2 * NB * 32), std::integral_constant<int, 0>(), std::true_type());
+                } else if (full_chunk) {
 #pragma unroll 1
-                    for (int kp = k0; kp < k1; ++kp) mma_kp(kb + (kp - k0) * (2 * NB * 32), kp, std::true_type(), std::false_type());
+                    for (int kp = k0; kp < k1; ++kp) mma_diag(kb + (kp - k0) * (2 * NB * 32), kp);
                 } else {
 #pragma unroll 1
-                    for (int kp = k0; kp < k1; ++kp) mma_kp(kb + (kp - k0) * (2 * NB * 32), kp, std::false_type(), std::false_type());
+                    for (int kp = k0; kp < k1; ++kp) mma_ragged(kb + (kp - k0) * (2 * NB * 32), kp);
                 }
                 if (g >= RG) {                        // release the streaming buffer (its B fragments are consumed)
                     __syncwarp();

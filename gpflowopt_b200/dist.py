@@ -78,6 +78,76 @@ def scatter_points(points):
     return (block if block.is_cuda else block.numpy()), lo, n
 
 
+def pipelined_argmax(n_total, d, produce, score, rounds=8):
+    """The reference's single-stream candidate route under data parallelism (gpflowopt/design.py:55-70, 83-94;
+    optim.py:152-164), pipelined: ONLY rank 0 produces rows -- in order, ``produce(first_row, count)`` returns rows
+    [first_row, first_row + count) as a float64 ndarray, so successive ``np.random.rand`` draws form the reference's stream --
+    and the rows travel in ``rounds`` scatter steps of one equal chunk per rank.  Rank 0 scores its own chunk on a worker
+    thread, so producing + uploading round q+1 overlaps the device time of round q on every GPU.  Chunk j (global rows
+    [j C, (j+1) C)) goes to rank j mod world_size; every rank folds its chunks lexicographically (max value, lowest GLOBAL
+    index) and keeps a host copy of its best row.
+
+    ``score(block) -> (best value, best local index)``; ``block`` is a CUDA tensor under NCCL, an ndarray otherwise.
+    Returns (value, global index, row 1 x d) on every rank; index -1 when no row has a finite score."""
+    td = _pg()
+    if td is None or td.get_world_size() == 1:
+        rows = produce(0, n_total)
+        v, i = score(rows) if n_total > 0 else (0.0, -1)
+        return v, i, (np.array(rows[i:i + 1], dtype=np.float64) if i >= 0 else np.empty((0, d)))
+    import threading
+    import torch
+    dev = _device_for_collectives(td)
+    rank, ws = td.get_rank(), td.get_world_size()
+    meta = torch.tensor([int(n_total), int(d)], dtype=torch.int64, device=dev)
+    td.broadcast(meta, src=0)
+    n_total, d = int(meta[0]), int(meta[1])
+    rounds = max(1, min(int(rounds), -(-n_total // ws))) if n_total > 0 else 0
+    C = -(-n_total // (ws * rounds)) if n_total > 0 else 0          # rows per chunk
+    best = [0.0, -1, np.empty((0, d))]
+
+    def fold(block, first_row, count):
+        if count <= 0:
+            return
+        v, i = score(block[:count])
+        if i >= 0 and v == v and (best[1] < 0 or v > best[0]):        # chunks arrive in ascending global order: ties keep the first
+            row = block[i:i + 1]
+            best[:] = [v, first_row + i, np.array(row.cpu().numpy() if hasattr(row, 'cpu') else row, dtype=np.float64)]
+
+    worker = None
+    for q in range(rounds):
+        first = q * ws * C                                             # first global row of this round
+        out = torch.empty((C, d), dtype=torch.float64, device=dev)
+        chunks = None
+        if rank == 0:
+            count = max(0, min(n_total - first, ws * C))
+            full = torch.zeros((ws * C, d), dtype=torch.float64, device=dev)
+            if count > 0:
+                full[:count] = torch.from_numpy(np.ascontiguousarray(produce(first, count), dtype=np.float64)).to(dev)
+            chunks = list(full.split(C))
+        td.scatter(out, scatter_list=chunks, src=0)
+        mine = first + rank * C
+        count = max(0, min(n_total - mine, C))
+        block = out if out.is_cuda else out.numpy()
+        if rank == 0:                                                 # score while the next round is being produced
+            if worker is not None:
+                worker.join()
+            worker = threading.Thread(target=fold, args=(block, mine, count))
+            worker.start()
+        else:
+            fold(block, mine, count)
+    if worker is not None:
+        worker.join()
+    v, i = reduce_pairs(*allgather_pair(best[0], best[1]))
+    if i < 0:
+        return v, i, np.empty((0, d))
+    owner = int((i // C) % ws)
+    row = torch.empty((1, d), dtype=torch.float64, device=dev)
+    if rank == owner:
+        row.copy_(torch.from_numpy(best[2]))
+    td.broadcast(row, src=owner)
+    return v, i, row.cpu().numpy()
+
+
 def fetch_row(block, lo, index, n_total, d):
     """Row ``index`` of the scattered matrix on every rank (its owner broadcasts D doubles)."""
     td = _pg()

@@ -97,6 +97,11 @@ class MCOptimizer(Optimizer):
     def _get_eval_points(self):
         return RandomDesign(self._nsamples, self.domain).generate()
 
+    def _get_eval_rows(self, first_row, count):
+        """Rows [first_row, first_row + count) of the candidate set, for the pipelined multi-GPU route.  Successive calls
+        continue np.random's stream, so the chunks concatenate to exactly what one ``_get_eval_points()`` call draws."""
+        return RandomDesign(count, self.domain).generate()
+
     def _optimize_device_rng(self, objective, acq):
         from ._lib import random_rows
         n, lower, upper = self._nsamples, self.domain.lower, self.domain.upper
@@ -125,23 +130,24 @@ class MCOptimizer(Optimizer):
         acq = getattr(objective, 'acquisition', None)
         if acq is not None and self._device_rng and type(self)._get_eval_points is MCOptimizer._get_eval_points:
             return self._optimize_device_rng(objective, acq)
-        points = self._get_eval_points()
         if acq is not None:
             # fused route: argmin of -acq == argmax of acq with the same first-occurrence tie-break.  Under
-            # torch.distributed the rows are rank 0's, every rank receives and scores only its own block
-            n_total, d = points.shape
-            block, lo, n_total = dist.scatter_points(points)
-            if block.shape[0] > 0:
-                v, i = acq.argmax(block)
-                i = i + lo if i >= 0 else -1
+            # torch.distributed only rank 0 produces the rows (the reference's single RNG stream); they are scattered in
+            # pipelined rounds and every rank scores its chunks while rank 0 draws the next ones (dist.pipelined_argmax)
+            custom = type(self)._get_eval_points not in (MCOptimizer._get_eval_points, CandidateOptimizer._get_eval_points)
+            if custom:                                # a subclass that only overrides _get_eval_points: one draw, then slices
+                held = self._get_eval_points() if dist.world()[0] == 0 else None
+                produce = lambda first, count: held[first:first + count]
+                n_total = held.shape[0] if held is not None else 0
             else:
-                v, i = 0.0, -1
-            best, idx = dist.reduce_pairs(*dist.allgather_pair(v, i))
+                produce, n_total = self._get_eval_rows, self._nsamples
+            best, idx, x = dist.pipelined_argmax(n_total, self.domain.size, produce, acq.argmax)
+            n_total = self._nsamples if not custom else int(dist.broadcast_int(n_total))
             objective.counter += n_total
             if idx < 0:
                 return self._no_finite_score(n_total)
-            x = dist.fetch_row(block, lo, idx, n_total, d)
             return OptimizeResult(x=x, success=True, fun=np.array([[-best]]), nfev=n_total, message="OK")
+        points = self._get_eval_points()
         evaluations = objective(points)
         idx_best = np.argmin(evaluations, axis=0)
         return OptimizeResult(x=points[idx_best, :], success=True, fun=evaluations[idx_best, :],
@@ -165,6 +171,9 @@ class CandidateOptimizer(MCOptimizer):
 
     def _get_eval_points(self):
         return self.candidates
+
+    def _get_eval_rows(self, first_row, count):
+        return self.candidates[first_row:first_row + count]
 
     @property
     def domain(self):
