@@ -15,6 +15,12 @@ Printed JSON (rank 0, one line):
              H2D of the candidates and D2H of the (value, index) result inside the timed region
   roofline   the DMMA contraction kernel vs this GPU's FP64 tensor peak measured live (register-only mma.sync loop)
   cpu_baseline  the CPU oracle (NumPy/SciPy restatement of the reference path) on the host cores, bounded sample
+  configs    sub-records for the other BASELINE configs under the same clock: configs[2] (EI x PoF, M=4096, D=16, 1e7
+             candidates STRONG-scaled over the ranks, host-candidate and device-RNG routes, device time and wall),
+             configs[3] (HVPoI: GP contractions and cell kernel), configs[4] (values + gradients over M = 512...8192)
+  bars       library / CPU sanity bars of SURVEY 8(d): torch-fp64 `Linv @ K(X,X*)` on this GPU, best-of-10 FP64 GEMM 8192^3
+             (cuBLAS through torch.matmul) beside the DMMA issue peak, 1-thread CPU, per-call-Cholesky CPU, pageable e2e
+(--no-extras prints the headline only.)
 """
 import argparse
 import json
@@ -31,12 +37,20 @@ sys.path.insert(0, ROOT)
 M, D = 2048, 8
 N_PER_GPU = 1000000
 METRIC = "acq candidate evals/sec (M=2048,D=8,fp64)"
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel for one launch of this workload (N = 1e6),
-# taken from profiles/r01_final_contract2_v12.metrics.csv (27.7 GB read + 16.3 GB written: the per-CTA K(X*,X) scratch of
-# variant 12 is written back to HBM and partly re-read from it -- an earlier capture of the same kernel saw 44.7 GB read, the
-# split between L2 hits and HBM varies; the strictly on-chip variant 4 moves 36.5 MB per launch)
-NCU_DRAM_BYTES_PER_LAUNCH = 27688939000 + 16286433000      # profiles/r01_final_contract2_v12.metrics.csv (read + write)
 UNIT = "candidates/s"
+# The forward kernels a large batch can select (gpfo_timings.variant): name, and dram__bytes_read.sum + dram__bytes_write.sum
+# of ONE launch at this workload (N = 1e6, M = 2048) from the ncu capture named beside it -- DRAM bytes cannot be measured
+# outside a profiler, so the figure is a cited measurement, never a constant invented here.
+KERNELS = {
+    20: {"kernel": "contract5_kernel<8,2,2> (FP64 DMMA.8x8x4 contraction + fused EI epilogue + block argmax; 16-candidate tiles, "
+                   "1024-row chunks, K(X*,X) generated once per tile into a resident shared-memory panel, no global scratch)",
+         "traffic": None, "traffic_source": None},
+    21: {"kernel": "contract5_kernel<4,4,2> (as variant 20 with 32-candidate tiles and 512-row chunks)",
+         "traffic": None, "traffic_source": None},
+    12: {"kernel": "contract2_kernel<16,2,8,5,*,8> (FP64 DMMA.8x8x4 contraction + fused EI epilogue + block argmax; 64-candidate "
+                   "tiles, 256-row chunks, K(X*,X) generated once per tile and parked in a per-CTA global scratch)",
+         "traffic": 27688939000 + 16286433000, "traffic_source": "profiles/r01_final_contract2_v12.metrics.csv (2026-10-19)"},
+}
 
 
 def _workload_text(n):
@@ -136,6 +150,216 @@ def run_reference(args):
                 "the CPU oracle port of its path (oracle/), all host threads via OpenBLAS"})
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Sub-records: the other BASELINE configs and the library / CPU bars of SURVEY 8(d), all under the same driver clock
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_side_bars():
+    """1-thread CPU rate and the "reference-faithful" rate (Cholesky re-run inside every 4096-row call, as every
+    session.run of the reference does: SURVEY Appendix B), both with the oracle port on a bounded sample."""
+    from threadpoolctl import threadpool_limits
+    from gpflowopt_b200 import synthetic
+    from oracle import acq as oacq, gp as ogp
+    out = {}
+    with threadpool_limits(limits=1):
+        v1, dt1 = _cpu_oracle_throughput(4096)
+    out["cpu_1_thread"] = {"value": v1, "unit": UNIT, "cores": 1, "sample": "4096 candidates (%.1f s), Cholesky hoisted" % dt1}
+    with threadpool_limits(limits=host_threads()):
+        X, Y = synthetic.training_set(M, D)
+        h = synthetic.hypers(D)
+        Xc = synthetic.candidates(2 * 4096, D)
+        t0 = time.perf_counter()
+        for s in range(0, Xc.shape[0], 4096):
+            g = ogp.ScaledGPR(X, Y, ogp.MATERN52, h["lengthscales"], h["variance"], h["noise_variance"])   # fresh: K, chol per call
+            oacq.Leaf('ei', g, -1.5).value(Xc[s:s + 4096])
+        dt = time.perf_counter() - t0
+    out["cpu_per_call_cholesky"] = {"value": Xc.shape[0] / dt, "unit": UNIT, "cores": host_threads(),
+                                    "sample": "2 calls of 4096 candidates (%.1f s), K + Cholesky rebuilt inside each call "
+                                              "as the reference's session.run does" % dt}
+    return out
+
+
+def gpu_library_bars(torch, ctx_peak):
+    """(1) torch-fp64 restatement of the same scoring on this GPU with library kernels only (cdist-style r^2, Matern52,
+    `Linv @ Kx` through cuBLAS DGEMM, reductions): the "library bar".  (2) best-of-10 FP64 GEMM 8192^3 through torch.matmul
+    (cuBLAS): the library's FP64 tensor throughput beside the register-only DMMA issue peak."""
+    from gpflowopt_b200 import synthetic
+    dev = torch.device("cuda", torch.cuda.current_device())
+    X, Y = synthetic.training_set(M, D)
+    h = synthetic.hypers(D)
+    Xs = torch.from_numpy(X / h["lengthscales"]).to(dev)
+    r2 = (Xs * Xs).sum(1)[:, None] + (Xs * Xs).sum(1)[None, :] - 2.0 * Xs @ Xs.T
+    r = torch.sqrt(torch.clamp(r2, min=0.0) + 1e-12)
+    s5 = 5.0 ** 0.5
+    K = h["variance"] * (1.0 + s5 * r + (5.0 / 3.0) * r * r) * torch.exp(-s5 * r) + h["noise_variance"] * torch.eye(M, dtype=torch.float64, device=dev)
+    L = torch.linalg.cholesky(K)
+    Linv = torch.linalg.solve_triangular(L, torch.eye(M, dtype=torch.float64, device=dev), upper=False)
+    V = Linv @ torch.from_numpy(Y).to(dev)
+    ell = torch.from_numpy(h["lengthscales"]).to(dev)
+    n_lib, chunk = 131072, 16384
+    Xc = torch.from_numpy(synthetic.candidates(n_lib, D)).to(dev)
+    xn = (Xs * Xs).sum(1)[:, None]
+    fmin = -1.5
+
+    def score(xc):
+        xs = xc / ell
+        r2c = xn + (xs * xs).sum(1)[None, :] - 2.0 * Xs @ xs.T                   # M x n
+        rc = torch.sqrt(r2c + 1e-12)
+        Kx = h["variance"] * (1.0 + s5 * rc + (5.0 / 3.0) * rc * rc) * torch.exp(-s5 * rc)
+        A = Linv @ Kx                                                          # the dense N x M x M term (cuBLAS DGEMM)
+        mean = (A.T @ V)[:, 0]
+        var = torch.clamp(h["variance"] - (A * A).sum(0), min=1e-6)
+        sd = torch.sqrt(var)
+        z = (fmin - mean) / sd
+        ei = (fmin - mean) * 0.5 * (1.0 + torch.erf(z / 2.0 ** 0.5)) + sd * torch.exp(-0.5 * z * z) / (2.0 * np.pi) ** 0.5
+        return ei.max()
+
+    score(Xc[:chunk])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(0, n_lib, chunk):
+        score(Xc[s:s + chunk])
+    e1.record()
+    torch.cuda.synchronize()
+    lib_ms = e0.elapsed_time(e1)
+    a = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    b = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    torch.matmul(a, b)
+    best = 1e30
+    for _ in range(10):
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    dgemm = 2.0 * 8192.0 ** 3 / (best * 1e-3) / 1e12
+    del a, b
+    return {
+        "torch_fp64_library": {"value": n_lib / (lib_ms * 1e-3), "unit": UNIT,
+                               "sample": "%d candidates in %d-row chunks, same M/D/kernel; Kx materialised, Linv @ Kx = dense "
+                                         "cuBLAS DGEMM (2 M^2 flop/candidate), torch elementwise ops" % (n_lib, chunk),
+                               "tflops_dense": 2.0 * M * M * n_lib / (lib_ms * 1e-3) / 1e12},
+        "fp64_gemm_8192_best_of_10": {"value": dgemm, "unit": "TFLOP/s", "how": "torch.matmul float64 (cuBLAS), CUDA events"},
+        "dmma_issue_peak": {"value": ctx_peak, "unit": "TFLOP/s", "how": "gpfo_measure_dmma_peak: register-only mma.sync m8n8k4 loop"},
+    }
+
+
+def sub_config3_constrained(torch, td, gpfo, world, rank, barrier):
+    """BASELINE configs[2]: EI x PoF (2 GPs, M = 4096, D = 16) over 1e7 candidates, STRONG-scaled over the ranks, through the
+    public optimiser API.  Two candidate routes: the reference's (rank 0 draws np.random rows, pipelined scatter) and the
+    device generator.  Wall clock around Optimizer.optimize (max over ranks) and summed device time of the scoring calls."""
+    from gpflowopt_b200 import synthetic
+    from gpflowopt_b200.acquisition import ExpectedImprovement, ProbabilityOfFeasibility
+    from gpflowopt_b200.bo import _InverseAcquisition
+    from gpflowopt_b200.domain import UnitCube
+    from gpflowopt_b200.optim import MCOptimizer
+    M3, D3, N3 = 4096, 16, 10 ** 7
+    X, Y = synthetic.training_set(M3, D3, constraint=True)
+    h = synthetic.hypers(D3)
+
+    def mk(c):
+        return gpfo.GPR(X, Y[:, [c]], gpfo.Matern52(D3, variance=h["variance"], lengthscales=h["lengthscales"], ARD=True),
+                        noise_variance=h["noise_variance"])
+    t0 = time.perf_counter()
+    ei, pof = ExpectedImprovement(mk(0)), ProbabilityOfFeasibility(mk(1))
+    ei.optimize_restarts = pof.optimize_restarts = 0
+    joint = ei * pof
+    joint.evaluate(np.full((1, D3), 0.5))                               # setup: two factorisations, feasibility, fmin, program
+    setup_s = time.perf_counter() - t0
+    ctx = joint._get_engine().ctx
+    dom = UnitCube(D3)
+    rec = {"workload": "EI x PoF, 2 GPs, Matern52-ARD M=4096, D=16, 1e7 candidates over %d GPU(s) (BASELINE configs[2])" % world,
+           "scaling": "strong", "n_gpus": world, "candidates_total": N3, "setup_s": setup_s,
+           "flop_per_candidate": 2 * M3 * (M3 + 1)}
+    winners = {}
+    for key, opt in (("host_candidates", MCOptimizer(dom, N3)), ("device_rng", MCOptimizer(dom, N3, device_rng=True))):
+        np.random.seed(4321)
+        ctx.reset_cum()
+        barrier()
+        t0 = time.perf_counter()
+        res = opt.optimize(_InverseAcquisition(joint, False))
+        barrier()
+        wall = time.perf_counter() - t0
+        st = torch.tensor([wall, ctx.cum["eval_ms"], ctx.cum["hot_kernel_ms"]], dtype=torch.float64, device="cuda")
+        if world > 1:
+            td.all_reduce(st, op=td.ReduceOp.MAX)
+        wall, dev_ms, hot_ms = [float(v) for v in st.cpu()]
+        winners[key] = (res.x.copy(), float(np.ravel(res.fun)[0]))
+        rec[key] = {"wall_s": wall, "value_wall": N3 / wall, "device_ms": dev_ms, "value_device": N3 / (dev_ms * 1e-3),
+                    "unit": UNIT, "tflops_per_gpu": rec["flop_per_candidate"] * (N3 / world) / (hot_ms * 1e-3) / 1e12,
+                    "scoring_calls_per_rank": ctx.cum["calls"], "best_acq": -winners[key][1]}
+    rec["host_candidates"]["route"] = ("rank 0 draws np.random.rand rows in order (the reference's single stream, design.py:83-94), "
+                                       "8 pipelined scatter rounds; every rank scores its chunk while the next is drawn")
+    rec["device_rng"]["route"] = "counter-based generator inside the scoring kernel, every rank its own rows (opt-in, different stream)"
+    joint._get_engine().close()
+    return rec
+
+
+def sub_config4_hvpoi(gpfo):
+    """BASELINE configs[3]: HVProbabilityOfImprovement, 3 objectives, M = 1024 per GP, D = 6, 1e6 candidates, front ~200."""
+    from gpflowopt_b200 import synthetic
+    from gpflowopt_b200.acquisition import HVProbabilityOfImprovement
+    M4, D4, R4, N4 = 1024, 6, 3, 1000000
+    X = synthetic.candidates(M4, D4, seed=5)
+    F = synthetic.dtlz2_objectives(X, R4, g_scale=0.4)
+    h = synthetic.hypers(D4, 1e-3)
+    models = [gpfo.GPR(X, F[:, [j]], gpfo.Matern52(D4, variance=h["variance"], lengthscales=h["lengthscales"], ARD=True),
+                       noise_variance=h["noise_variance"]) for j in range(R4)]
+    t0 = time.perf_counter()
+    hv = HVProbabilityOfImprovement(models)
+    hv.optimize_restarts = 0
+    Xc = synthetic.candidates(N4, D4)
+    hv.evaluate(Xc[:256])                                               # setup: 3 factorisations, front, cell decomposition
+    setup_s = time.perf_counter() - t0
+    ctx = hv._get_engine().ctx
+    hv.argmax(Xc)
+    best = None
+    for _ in range(2):
+        v, i = hv.argmax(Xc)
+        t = ctx.timings()
+        if best is None or t["eval_ms"] < best["eval_ms"]:
+            best = t
+    P = int(hv.pareto.front.shape[0]) if hasattr(hv, "pareto") else None
+    rec = {"workload": "HVPoI, 3 objectives, Matern52-ARD M=1024 per GP, D=6, 1e6 candidates (BASELINE configs[3])",
+           "pareto_front": P, "setup_s": setup_s, "eval_ms": best["eval_ms"], "gp_contractions_ms": best["hot_kernel_ms"],
+           "cell_kernel_ms": best["eval_ms"] - best["hot_kernel_ms"], "value": N4 / (best["eval_ms"] * 1e-3), "unit": UNIT,
+           "launches": int(best["launches"]), "best": {"value": v, "index": i}}
+    hv._get_engine().close()
+    return rec
+
+
+def sub_config5_sweep(gpfo, peak):
+    """BASELINE configs[4] on one GPU: M = 512 ... 8192, values (argmax) and evaluate_with_gradients, device time."""
+    from gpflowopt_b200 import synthetic
+    from gpflowopt_b200.acquisition import ExpectedImprovement
+    rows = []
+    for Ms in (512, 1024, 2048, 4096, 8192):
+        X, Y = synthetic.training_set(Ms, D)
+        h = synthetic.hypers(D)
+        acq = ExpectedImprovement(gpfo.GPR(X, Y, gpfo.Matern52(D, variance=h["variance"], lengthscales=h["lengthscales"], ARD=True),
+                                           noise_variance=h["noise_variance"]))
+        acq.optimize_restarts = 0
+        n = int(min(2e6, 5e5 * (2048.0 / Ms) ** 2))
+        ng = max(40000, n // 4)
+        Xc = synthetic.candidates(n, D)
+        acq.argmax(Xc[:65536])
+        ctx = acq._get_engine().ctx
+        acq.argmax(Xc)
+        t = ctx.timings()
+        tf = n * Ms * (Ms + 1.0) / (t["hot_kernel_ms"] * 1e-3) / 1e12
+        acq.evaluate_with_gradients(Xc[:ng])
+        acq.evaluate_with_gradients(Xc[:ng])
+        tg = ctx.timings()
+        tfg = ng * 2.0 * Ms * (Ms + 1.0) / (tg["eval_ms"] * 1e-3) / 1e12
+        rows.append({"M": Ms, "values": {"candidates": n, "eval_ms": t["eval_ms"], "value": n / (t["eval_ms"] * 1e-3),
+                                         "tflops": tf, "frac_of_dmma_peak": tf / peak, "kernel_variant": int(t["variant"])},
+                     "gradients": {"candidates": ng, "eval_ms": tg["eval_ms"], "value": ng / (tg["eval_ms"] * 1e-3),
+                                   "tflops_algorithmic_2M2": tfg, "frac_of_dmma_peak": tfg / peak}})
+        acq._get_engine().close()
+    return {"workload": "EI, Matern52-ARD, D=8, M sweep, values and evaluate_with_gradients on one GPU (BASELINE configs[4])",
+            "unit": UNIT, "rows": rows}
+
+
 _REAL_STDOUT = None
 
 
@@ -164,6 +388,7 @@ def main():
     ap.add_argument("--candidates", type=int, default=N_PER_GPU)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline only: skip the configs / bars sub-records")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -251,16 +476,25 @@ def main():
     e2e_ms = (time.perf_counter() - t0) * 1e3
     assert best_e2e == best, "host and device candidate paths disagree: %r vs %r" % (best_e2e, best)
 
-    # ---- side measurement: the strictly-on-chip variant (K(X*,X) never leaves the SM; no global scratch) ----------
-    strict_ms = 0.0
+    variant_used = int(ctx.timings()["variant"])
+
+    # ---- side measurements (rank-local, short): e2e from a PAGEABLE ndarray (what RandomDesign.generate() hands over), and
+    # the previous default kernel (64-candidate tiles + global K(X*,X) scratch) for comparison
+    pageable = np.array(host.numpy())                    # ordinary malloc'ed copy
+    acq.argmax(pageable)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        acq.argmax(pageable)
+    pageable_ms = (time.perf_counter() - t0) * 1e3
+    alt_ms, alt_variant = 0.0, (12 if variant_used != 12 else 20)
     if not args.variant:
-        ctx.set_variant(4)
+        ctx.set_variant(alt_variant)
         step_device()
         for s in range(args.steps):
             flush.fill_(float(s))
             torch.cuda.synchronize()
             step_device()
-            strict_ms += ctx.timings()["eval_ms"]
+            alt_ms += ctx.timings()["eval_ms"]
         ctx.set_variant(0)
 
     stats = torch.tensor([dev_ms, hot_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
@@ -289,26 +523,48 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                         "traffic_note": "dram__bytes_read+write of one contract2_kernel launch at this workload from "
-                                         "profiles/ (ncu --set full); bytes, not flop: the kernel is tensor bound, HBM is not",
-                         "kernel": "contract2_kernel<16,2,8,4> (FP64 DMMA.8x8x4 contraction + fused EI epilogue + block "
-                                   "argmax; 64-candidate tiles, 256-row chunks, K(X*,X) generated once per tile)",
+                         "frac": achieved / fp64_peak, "traffic": KERNELS.get(variant_used, {}).get("traffic"),
+                         "traffic_note": "dram__bytes_read+write of ONE launch of this kernel at this workload, from the ncu "
+                                         "capture named in traffic_source (not measurable outside a profiler); algorithmic "
+                                         "bytes per launch = 8(D+1) N + 8 M(M+1)/2 = %d" % (8 * (D + 1) * n_local + 4 * M * (M + 1)),
+                         "traffic_source": KERNELS.get(variant_used, {}).get("traffic_source"),
+                         "kernel_variant": variant_used,
+                         "kernel": KERNELS.get(variant_used, {}).get("kernel", "variant %d" % variant_used),
                          "flop_per_candidate": M * (M + 1),
                          "peak_source": "FP64 DMMA issue peak measured live on this GPU (gpfo_measure_dmma_peak); "
                                         "MEASURED_PEAKS.json holds no FP64 figure; nominal 37.2 TFLOP/s"},
             "best": {"value": best[0], "index": best[1]},
         }
-        if strict_ms > 0.0:
-            out["strict_onchip"] = {"value": n_local / (strict_ms / args.steps * 1e-3), "unit": UNIT,
-                                    "note": "rank 0, variant 4: covariance tiles strictly on chip (no global scratch), "
-                                            "the literal north_star dataflow"}
-        if not args.no_cpu_baseline:
+        out["e2e_pageable"] = {"value": n_local / (pageable_ms / args.steps * 1e-3), "unit": UNIT,
+                               "note": "rank 0 alone, Acquisition.argmax(pageable ndarray): the H2D copy goes through the driver's staging"}
+        if alt_ms > 0.0:
+            out["alt_kernel"] = {"kernel_variant": alt_variant, "value": n_local / (alt_ms / args.steps * 1e-3), "unit": UNIT,
+                                 "kernel": KERNELS.get(alt_variant, {}).get("kernel"),
+                                 "traffic": KERNELS.get(alt_variant, {}).get("traffic"),
+                                 "note": "rank 0, same workload through the other large-batch kernel (gpfo_set_variant)"}
+        if not args.no_cpu_baseline and world == 1:      # reported baseline: rank 0 at N = 1 only (the host is the same at every N)
             n_cpu = 100000
             v_cpu, dt = cpu_oracle_throughput(n_cpu)
             out["cpu_baseline"] = {"value": v_cpu, "unit": UNIT, "cores": host_threads(), "kind": "port",
                                    "sample": "%d candidates (%.1f s) in 4096-row chunks, Cholesky hoisted, "
                                              "NumPy/SciPy + OpenBLAS on all host cores" % (n_cpu, dt)}
+    engine.close()
+    del dev, flush
+    torch.cuda.empty_cache()
+    if not args.no_extras:
+        t_extra = time.perf_counter()
+        cfg3 = sub_config3_constrained(torch, td, gpfo, world, rank, barrier)          # collective: every rank takes part
+        if rank == 0:
+            out["configs"] = {"configs[2]": cfg3}
+            if world == 1:                                # single-GPU records and bars: once, in the N = 1 run
+                out["configs"]["configs[3]"] = sub_config4_hvpoi(gpfo)
+                out["configs"]["configs[4]"] = sub_config5_sweep(gpfo, fp64_peak)
+                out["bars"] = gpu_library_bars(torch, fp64_peak)
+                if not args.no_cpu_baseline:
+                    out["bars"].update(cpu_side_bars())
+            out["extras_wall_s"] = time.perf_counter() - t_extra
+        barrier()
+    if rank == 0:
         emit(out)
     if world > 1:
         td.destroy_process_group()

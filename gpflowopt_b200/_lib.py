@@ -17,12 +17,13 @@ MAX_GPS, MAX_SLOTS, MAX_OPS, MAX_PARAMS, MAX_DIM = 16, 16, 64, 64, 64
 EXPORTS = ["gpfo_version", "gpfo_ctx_create", "gpfo_ctx_destroy", "gpfo_last_error", "gpfo_status_string",
            "gpfo_gp_set", "gpfo_gp_count_set", "gpfo_gp_get_factor", "gpfo_program_set", "gpfo_cells_set",
            "gpfo_eval", "gpfo_predict", "gpfo_timings_get", "gpfo_set_variant", "gpfo_measure_dmma_peak",
-           "gpfo_measure_fp64_pipes", "gpfo_pareto_cells", "gpfo_eval_random", "gpfo_random_rows"]
+           "gpfo_measure_fp64_pipes", "gpfo_pareto_cells", "gpfo_eval_random", "gpfo_random_rows", "gpfo_ndtr_fast_host"]
 
 
 class Timings(ctypes.Structure):
     _fields_ = [("factor_ms", ctypes.c_double), ("h2d_ms", ctypes.c_double), ("eval_ms", ctypes.c_double),
-                ("d2h_ms", ctypes.c_double), ("hot_kernel_ms", ctypes.c_double), ("launches", ctypes.c_int64)]
+                ("d2h_ms", ctypes.c_double), ("hot_kernel_ms", ctypes.c_double), ("launches", ctypes.c_int64),
+                ("variant", ctypes.c_int64)]
 
 
 class GpfoError(RuntimeError):
@@ -75,6 +76,7 @@ def load():
     lib.gpfo_eval_random.argtypes = [vp, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, c_dp, c_dp, c_dp,
                                      ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]
     lib.gpfo_random_rows.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, c_dp, c_dp, c_dp]
+    lib.gpfo_ndtr_fast_host.argtypes = [c_dp, ctypes.c_int64, c_dp]
     lib.gpfo_pareto_cells.argtypes = [c_dp, c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_double, c_dp, c_dp, ctypes.c_int64,
                                       ctypes.POINTER(ctypes.c_int64)]
     for name in EXPORTS:
@@ -94,6 +96,17 @@ def _f64(a, shape=None):
     if shape is not None:
         a = a.reshape(shape)
     return a
+
+
+def ndtr_fast_host(z):
+    """The HVPoI kernel's branch-free Normal CDF (csrc/ndtr_fast.cuh), evaluated on the host (tests; no GPU needed)."""
+    lib = load()
+    z = _f64(z).ravel()
+    out = np.empty_like(z)
+    st = lib.gpfo_ndtr_fast_host(_ptr(z), z.size, _ptr(out))
+    if st != OK:
+        raise GpfoError(st, "gpfo_ndtr_fast_host failed")
+    return out
 
 
 def random_rows(seed, first_row, n, lower, upper):
@@ -139,6 +152,7 @@ class Context(object):
                                 "no CPU fallback)" % (device, self._lib.gpfo_status_string(st).decode()))
         self._h = h
         self.device = int(device)
+        self.cum = dict(eval_ms=0.0, hot_kernel_ms=0.0, h2d_ms=0.0, launches=0, calls=0)   # running totals over gpfo_eval calls
 
     def close(self):
         if getattr(self, "_h", None):
@@ -212,6 +226,7 @@ class Context(object):
         bv, bi = ctypes.c_double(0.0), ctypes.c_int64(-1)
         self._check(self._lib.gpfo_eval(self._h, _ptr(X) if N else None, N, D, _ptr(vals) if N else None,
                                         _ptr(grads) if (want_grads and N) else None, ctypes.byref(bv), ctypes.byref(bi)))
+        self._accumulate()
         return vals, grads, bv.value, bi.value
 
     def eval_device(self, x_ptr, N, D, values_ptr=None, grads_ptr=None):
@@ -221,6 +236,7 @@ class Context(object):
                                         ctypes.c_void_p(values_ptr) if values_ptr else None,
                                         ctypes.c_void_p(grads_ptr) if grads_ptr else None,
                                         ctypes.byref(bv), ctypes.byref(bi)))
+        self._accumulate()
         return bv.value, bi.value
 
     def eval_random(self, seed, first_row, N, lower, upper, want_values=False):
@@ -230,6 +246,7 @@ class Context(object):
         bv, bi = ctypes.c_double(0.0), ctypes.c_int64(-1)
         self._check(self._lib.gpfo_eval_random(self._h, int(seed), int(first_row), int(N), lower.size, _ptr(lower), _ptr(upper),
                                                _ptr(vals) if (want_values and N) else None, ctypes.byref(bv), ctypes.byref(bi)))
+        self._accumulate()
         return vals, bv.value, bi.value
 
     def predict(self, gp_id, X, R):
@@ -239,6 +256,17 @@ class Context(object):
         self._check(self._lib.gpfo_predict(self._h, gp_id, _ptr(X) if N else None, N, D, _ptr(mean) if N else None,
                                            _ptr(var) if N else None))
         return mean, var
+
+    def _accumulate(self):
+        t = Timings()
+        if self._lib.gpfo_timings_get(self._h, ctypes.byref(t)) == OK:
+            c = self.cum
+            c["eval_ms"] += t.eval_ms; c["hot_kernel_ms"] += t.hot_kernel_ms; c["h2d_ms"] += t.h2d_ms
+            c["launches"] += t.launches; c["calls"] += 1
+
+    def reset_cum(self):
+        for k in self.cum:
+            self.cum[k] = 0 if k in ("launches", "calls") else 0.0
 
     def timings(self):
         t = Timings()

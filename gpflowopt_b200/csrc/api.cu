@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include "gpfo_internal.cuh"
+#include "ndtr_fast.cuh"
 
 #define FB 64
 #define GPFO_STAGE_BYTES (4 * 65536)          // pinned staging: four 64 KB areas (candidates, values, gradients, best record)
@@ -54,7 +55,8 @@ struct gpfo_ctx {
     // cells
     CellsDev cells;
     double* dpf = nullptr;
-    int32_t *dlb = nullptr, *dub = nullptr;
+    int32_t *dlb = nullptr, *dub = nullptr, *dcoff = nullptr;
+    double* dcbnd = nullptr;
     bool cells_set = false;
     // scratch
     double* dXc = nullptr; size_t cap_xc = 0;
@@ -170,7 +172,7 @@ int gpfo_ctx_destroy(gpfo_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < GPFO_MAX_GPS; ++i) free_gp(ctx->gps[i]);
-    cudaFree(ctx->dprog); cudaFree(ctx->dpf); cudaFree(ctx->dlb); cudaFree(ctx->dub);
+    cudaFree(ctx->dprog); cudaFree(ctx->dpf); cudaFree(ctx->dlb); cudaFree(ctx->dub); cudaFree(ctx->dcoff); cudaFree(ctx->dcbnd);
     cudaFree(ctx->dXc); cudaFree(ctx->dvalues); cudaFree(ctx->dmom_mean); cudaFree(ctx->dmom_var);
     cudaFree(ctx->dcmu); cudaFree(ctx->dcva); cudaFree(ctx->dgrads); cudaFree(ctx->dkx_scratch); cudaFree(ctx->dgen);
     cudaFree(ctx->dpartials); cudaFree(ctx->da_scratch);
@@ -182,15 +184,44 @@ int gpfo_ctx_destroy(gpfo_ctx* ctx) {
     return GPFO_OK;
 }
 
-static int effective_variant(const gpfo_ctx* ctx, int64_t N) {
+// Relative cost of one large-batch pass over Mp training points with a given forward kernel: block-steps the kernel issues
+// (its last, ragged chunk is padded to whole quads of row blocks per warp in v5) over its measured DMMA efficiency on full
+// chunks (profiles/r02_v5_sweep_2_static_triangles.log: v20 77-82 %, v21 65-70 %, v12 51-75 %).
+static double large_batch_cost(int variant, int Mp) {
+    const int nrb = Mp / 8;
+    if (variant == 12) return (double)nrb * (nrb + 1) / 2 / (Mp >= 1536 ? 0.74 : (Mp >= 768 ? 0.65 : 0.51));
+    const int rbc = variant == 20 ? 128 : 64, rbw = rbc / 16;
+    double steps = 0.0;
+    for (int row0 = 0; row0 < nrb; row0 += rbc) {
+        const int nr = nrb - row0 < rbc ? nrb - row0 : rbc;
+        if (nr == rbc) steps += (double)nr * row0 + (double)nr * (nr + 1) / 2;
+        else {                                      // ragged chunk: every warp runs whole quads of row blocks, predicated
+            const int rq = rbw >= 4 ? 4 : rbw;
+            const int rows_per_warp = ((nr + 15) / 16 + rq - 1) / rq * rq;
+            steps += (double)rows_per_warp * 16 * (row0 + nr);
+        }
+    }
+    return steps / (variant == 20 ? (Mp >= 1536 ? 0.78 : 0.64) : (Mp >= 768 ? 0.67 : 0.50));
+}
+
+static int effective_variant(const gpfo_ctx* ctx, int64_t N, int Mp) {
     if (ctx->variant >= 1) return ctx->variant;
-    // automatic: 64-candidate tiles with the K(X*,X) tile parked in a per-CTA global scratch (variant 12) for large
-    // batches; `strict_onchip` (gpfo_set_variant(ctx, 4) or GPFO_STRICT_ONCHIP=1) keeps the covariance strictly on chip
-    // at ~13% lower throughput.  Below four waves of 64-candidate tiles wave quantisation decides: cost = waves of tiles x
+    // automatic.  Large batches (>= four waves of 64-candidate tiles): the resident-panel kernels (v5: variant 20 = 16
+    // candidates x 1024-row chunks, 21 = 32 x 512; K(X*,X) never leaves the SM) unless the training-set size leaves a mostly
+    // empty last chunk, where the 64-candidate tiles with the K(X*,X) scratch (variant 12) do less padded work;
+    // GPFO_STRICT_ONCHIP=1 rules the scratch out altogether.  Below that wave quantisation decides: cost = waves of tiles x
     // measured time of one wave relative to the others (M = 2048: 0.29 / 0.50 / 0.77 (0.85 on chip) / 1.46 ms for
     // T = 8 / 16 / 32 / 64); ties go to the wider tile.
     static const bool strict = getenv("GPFO_STRICT_ONCHIP") && atoi(getenv("GPFO_STRICT_ONCHIP")) != 0;
-    if (!strict && N >= (int64_t)64 * 4 * ctx->num_sms) return 12;
+    if (N >= (int64_t)64 * 4 * ctx->num_sms) {
+        int best = strict ? 20 : 12;
+        double best_cost = large_batch_cost(best, Mp);
+        for (int v : {20, 21}) {
+            const double c = large_batch_cost(v, Mp);
+            if (c < best_cost) { best = v; best_cost = c; }
+        }
+        return best;
+    }
     const int var[4] = {6, 5, strict ? 4 : 11, 12};
     const int tile[4] = {8, 16, 32, 64};
     const double wave_cost[4] = {0.29, 0.50, strict ? 0.85 : 0.77, 1.46};
@@ -507,18 +538,34 @@ int gpfo_cells_set(gpfo_ctx* ctx, const double* pf_ext, int n_ext_rows, int R, c
     for (int64_t i = 0; i < C * R; ++i)
         if (lb[i] < 0 || lb[i] >= n_ext_rows || ub[i] < 0 || ub[i] >= n_ext_rows)
             return fail(ctx, GPFO_ERR_BAD_SHAPE, "cell index outside pf_ext");
-    cudaFree(ctx->dpf); cudaFree(ctx->dlb); cudaFree(ctx->dub);
-    ctx->dpf = nullptr; ctx->dlb = ctx->dub = nullptr; ctx->cells_set = false;
+    cudaFree(ctx->dpf); cudaFree(ctx->dlb); cudaFree(ctx->dub); cudaFree(ctx->dcoff); cudaFree(ctx->dcbnd);
+    ctx->dpf = nullptr; ctx->dlb = ctx->dub = ctx->dcoff = nullptr; ctx->dcbnd = nullptr; ctx->cells_set = false;
     CK(cudaMalloc((void**)&ctx->dpf, (size_t)n_ext_rows * R * sizeof(double)));
     CK(cudaMalloc((void**)&ctx->dlb, (size_t)(C > 0 ? C : 1) * R * sizeof(int32_t)));
     CK(cudaMalloc((void**)&ctx->dub, (size_t)(C > 0 ? C : 1) * R * sizeof(int32_t)));
     CK(cudaMemcpy(ctx->dpf, pf_ext, (size_t)n_ext_rows * R * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMalloc((void**)&ctx->dcoff, (size_t)(C > 0 ? C : 1) * R * 2 * sizeof(int32_t)));
+    CK(cudaMalloc((void**)&ctx->dcbnd, (size_t)(C > 0 ? C : 1) * R * 2 * sizeof(double)));
     if (C > 0) {
         CK(cudaMemcpy(ctx->dlb, lb, (size_t)C * R * sizeof(int32_t), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(ctx->dub, ub, (size_t)C * R * sizeof(int32_t), cudaMemcpyHostToDevice));
+        // per-cell records of the candidate-per-lane kernel: Phi-table entries and bound values, upper first
+        std::vector<int32_t> off((size_t)C * R * 2);
+        std::vector<double> bnd((size_t)C * R * 2);
+        for (int64_t c = 0; c < C; ++c)
+            for (int j = 0; j < R; ++j) {
+                const int iu = ub[c * R + j], il = lb[c * R + j];
+                off[(c * R + j) * 2] = iu * R + j;
+                off[(c * R + j) * 2 + 1] = il * R + j;
+                bnd[(c * R + j) * 2] = pf_ext[(size_t)iu * R + j];
+                bnd[(c * R + j) * 2 + 1] = pf_ext[(size_t)il * R + j];
+            }
+        CK(cudaMemcpy(ctx->dcoff, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->dcbnd, bnd.data(), bnd.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
     ctx->cells.n_ext = n_ext_rows; ctx->cells.R = R; ctx->cells.C = C;
     ctx->cells.pf_ext = ctx->dpf; ctx->cells.lb = ctx->dlb; ctx->cells.ub = ctx->dub;
+    ctx->cells.off = ctx->dcoff; ctx->cells.bnd = ctx->dcbnd;
     ctx->cells_set = true;
     return GPFO_OK;
 }
@@ -611,7 +658,7 @@ static int launch_stored_a(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
     const int64_t nslabs = (ntiles + slab_tiles - 1) / slab_tiles;
     const int sgrid = (int)(slab_tiles < ctx->num_sms ? slab_tiles : ctx->num_sms);
     const int64_t slab_n = slab_tiles * Tt;
-    const int ppg = hv ? gpfo_hvpoi_grid(slab_n, ctx->num_sms) : gpfo_program_grad_grid(slab_n, ctx->num_sms);
+    const int ppg = hv ? gpfo_hvpoi_grid(slab_n, ctx->num_sms, ctx->cells.n_ext, ctx->cells.R, 1) : gpfo_program_grad_grid(slab_n, ctx->num_sms);
     rc = ensure_parts(ctx, (int)(nslabs * ppg));
     if (rc != GPFO_OK) return rc;
     io.part_val = ctx->dpart_val; io.part_idx = ctx->dpart_idx;
@@ -653,7 +700,7 @@ static int launch_stored_a(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
         if (hv) {
             EvalIO hio = sio;
             hio.run_program = 1;
-            parts_k = gpfo_hvpoi_grid(ns, ctx->num_sms);
+            parts_k = gpfo_hvpoi_grid(ns, ctx->num_sms, ctx->cells.n_ext, ctx->cells.R, 1);
             CK(gpfo_hvpoi_launch(st, ctx->dprog, ctx->cells, hio, parts_k, slot_first, 1));
         } else {
             parts_k = gpfo_program_grad_grid(ns, ctx->num_sms);
@@ -705,7 +752,7 @@ static int launch_standard(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
             }
             gio.kx_scratch_stride = (long long)stride;
         }
-        if (variant == 20 || variant == 21) {   // v5 reads its block stream and layout from the launch record
+        if (variant >= 20 && variant <= 26) {   // v5 reads its block stream and layout from the launch record
             gio.packed_o = ctx->gps[g].hdev.packed; gio.geom_o = ctx->gps[g].hdev.geom;
         }
         CK(cudaEventRecord(ctx->ev[6], st));
@@ -795,7 +842,9 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     if (rc != GPFO_OK) return rc;
     const bool host_in = !generate && (dX != Xcand);
 
-    int variant = effective_variant(ctx, N);
+    int mp_max = 0;
+    for (int g = 0; g < ctx->ngps; ++g) mp_max = std::max(mp_max, ctx->gps[g].Mp);
+    int variant = effective_variant(ctx, N, mp_max);
     if (generate && variant == 10) variant = 12;
     if ((variant == 20 || variant == 21) && (want_grad || D > gpfo_contract5_max_dim(variant)))
         variant = 12;     // the gradient pass parks A in the 64-candidate tile layout; very wide inputs exceed v5's shared memory
@@ -850,7 +899,7 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
 #else
     const int grid = gpfo_contract_grid(variant, N, ctx->num_sms);
 #endif
-    const int hv_grid = gpfo_hvpoi_grid(N, ctx->num_sms);
+    const int hv_grid = hv ? gpfo_hvpoi_grid(N, ctx->num_sms, ctx->cells.n_ext, ctx->cells.R, want_grad ? 1 : 0) : 1;
     const int pg_grid = gpfo_program_grad_grid(N, ctx->num_sms);
     int max_parts = grid > hv_grid ? grid : hv_grid;
     if (pg_grid > max_parts) max_parts = pg_grid;
@@ -912,6 +961,7 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     if (ctx->ngps == 1) { cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); hot_ms = ms; }
     ctx->tm.hot_kernel_ms = hot_ms;
     ctx->tm.launches = launches;
+    ctx->tm.variant = variant;
     return GPFO_OK;
 }
 
@@ -965,7 +1015,7 @@ int gpfo_predict(gpfo_ctx* ctx, int gp_id, const double* X, int64_t N, int D, do
     const double* dX = nullptr;
     int rc = stage_candidates(ctx, X, N, D, &dX);
     if (rc != GPFO_OK) return rc;
-    int variant = effective_variant(ctx, N);
+    int variant = effective_variant(ctx, N, g.Mp);
     if ((variant == 20 || variant == 21) && D > gpfo_contract5_max_dim(variant)) variant = 12;
     if (variant == 10 || variant == 11 || variant == 12 || variant == 13 || variant == 14) variant = (N >= (int64_t)32 * ctx->num_sms) ? 4 : ((N >= (int64_t)16 * ctx->num_sms) ? 5 : 6);
     const int rbc = gpfo_contract_rbc(variant);
@@ -980,7 +1030,7 @@ int gpfo_predict(gpfo_ctx* ctx, int gp_id, const double* X, int64_t N, int D, do
     io.X = dX; io.N = N; io.mstride = N; io.mom_mean = ctx->dmom_mean; io.mom_var = ctx->dmom_var;
     io.part_val = ctx->dpart_val; io.part_idx = ctx->dpart_idx;
     io.write_moments = 1; io.run_program = 0;
-    if (variant == 20 || variant == 21) { io.packed_o = g.hdev.packed; io.geom_o = g.hdev.geom; }
+    if (variant >= 20 && variant <= 26) { io.packed_o = g.hdev.packed; io.geom_o = g.hdev.geom; }
     const int ns = split_count(ctx, N, gpfo_split_tile(), g.geom_s.nchunks);
     if (ns > 1) {
         rc = ensure_partials(ctx);
@@ -1011,7 +1061,7 @@ int gpfo_timings_get(const gpfo_ctx* ctx, gpfo_timings* out) {
 int gpfo_set_variant(gpfo_ctx* ctx, int variant) {
     if (!ctx) return GPFO_ERR_STATE;
 #ifdef GPFO_BUILD_EXPERIMENTS
-    static const int known[] = {0, 4, 5, 6, 10, 11, 12, 13, 14, 20, 21, 41, 42, 43, 121, 122, 123, 125, 127};
+    static const int known[] = {0, 4, 5, 6, 10, 11, 12, 13, 14, 20, 21, 22, 23, 24, 25, 26, 41, 42, 43, 121, 122, 123, 125, 127};
 #else
     static const int known[] = {0, 4, 5, 6, 11, 12, 20, 21};
 #endif
@@ -1028,6 +1078,14 @@ int gpfo_measure_dmma_peak(gpfo_ctx* ctx, double* tflops) {
     const double v = gpfo_dmma_peak(ctx->stream, ctx->num_sms);
     if (v < 0.0) return fail(ctx, GPFO_ERR_CUDA, "DMMA peak kernel failed");
     *tflops = v;
+    return GPFO_OK;
+}
+
+int gpfo_ndtr_fast_host(const double* z, int64_t n, double* out) {
+    if (!z || !out || n < 0) return GPFO_ERR_BAD_SHAPE;
+    double tab32[32];
+    for (int i = 0; i < 32; ++i) tab32[i] = exp2(i * (1.0 / 32.0));
+    for (int64_t i = 0; i < n; ++i) out[i] = gpfo_ndtr_fast(z[i], tab32);
     return GPFO_OK;
 }
 

@@ -58,6 +58,8 @@ __device__ __forceinline__ double2 lds128(unsigned addr) {                      
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
     return v;
 }
+template <int ABL>
+__device__ __forceinline__ void cp5(unsigned smem_dst, const void* gmem_src) { if (!(ABL & 2)) cp_async16(smem_dst, gmem_src); }
 __device__ __forceinline__ void mbar_wait_par(unsigned bar_s, unsigned parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -66,7 +68,9 @@ __device__ __forceinline__ void mbar_wait_par(unsigned bar_s, unsigned parity) {
         "@!p bra WAIT5_%=;\n\t}" ::"r"(bar_s), "r"(parity) : "memory");
 }
 
-template <int RBW, int NB, int QD, int KIND>
+// ABL (profiling builds only, GPFO_BUILD_EXPERIMENTS): bit 0 = K(X*,X) elements are constants (no generation arithmetic),
+// bit 1 = no L^-1 copies (the ring is never filled), bit 2 = no mbarrier hand-off of the groups (wrong results; timing only)
+template <int RBW, int NB, int QD, int KIND, int ABL = 0>
 __global__ void __launch_bounds__(512, 1)
 contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ prog, EvalIO io, int nbuf) {
     using C = Contract5Cfg<RBW, NB, QD>;
@@ -176,7 +180,7 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                     const unsigned dst = myring_s + ring_off * 8;
 #pragma unroll
                     for (int i = 0; i < RQ; ++i)
-                        if (qd * RQ + i >= n_lo && qd * RQ + i < r_hi) cp_async16(dst + i * 512, src_next + (qd * RQ + i) * (NW * 64));
+                        if (qd * RQ + i >= n_lo && qd * RQ + i < r_hi) cp5<ABL>(dst + i * 512, src_next + (qd * RQ + i) * (NW * 64));
                 }
                 cp_async_commit();
             };
@@ -198,17 +202,23 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                     jj[q] = j < M ? j : M - 1;            // clamp: keeps the loads in range, result masked below
                     dot[q] = 0.0;
                 }
-                for (int d = 0; d < D; ++d) {
-                    const double c = xc[d * T + gen_n];
+                if (!(ABL & 1)) {
+                    for (int d = 0; d < D; ++d) {
+                        const double c = xc[d * T + gen_n];
 #pragma unroll
-                    for (int q = 0; q < C::GEN_ITERS; ++q) dot[q] = fma(__ldg(Xs + (size_t)jj[q] * D + d), c, dot[q]);
+                        for (int q = 0; q < C::GEN_ITERS; ++q) dot[q] = fma(__ldg(Xs + (size_t)jj[q] * D + d), c, dot[q]);
+                    }
                 }
 #pragma unroll
                 for (int q = 0; q < C::GEN_ITERS; ++q) {
                     const int ksl = (w + NW * q) / NB;
                     const int j = (g * GK) * 8 + 4 * ksl + gen_jl;
-                    const double r2 = (-2.0 * dot[q] + __ldg(xn + jj[q])) + x2[gen_n];    // square_dist, expanded form
-                    const double val = kx_branchless<KIND>(variance, r2, tab32);
+                    double val;
+                    if (ABL & 1) val = 1e-3 * j;
+                    else {
+                        const double r2 = (-2.0 * dot[q] + __ldg(xn + jj[q])) + x2[gen_n];    // square_dist, expanded form
+                        val = kx_branchless<KIND>(variance, r2, tab32);
+                    }
                     dst[(ksl * NB + gen_nb) * 32 + lane] = j < M ? val : 0.0;
                 }
             };
@@ -218,7 +228,7 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_res + 8 * g);
                 } else {                                  // streaming ring: wait until every warp has released the buffer
-                    mbar_wait_par(bar_empty + 8 * gen_buf, (empty_ph >> gen_buf) & 1u);
+                    if (!(ABL & 4)) mbar_wait_par(bar_empty + 8 * gen_buf, (empty_ph >> gen_buf) & 1u);
                     empty_ph ^= 1u << gen_buf;
                     gen_elems(g, kstr + (size_t)gen_buf * GS);
                     __syncwarp();
@@ -271,8 +281,8 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
 #pragma unroll
                     for (int i = 0; i < RQ; ++i) {
                         const int r = qd * RQ + i;
-                        if (r > RLO) { if (NEXT_DENSE || has_next) cp_async16(slot + i * 512, src_next + r * (NW * 64)); }
-                        else if (r == RLO) { if (NEXT_DENSE || (has_next && keep_first)) cp_async16(slot + i * 512, src_next + r * (NW * 64)); }
+                        if (r > RLO) { if (NEXT_DENSE || has_next) cp5<ABL>(slot + i * 512, src_next + r * (NW * 64)); }
+                        else if (r == RLO) { if (NEXT_DENSE || (has_next && keep_first)) cp5<ABL>(slot + i * 512, src_next + r * (NW * 64)); }
                     }
                     cp_async_commit();
 #pragma unroll
@@ -315,6 +325,11 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 { const int t = kp_next - row0 - w + (NW - 1); n_lo = kp_next < kp_end ? (t > 0 ? t / NW : 0) : RBW; }
 #pragma unroll
                 for (int qd = 0; qd < QPC; ++qd) {
+                    if (qd * RQ >= r_hi || (qd + 1) * RQ <= r_lo) {       // no row block of this quad exists here (and none next)
+                        cp_async_commit();
+                        ring_step();
+                        continue;
+                    }
                     cp_async_wait<QD - 1>();
                     const unsigned slot = myring_s + ring_off * 8;
                     double2 a[RQ];
@@ -326,7 +341,7 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
 #pragma unroll
                     for (int i = 0; i < RQ; ++i)
                         if (qd * RQ + i >= n_lo && qd * RQ + i < r_hi)
-                            cp_async16(slot + i * 512, src_next + (qd * RQ + i) * (NW * 64));
+                            cp5<ABL>(slot + i * 512, src_next + (qd * RQ + i) * (NW * 64));
                     cp_async_commit();
 #pragma unroll
                     for (int h = 0; h < 2; ++h)
@@ -363,10 +378,10 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 // wait for group g
                 const double* kb;
                 if (g < RG) {
-                    if (p == 0) mbar_wait_par(bar_res + 8 * g, res_par);
+                    if (p == 0 && !(ABL & 4)) mbar_wait_par(bar_res + 8 * g, res_par);
                     kb = kres + (size_t)g * GS + lane;
                 } else {
-                    mbar_wait_par(bar_full + 8 * use_buf, (full_ph >> use_buf) & 1u);
+                    if (!(ABL & 4)) mbar_wait_par(bar_full + 8 * use_buf, (full_ph >> use_buf) & 1u);
                     full_ph ^= 1u << use_buf;
                     kb = kstr + (size_t)use_buf * GS + lane;
                 }
@@ -474,14 +489,14 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     }
 }
 
-template <int RBW, int NB, int QD, int KIND>
+template <int RBW, int NB, int QD, int KIND, int ABL = 0>
 static inline cudaError_t launch5_kind(cudaStream_t st, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io, int grid, int D) {
     using C = Contract5Cfg<RBW, NB, QD>;
     int nbuf = C::NBUF_MAX;
     while (nbuf >= 2 && C::smem_bytes(D, nbuf) > (size_t)227 * 1024) --nbuf;
     if (nbuf < 2) return cudaErrorInvalidConfiguration;
     const size_t smem = C::smem_bytes(D, nbuf);
-    auto kern = contract5_kernel<RBW, NB, QD, KIND>;
+    auto kern = contract5_kernel<RBW, NB, QD, KIND, ABL>;
     static size_t smem_set[16] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -494,11 +509,11 @@ static inline cudaError_t launch5_kind(cudaStream_t st, const GpDev* d_gp, const
     return cudaGetLastError();
 }
 
-template <int RBW, int NB, int QD>
+template <int RBW, int NB, int QD, int ABL = 0>
 static inline cudaError_t launch5(cudaStream_t st, int kind, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io, int grid, int D) {
     switch (kind) {
-        case GPFO_KERN_RBF: return launch5_kind<RBW, NB, QD, GPFO_KERN_RBF>(st, d_gp, d_prog, io, grid, D);
-        case GPFO_KERN_MATERN52: return launch5_kind<RBW, NB, QD, GPFO_KERN_MATERN52>(st, d_gp, d_prog, io, grid, D);
-        default: return launch5_kind<RBW, NB, QD, GPFO_KERN_MATERN32>(st, d_gp, d_prog, io, grid, D);
+        case GPFO_KERN_RBF: return launch5_kind<RBW, NB, QD, GPFO_KERN_RBF, ABL>(st, d_gp, d_prog, io, grid, D);
+        case GPFO_KERN_MATERN52: return launch5_kind<RBW, NB, QD, GPFO_KERN_MATERN52, ABL>(st, d_gp, d_prog, io, grid, D);
+        default: return launch5_kind<RBW, NB, QD, GPFO_KERN_MATERN32, ABL>(st, d_gp, d_prog, io, grid, D);
     }
 }

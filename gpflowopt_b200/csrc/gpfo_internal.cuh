@@ -375,8 +375,10 @@ struct CellsDev {
     const double* pf_ext;       // n_ext x R
     const int32_t* lb;          // C x R
     const int32_t* ub;
+    const int32_t* off;         // C x R x 2: Phi-table entries (row * R + objective) of the upper / lower bound   (hvpoi2_kernel)
+    const double* bnd;          // C x R x 2: pf_ext values of the upper / lower bound
 };
-int gpfo_hvpoi_grid(int64_t N, int num_sms);
+int gpfo_hvpoi_grid(int64_t N, int num_sms, int n_ext, int R, int with_grad);
 size_t gpfo_hvpoi_smem_bytes(int n_ext, int R);
 cudaError_t gpfo_hvpoi_launch(cudaStream_t st, const ProgramDev* d_prog, const CellsDev& cells, EvalIO io, int grid,
                               int slot_first, int with_grad);

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GPFO_VERSION 100
+#define GPFO_VERSION 200
 
 /* status codes */
 enum {
@@ -74,6 +74,7 @@ typedef struct gpfo_timings {
     double d2h_ms;         /* last gpfo_eval: result download */
     double hot_kernel_ms;  /* last gpfo_eval: sum over GPs of the DMMA contraction kernel alone */
     int64_t launches;      /* kernels launched by the last gpfo_eval */
+    int64_t variant;       /* forward contraction kernel the last gpfo_eval selected (table in csrc/contract.cu) */
 } gpfo_timings;
 
 /* ---- lifetime -------------------------------------------------------------------------------------- */
@@ -174,6 +175,11 @@ int gpfo_measure_dmma_peak(gpfo_ctx* ctx, double* tflops);
  * Returns GPFO_ERR_BAD_SHAPE with *count set when capacity is too small (call again with a larger buffer). */
 int gpfo_pareto_cells(const double* front, const int32_t* order, int P, int R, double threshold, int32_t* lb,
                       int32_t* ub, int64_t capacity, int64_t* count);
+
+/* Host evaluation of the branch-free Normal CDF the HVPoI Phi table uses on the device (csrc/ndtr_fast.cuh; replaces
+   tf.contrib.distributions.Normal.cdf at hvpoi.py:112-113).  Same source compiled for the host: lets the CPU tests pin its
+   accuracy against scipy.special.ndtr without a GPU.  Needs no ctx. */
+int gpfo_ndtr_fast_host(const double* z, int64_t n, double* out);
 
 /* FP64 pipe microbenchmarks (register-only loops, 16 warps/SM): mode 0 = DMMA only, 1 = DFMA only,
    2 = half of the warps of every scheduler DMMA and half DFMA concurrently.  TFLOP/s of each instruction class. */

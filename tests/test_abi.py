@@ -25,7 +25,7 @@ def test_header_symbols_are_exported(libgpfo):
 
 
 def test_version_and_status_strings(libgpfo):
-    assert libgpfo.gpfo_version() == 100
+    assert libgpfo.gpfo_version() == 200
     assert libgpfo.gpfo_status_string(0) == b"ok"
     assert b"positive definite" in libgpfo.gpfo_status_string(1)
     assert libgpfo.gpfo_status_string(99) == b"unknown status"
@@ -73,3 +73,24 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
                 assert "oracle." not in src and "oracle/" not in src, os.path.join(dirpath, f)
+
+
+def test_fast_normal_cdf_of_the_hvpoi_kernel(libgpfo):
+    """csrc/ndtr_fast.cuh (same source on host and device) against scipy.special.ndtr -- itself the float64 erf/erfc forms TF's
+    ndtr uses -- and against 50-digit mpmath in the tails: relative error of a few ulp wherever the value
+    is a normal number, exact limits at +-inf."""
+    import mpmath as mp
+    from scipy.special import ndtr
+    from gpflowopt_b200 import _lib
+    z = np.concatenate((np.linspace(-37.0, 9.0, 200001), np.random.RandomState(0).randn(50000) * 3.0, [0.0, -0.0, 1e-300, -1e-300]))
+    got = _lib.ndtr_fast_host(z)
+    ref = ndtr(z)
+    rel = np.abs(got - ref) / ref
+    assert np.max(rel[z > -30]) < 1e-13, np.max(rel[z > -30])          # |z| <= 30: Phi down to 5e-198
+    assert np.max(np.abs(got - ref)) < 5e-16                            # absolute: what the cell sums see
+    assert np.all(np.diff(got[:200001]) >= 0.0)                         # monotone on the grid
+    np.testing.assert_array_equal(_lib.ndtr_fast_host([np.inf, -np.inf]), [1.0, 0.0])
+    mp.mp.dps = 40
+    for zz in (-35.0, -20.0, -8.3, -1.0, -0.3, 0.3, 1.0, 5.0):
+        true = float(mp.ncdf(mp.mpf(zz)))
+        assert abs(_lib.ndtr_fast_host([zz])[0] - true) <= 2e-14 * true + 3e-17

@@ -310,8 +310,11 @@ def test_headline_shape_subset_and_properties(ctx):
     Xs = synthetic.candidates(3000, 8, seed=8)
     mean, var = ctx.predict(0, Xs, 1)
     mo, vo = g2.predict(Xs)
-    assert_parity(mean, mo, tol=1e-8, what="mean, cond 4e7")      # documented: conditioning-limited (both sides)
-    assert_parity(var, vo, scale=g2.variance, tol=1e-8, what="var, cond 4e7")
+    from helpers import scale_rel_err
+    e_mean, e_var = scale_rel_err(mean, mo), scale_rel_err(var, vo, g2.variance)
+    print("cond-4e7 stress (RBF, M=1024, noise 1e-6): scale-relative error mean %.3e, variance %.3e" % (e_mean, e_var))
+    # measured on B200 ("stress conditioning"): the bar stays 1e-9
+    assert e_mean <= RTOL and e_var <= RTOL, (e_mean, e_var)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -700,9 +703,9 @@ def test_config3_full_size_constrained_ei(ctx):
 def test_config4_full_size_hvpoi(ctx):
     """configs[3]: HVPoI, 3 objectives, M = 1024 per GP, 1e6 candidates, Pareto front of ~200 points."""
     from gpflowopt_b200 import pareto as gpareto
-    M, D, R, N = 1024, 4, 3, 1000000
+    M, D, R, N = 1024, 6, 3, 1000000                       # D = 6 as SURVEY 8(d) states
     X = synthetic.candidates(M, D, seed=5)
-    F = synthetic.dtlz2_objectives(X, R)
+    F = synthetic.dtlz2_objectives(X, R, g_scale=0.4)
     h = synthetic.hypers(D, 1e-3)
     gps = [oracle_gp(X, F[:, [j]], ogp.MATERN52, h) for j in range(R)]
     for j, g in enumerate(gps):
@@ -727,3 +730,76 @@ def test_config4_full_size_hvpoi(ctx):
         assert_parity(part, vals[123456:123456 + 40000], tol=1e-11, what="config 4 slice vs whole")
     finally:
         ctx.gp_count_set(1)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE configs[0] as stated and configs[4] as a test grid
+# ------------------------------------------------------------------------------------------------------------------
+def test_config1_branin_mc1000_as_stated(ctx):
+    """configs[0]: ExpectedImprovement on 2-D Branin ([-5, 10] x [0, 15]), GPR RBF-ARD with 20 training points, seeded
+    MCOptimizer(domain, 1000) (gpflowopt/optim.py:152-164).  Same np.random stream on both sides: the selected ROW must be the
+    one oracle.acq.mc_optimize picks (first-occurrence argmin of -EI) and `fun` must agree to 1e-9."""
+    import gpflowopt_b200 as gpfo
+    from gpflowopt_b200.acquisition import ExpectedImprovement
+    from gpflowopt_b200.bo import _InverseAcquisition
+    from gpflowopt_b200.design import RandomDesign
+    from gpflowopt_b200.domain import ContinuousParameter
+    from gpflowopt_b200.optim import MCOptimizer
+
+    def branin(x):
+        x1, x2 = x[:, 0], x[:, 1]
+        a, b, c, r, s, t = 1, 5.1 / (4 * np.pi ** 2), 5 / np.pi, 6, 10, 1 / (8 * np.pi)
+        return (a * (x2 - b * x1 ** 2 + c * x1 - r) ** 2 + s * (1 - t) * np.cos(x1) + s)[:, None]
+
+    domain = ContinuousParameter('x1', -5, 10) + ContinuousParameter('x2', 0, 15)
+    rs = np.random.RandomState(7)
+    X = domain.lower + rs.rand(20, 2) * (domain.upper - domain.lower)
+    Y = branin(X)
+    hyp = dict(lengthscales=np.array([0.3, 0.4]), variance=1.0, noise_variance=1e-3)
+    for scaled in (True, False):                    # BayesianOptimizer's default (domain -> unit cube, normalised Y) and raw
+        ell = hyp["lengthscales"] if scaled else hyp["lengthscales"] * (domain.upper - domain.lower)
+        var = hyp["variance"] if scaled else float(np.var(Y))
+        model = gpfo.GPR(X, Y, gpfo.RBF(2, variance=var, lengthscales=ell, ARD=True), noise_variance=hyp["noise_variance"])
+        acq = ExpectedImprovement(model)
+        acq.optimize_restarts = 0
+        if scaled:
+            acq.enable_scaling(domain)
+        g = oracle_gp(X, Y, ogp.RBF, dict(lengthscales=ell, variance=var, noise_variance=hyp["noise_variance"]),
+                      lower=domain.lower if scaled else None, upper=domain.upper if scaled else None, normalize=scaled)
+        node = oacq.Leaf('ei', g, oacq.fmin_of(g, X))
+        np.random.seed(11)
+        res = MCOptimizer(domain, 1000).optimize(_InverseAcquisition(acq, False))
+        np.random.seed(11)
+        points = RandomDesign(1000, domain).generate()                # the stream MCOptimizer consumed
+        x_ref, f_ref, idx_ref, evals = oacq.mc_optimize(node, points)
+        assert res.success and res.nfev == 1000 and res.x.shape == (1, 2) and res.fun.shape == (1, 1)
+        assert np.array_equal(res.x, x_ref), "selected row differs from the oracle's (scaled=%s)" % scaled
+        assert abs(res.fun[0, 0] - f_ref[0, 0]) <= RTOL * np.max(np.abs(evals))
+        assert_parity(acq.evaluate(points), -evals, what="config 1 scores, scaled=%s" % scaled)
+        acq._get_engine().close()
+
+
+@pytest.mark.parametrize("M", [512, 1024, 2048, 4096, 8192])
+def test_config5_sweep_values_and_gradients(ctx, M):
+    """configs[4] at reduced N: every M of the sweep, values and evaluate_with_gradients, through the batch sizes that select
+    the large-batch kernels (resident-panel forward, stored-A gradient pass), against an oracle subset."""
+    D = 8
+    g, lo, up = _model(M, D, "matern52")
+    upload_oracle_gp(ctx, 0, g)
+    fmin = -1.5
+    ctx.program_set([[_lib.OP_EI, 0, 0, 0]], [fmin])
+    node = oacq.Leaf('ei', g, fmin)
+    N = 40000 if M <= 4096 else 38000                       # >= 256 candidates per SM: the automatic large-batch path
+    Xc = _cands(N, D, lo, up, seed=M)
+    vals, _, bv, bi = ctx.eval(Xc)
+    nsub = 600 if M <= 2048 else 150
+    sub = np.random.RandomState(M).choice(N, nsub, replace=False)
+    sub[0] = bi
+    ref = node.value(Xc[sub])
+    assert_parity(vals[sub], ref, what="values M=%d" % M)
+    assert bi == int(np.argmax(vals)) and bv == vals[bi, 0]
+    vg, grads, _, big = ctx.eval(Xc, want_grads=True)
+    assert big == bi
+    assert_parity(vg[sub], ref, what="values of the gradient call M=%d" % M)
+    _, rg = node.value_and_grad(Xc[sub[:100]])
+    assert_parity(grads[sub[:100]], rg, what="gradients M=%d" % M)
