@@ -4,8 +4,15 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <nvtx3/nvToolsExt.h>
 #include "gpfo_internal.cuh"
 #include "ndtr_fast.cuh"
+
+// NVTX ranges around the phases of a call (upload / factor / eval / argmax / download): visible in Nsight Systems timelines
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 #define FB 64
 #define GPFO_STAGE_BYTES (4 * 65536)          // pinned staging: four 64 KB areas (candidates, values, gradients, best record)
@@ -76,6 +83,7 @@ struct gpfo_ctx {
     char* hstage = nullptr;
     int* dflag = nullptr;
     cudaEvent_t ev[8];
+    cudaEvent_t gp_ev[GPFO_MAX_GPS][2];        // per-GP event pair around the contraction launch (read after the final sync)
     gpfo_timings tm;
     int variant = 0;
 };
@@ -146,6 +154,7 @@ int gpfo_ctx_create(int device, gpfo_ctx** out) {
     memset(&ctx->cells, 0, sizeof(ctx->cells));
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    for (int i = 0; i < 2 * GPFO_MAX_GPS && ok; ++i) ok = cudaEventCreate(&ctx->gp_ev[i / 2][i % 2]) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&ctx->dprog, sizeof(ProgramDev)) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&ctx->dbest_val, 16) == cudaSuccess;
     if (ok) ctx->dbest_idx = reinterpret_cast<long long*>(ctx->dbest_val + 1);
@@ -179,6 +188,7 @@ int gpfo_ctx_destroy(gpfo_ctx* ctx) {
     cudaFree(ctx->dpart_val); cudaFree(ctx->dpart_idx); cudaFree(ctx->dbest_val); cudaFreeHost(ctx->hstage);
     cudaFree(ctx->dflag);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 2 * GPFO_MAX_GPS; ++i) cudaEventDestroy(ctx->gp_ev[i / 2][i % 2]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return GPFO_OK;
@@ -421,6 +431,7 @@ int gpfo_gp_set(gpfo_ctx* ctx, int gp_id, int64_t M64, int D, int R, const doubl
         if (g.hdev.out_scale[r] == 0.0) return fail(ctx, GPFO_ERR_BAD_SHAPE, "out_scale must be non-zero");
     }
     cudaStream_t st = ctx->stream;
+    NvtxRange nvtx_factor("gpfo:factor");
     CK(cudaEventRecord(ctx->ev[0], st));
     CK(cudaMemsetAsync(g.dX, 0, (size_t)Mf * D * sizeof(double), st));
     CK(cudaMemsetAsync(g.dY, 0, (size_t)Mf * R * sizeof(double), st));
@@ -573,6 +584,7 @@ int gpfo_cells_set(gpfo_ctx* ctx, const double* pf_ext, int n_ext_rows, int R, c
 // Stages candidates on the device (if needed) and makes sure scratch buffers are large enough.
 static int stage_candidates(gpfo_ctx* ctx, const double* X, int64_t N, int D, const double** dX) {
     if (is_device_ptr(X)) { *dX = X; ctx->tm.h2d_ms = 0.0; return GPFO_OK; }
+    NvtxRange nvtx_upload("gpfo:upload");
     CK(ensure(&ctx->dXc, &ctx->cap_xc, (size_t)N * D));
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     const size_t bytes = (size_t)N * D * sizeof(double);
@@ -691,9 +703,9 @@ static int launch_stored_a(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
             gio.a_scratch = ctx->da_scratch + a_off;
             gio.a_stride = gpfo_contract_astore_stride(gh.Mp / 8);
             a_off += (size_t)slab_tiles * (size_t)gio.a_stride;
-            if (k == 0 && g == 0) CK(cudaEventRecord(ctx->ev[6], st));
+            if (k == 0) CK(cudaEventRecord(ctx->gp_ev[g][0], st));
             CK(gpfo_contract_astore_launch(st, gh.kind, gh.ddev, ctx->dprog, gio, g_s, D));
-            if (k == 0 && g == 0) CK(cudaEventRecord(ctx->ev[7], st));
+            if (k == 0) CK(cudaEventRecord(ctx->gp_ev[g][1], st));
             ++launches;
         }
         int parts_k;
@@ -721,7 +733,6 @@ static int launch_stored_a(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
             ++launches;
         }
     }
-    if (ctx->ngps > 1) { CK(cudaEventSynchronize(ctx->ev[7])); float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); hot_ms = ms; }
     *launches_out = launches; *nparts_out = nparts; *hot_ms_out = hot_ms;
     return GPFO_OK;
 }
@@ -755,7 +766,7 @@ static int launch_standard(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
         if (variant >= 20 && variant <= 26) {   // v5 reads its block stream and layout from the launch record
             gio.packed_o = ctx->gps[g].hdev.packed; gio.geom_o = ctx->gps[g].hdev.geom;
         }
-        CK(cudaEventRecord(ctx->ev[6], st));
+        CK(cudaEventRecord(ctx->gp_ev[g][0], st));
         const int ns = generate ? 1 : split_count(ctx, N, gpfo_split_tile(), ctx->gps[g].geom_s.nchunks);
         if (ns > 1) {
             gio.packed_o = ctx->gps[g].dpacked_s; gio.geom_o = ctx->gps[g].geom_s;
@@ -771,12 +782,8 @@ static int launch_standard(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
             CK(gpfo_contract_launch(st, variant, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
             fwd_parts = grid;
         }
-        CK(cudaEventRecord(ctx->ev[7], st));
+        CK(cudaEventRecord(ctx->gp_ev[g][1], st));         // one event pair per GP: nothing waits on the host between launches
         ++launches;
-        if (ctx->ngps > 1) {                 // per-GP timing needs a sync only when events are reused
-            CK(cudaEventSynchronize(ctx->ev[7]));
-            float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); hot_ms += ms;
-        }
     }
     nparts = fwd_parts;
     if (hv) {
@@ -926,13 +933,20 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     pl.N = N; pl.D = D; pl.variant = variant; pl.grid = grid; pl.hv_grid = hv_grid; pl.pg_grid = pg_grid;
     pl.slot_first = slot_first; pl.use_cluster = use_cluster; pl.hv = hv; pl.want_grad = want_grad;
     pl.need_mom = need_mom; pl.generate = generate;
-    rc = astore ? launch_stored_a(ctx, pl, io, &launches, &nparts, &hot_ms)
-                : launch_standard(ctx, pl, io, &launches, &nparts, &hot_ms);
-    if (rc != GPFO_OK) return rc;
-    gpfo_argmax_final(st, ctx->dpart_val, ctx->dpart_idx, nparts, ctx->dbest_val, ctx->dbest_idx);
-    CK(cudaGetLastError());
+    {
+        NvtxRange nvtx_eval("gpfo:eval");
+        rc = astore ? launch_stored_a(ctx, pl, io, &launches, &nparts, &hot_ms)
+                    : launch_standard(ctx, pl, io, &launches, &nparts, &hot_ms);
+        if (rc != GPFO_OK) return rc;
+    }
+    {
+        NvtxRange nvtx_argmax("gpfo:argmax");
+        gpfo_argmax_final(st, ctx->dpart_val, ctx->dpart_idx, nparts, ctx->dbest_val, ctx->dbest_idx);
+        CK(cudaGetLastError());
+    }
     ++launches;
     CK(cudaEventRecord(ctx->ev[5], st));
+    NvtxRange nvtx_download("gpfo:download");
     // results
     const size_t vbytes = (size_t)N * sizeof(double), gbytes = (size_t)N * D * sizeof(double);
     char* const hv_stage = ctx->hstage + GPFO_STAGE_AREA, *const hg_stage = ctx->hstage + 2 * GPFO_STAGE_AREA;
@@ -958,7 +972,8 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     if (host_in) { cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->tm.h2d_ms = ms; }
     cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->tm.eval_ms = ms;
     cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[1]); ctx->tm.d2h_ms = ms;
-    if (ctx->ngps == 1) { cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); hot_ms = ms; }
+    hot_ms = 0.f;
+    for (int g = 0; g < ctx->ngps; ++g) { cudaEventElapsedTime(&ms, ctx->gp_ev[g][0], ctx->gp_ev[g][1]); hot_ms += ms; }
     ctx->tm.hot_kernel_ms = hot_ms;
     ctx->tm.launches = launches;
     ctx->tm.variant = variant;
