@@ -11,6 +11,14 @@ cudaError_t gpfo_contract5_launch(cudaStream_t st, int variant, int kind, const 
     if (variant == 24) return launch5<8, 2, 2, 3>(st, kind, d_gp, d_prog, io, grid, D);
     if (variant == 25) return launch5<8, 2, 2, 4>(st, kind, d_gp, d_prog, io, grid, D);
     if (variant == 26) return launch5<8, 2, 2, 7>(st, kind, d_gp, d_prog, io, grid, D);
+    if (variant == 27) return launch5<8, 2, 2, 8>(st, kind, d_gp, d_prog, io, grid, D);      // 27 / 28: phase cycle counters of 20 / 21
+    if (variant == 28) return launch5<4, 4, 2, 8>(st, kind, d_gp, d_prog, io, grid, D);
+    if (variant == 30) return launch5<8, 2, 2, 16>(st, kind, d_gp, d_prog, io, grid, D);     // scheduling experiments: every warp
+    if (variant == 31) return launch5<4, 4, 2, 16>(st, kind, d_gp, d_prog, io, grid, D);     // generates first (30 / 31), one group
+    if (variant == 32) return launch5<8, 2, 2, 32>(st, kind, d_gp, d_prog, io, grid, D);     // of lookahead (32 / 33), every warp
+    if (variant == 33) return launch5<4, 4, 2, 32>(st, kind, d_gp, d_prog, io, grid, D);     // generates last (34 / 35)
+    if (variant == 34) return launch5<8, 2, 2, 64>(st, kind, d_gp, d_prog, io, grid, D);
+    if (variant == 35) return launch5<4, 4, 2, 64>(st, kind, d_gp, d_prog, io, grid, D);
 #endif
     return launch5<8, 2, 2>(st, kind, d_gp, d_prog, io, grid, D);
 }

@@ -17,6 +17,14 @@
 //     full[g] after writing its share of group g (generated two groups ahead of use) and waits on it right before the first
 //     B-fragment load; the streaming groups right of the panel cycle through a small ring with empty[] barriers.  Warps of a
 //     CTA may drift apart by a whole group instead of meeting at a __syncthreads every 8 column blocks.
+//   * Tile pipeline: a tile ends with the two barriers of its last chunk reduction and nothing else.  Between them idle
+//     threads stage the NEXT tile's (transformed, scaled) candidates into the other half of a double buffer; the epilogue of
+//     a tile (moments, acquisition program with its erf / exp, argmax) is run by warp 0 one tile LATER, after it has
+//     contributed its share of the first two covariance groups, while the other fifteen warps are already contracting.
+//   * K(X*,X) generation: the D-term dot products Xs . xc of a group are 8 x 8 tiles of DMMAs themselves (one tile per warp
+//     and group, ceil(D / 4) DMMAs instead of D DFMAs per element) -- on the shared FP64 pipe every generation instruction
+//     waits one arbitration round behind the other warps' 16-cycle DMMAs, so the instruction COUNT of the generation is what
+//     costs (phase counters: profiles/r02_phase5_*.log); the kernel variance is folded into the 64-entry 2^(i/64) table.
 //   * L^-1 blocks travel global -> shared with cp.async into a per-warp private ring of QD quads of row blocks (each lane
 //     copies and re-reads its own 16 bytes: no barrier); the slot just read is refilled for the column block one ahead.
 //     One 512-byte block feeds 2 NB DMMAs, so the stream is 4 x (T = 16) the L2 traffic of v2's T = 64 -- 7 TB/s at
@@ -43,9 +51,11 @@ struct Contract5Cfg {
     static_assert(NW % NB == 0 && GROUP_SLOTS % THREADS == 0, "generation loop must tile");
     static_assert(QD % QPC == 0 && KA >= 1, "ring depth must be whole column blocks");
     static_assert(RING_DOUBLES_PER_WARP >= T * (1 + RMAX), "the per-warp reduction slice lives in the drained ring");
+    static_assert(GK * NB == NW, "one 8 x 8 generation tile per warp and group");
+    static int dpad(int D) { return (D + 3) / 4 * 4; }     // input dimension rounded up to whole DMMA k-steps (zero padded)
     static size_t smem_bytes(int D, int nbuf) {
-        return ((size_t)NW * RING_DOUBLES_PER_WARP + (size_t)(RG + nbuf) * GROUP_SLOTS + (size_t)D * T + T + T * (1 + RMAX) + 2 +
-                34) * sizeof(double) + (size_t)(RG + 2 * NBUF_MAX) * 8;
+        return ((size_t)NW * RING_DOUBLES_PER_WARP + (size_t)(RG + nbuf) * GROUP_SLOTS + 2 * (size_t)dpad(D) * T +
+                2 * T * (1 + RMAX) + 2 + 66) * sizeof(double) + (size_t)(RG + 2 * NBUF_MAX) * 8;
     }
 };
 
@@ -60,6 +70,38 @@ __device__ __forceinline__ double2 lds128(unsigned addr) {                      
 }
 template <int ABL>
 __device__ __forceinline__ void cp5(unsigned smem_dst, const void* gmem_src) { if (!(ABL & 2)) cp_async16(smem_dst, gmem_src); }
+// variance * exp(x) for x <= 0 with the table tabv[i] = variance * 2^(i/64): k = round(64 x / ln 2), x = k ln2/64 + r,
+// |r| <= ln2/128, degree-5 Taylor (truncation 3.5e-17 relative).  10 FP64 instructions.
+__device__ __forceinline__ double exp_neg_tab64(double x, const double* __restrict__ tabv) {
+    x = fmax(x, -708.0);
+    const double magic = 6755399441055744.0;                 // 1.5 * 2^52
+    const double t = fma(x, 92.332482616893656, magic);      // 64 / ln 2
+    const double kf = t - magic;
+    double r = fma(kf, -1.0830424696249145e-02, x);          // ln2/64 (head)
+    r = fma(kf, -3.6235106526217448e-19, r);                 // ln2/64 (tail)
+    double p = 8.3333333333333332e-03;                       // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int k = __double2loint(t);
+    p *= tabv[k & 63];
+    return __hiloint2double(__double2hiint(p) + ((k >> 6) << 20), __double2loint(p));
+}
+// covariance from the squared distance, variance included through the table (forms of contract_common.cuh::kx_branchless)
+template <int KIND>
+__device__ __forceinline__ double kx5(double r2, const double* __restrict__ tabv) {
+    if (KIND == GPFO_KERN_RBF) return exp_neg_tab64(-0.5 * fmax(r2, 0.0), tabv);
+    const double x = r2 + 1e-12;                             // euclid_dist: sqrt(r2 + 1e-12); square(r) == x to 1 ulp
+    const double r = fast_sqrt_pos(x);
+    if (KIND == GPFO_KERN_MATERN52) {
+        const double s5 = 2.2360679774997898;
+        return fma(5.0 / 3.0, x, fma(s5, r, 1.0)) * exp_neg_tab64(-s5 * r, tabv);
+    }
+    const double s3 = 1.7320508075688772;
+    return fma(s3, r, 1.0) * exp_neg_tab64(-s3 * r, tabv);
+}
 __device__ __forceinline__ void mbar_wait_par(unsigned bar_s, unsigned parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -69,7 +111,8 @@ __device__ __forceinline__ void mbar_wait_par(unsigned bar_s, unsigned parity) {
 }
 
 // ABL (profiling builds only, GPFO_BUILD_EXPERIMENTS): bit 0 = K(X*,X) elements are constants (no generation arithmetic),
-// bit 1 = no L^-1 copies (the ring is never filled), bit 2 = no mbarrier hand-off of the groups (wrong results; timing only)
+// bit 1 = no L^-1 copies (the ring is never filled), bit 2 = no mbarrier hand-off of the groups (wrong results; timing only),
+// bit 3 = per-warp phase cycle counters
 template <int RBW, int NB, int QD, int KIND, int ABL = 0>
 __global__ void __launch_bounds__(512, 1)
 contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ prog, EvalIO io, int nbuf) {
@@ -78,21 +121,20 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     constexpr int GS = C::GROUP_SLOTS;
     extern __shared__ __align__(16) double smem[];
     const int D = gpp->D;
+    const int DP = (D + 3) / 4 * 4;
     double* ring = smem;                                             // [NW][QD][RQ][64]  private L^-1 rings
     double* kres = ring + (size_t)NW * C::RING_DOUBLES_PER_WARP;     // [RG][GS]          resident panel of K(X*,X)
     double* kstr = kres + (size_t)RG * GS;                           // [nbuf][GS]        streaming groups right of the panel
-    double* xc = kstr + (size_t)nbuf * GS;                           // [D][T]
-    double* x2 = xc + (size_t)D * T;                                 // [T]
-    double* tot = x2 + T;                                            // [T][1+RMAX] running colsum(A^2), A^T V
-    double* sbest = tot + T * (1 + RMAX);                            // [2] best value, best index (as bits)
-    double* tab32 = sbest + 2;                                       // [32] 2^(i/32) (+2 pad)
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(tab32 + 34);   // full_res[RG], full_str[4], empty_str[4]
+    double* xcb = kstr + (size_t)nbuf * GS;                          // [2][DP][T]        candidates of this / the next tile
+    double* totb = xcb + 2 * (size_t)DP * T;                         // [2][T][1+RMAX]    colsum(A^2), A^T V of this / the previous tile
+    double* sbest = totb + 2 * T * (1 + RMAX);                       // [2] best value, best index (as bits)
+    double* tabv = sbest + 2;                                        // [64] variance * 2^(i/64) (+2 pad)
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(tabv + 66);   // full_res[RG], full_str[4], empty_str[4]
     static_assert(T <= 32, "one epilogue warp");
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const GpDev& gp = *gpp;
     const int M = gp.M, R = gp.R;
-    const double variance = gp.variance;
     const double* __restrict__ Xs = gp.Xs;
     const double* __restrict__ xn = gp.xn;
     const double* __restrict__ Vv = gp.V;
@@ -103,67 +145,96 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     const unsigned bar_res = (unsigned)__cvta_generic_to_shared(bars);
     const unsigned bar_full = bar_res + 8 * RG, bar_empty = bar_full + 8 * C::NBUF_MAX;
 
-    const int gen_nb = w % NB;
-    const int gen_n = 8 * gen_nb + (lane >> 2);
-    const int gen_jl = lane & 3;
-    // warps w, w+4, w+8, w+12 share a scheduler: two generate before their DMMA work of a step, two after it, so the FP64
-    // generation of one pair overlaps the tensor work of the other
-    const bool gen_first = ((w >> 2) & 1) == 0;
-    const int la = nbuf >= 3 ? 2 : 1;                 // groups are generated `la` steps ahead of use
+    // generation: warp w owns the 8 x 8 tile (column block gen_jb of the group, candidate block gen_nb); after the DMMAs lane l
+    // holds the dot products of training point 8 jb + l/4 with candidates 8 nb + 2 (l%4) + {0, 1}
+    const int gen_nb = w % NB, gen_jb = w / NB;
+    const int gen_n0 = 8 * gen_nb + 2 * (lane & 3);
+    // B-fragment slot of element (j, n) inside its group: ((j / 4) * NB + n / 8) * 32 + (n % 8) * 4 + j % 4
+    const int gen_slot = ((2 * gen_jb + (lane >> 4)) * NB + gen_nb) * 32 + 8 * (lane & 3) + ((lane >> 2) & 3);
+    // warps w, w+4, w+8, w+12 share a scheduler: two generate before their DMMA work of a step, two after it
+    const bool gen_first = (ABL & 16) ? true : ((ABL & 64) ? false : ((w >> 2) & 1) == 0);
+    const int la = (ABL & 32) ? 1 : (nbuf >= 3 ? 2 : 1);   // groups are generated `la` steps ahead of use
 
     if (tid == 0) { sbest[0] = 0.0; reinterpret_cast<long long*>(sbest)[1] = -1; }
-    if (tid < 32) tab32[tid] = exp2(tid * (1.0 / 32.0));
+    if (tid < 64) tabv[tid] = gp.variance * exp2(tid * (1.0 / 64.0));
+    if (tid < 2 * T * (1 + RMAX)) totb[tid] = 0.0;
     if (tid == 0) {
         for (int b = 0; b < RG; ++b) mbar_init(bar_res + 8 * b, NW);
         for (int b = 0; b < C::NBUF_MAX; ++b) { mbar_init(bar_full + 8 * b, NW); mbar_init(bar_empty + 8 * b, NW); }
     }
+    // candidates of tile `tile` -> xcb[buf]: input transform (transforms.py:102-103), division by the lengthscales, zero padding
+    // of the input dimension up to DP.  One element per thread and pass; the caller provides the barrier that publishes them.
+    auto stage_candidates = [&](int64_t tile, int buf, int first_thread, int nthreads) {
+        const int64_t n0 = tile * T;
+        double* xc = xcb + (size_t)buf * DP * T;
+        for (int e = tid - first_thread; e >= 0 && e < T * DP; e += nthreads) {
+            const int n = e / DP, d = e - n * DP;
+            double v = 0.0;
+            if (d < D) {
+                double x = 0.0;
+                if (n0 + n < io.N) {
+                    if (io.gen_A) {     // RandomDesign on the device: unit-cube draw, then generative_domain >> domain (design.py:55-70, 93-94)
+                        const double u = gpfo_uniform(io.gen_seed, (unsigned long long)(io.gen_first + n0 + n) * D + d);
+                        x = __dadd_rn(__dmul_rn(u, io.gen_A[d]), io.gen_b[d]);
+                    } else {
+                        x = io.X[(size_t)(n0 + n) * D + d];
+                    }
+                }
+                const double xt = __dadd_rn(__dmul_rn(x, gp.in_scale[d]), gp.in_shift[d]);
+                v = xt / gp.ell[d];
+            }
+            xc[d * T + n] = v;
+        }
+    };
+    const int64_t ntiles = (io.N + T - 1) / T;
+    if ((int64_t)blockIdx.x < ntiles) stage_candidates(blockIdx.x, 0, 0, C::THREADS);
     __syncthreads();
     // every streaming buffer starts empty: complete phase 0 of the empty barriers
     if (lane == 0)
         for (int b = 0; b < C::NBUF_MAX; ++b) mbar_arrive(bar_empty + 8 * b);
 
+    constexpr bool TIM = (ABL & 8) != 0;              // profiling build: per-warp cycle counters per phase
+    long long t_all = 0, t_gen = 0, t_mma = 0, t_wait = 0, t_pro = 0, t_red = 0, t_epi = 0, t_mark = 0;
+    if (TIM) t_all = clock64();
     unsigned res_par = 0;                             // parity of the resident panel's barriers: one completion per tile
     unsigned full_ph = 0, empty_ph = 0;               // bit b: parity of the next completion to wait for on buffer b
     int gen_buf = 0, use_buf = 0;                     // streaming ring cursors (every thread walks the same sequence)
 
-    const int64_t ntiles = (io.N + T - 1) / T;
+    // tile epilogue, run by warp 0 one tile late: lane n owns candidate n0 + n of the tile whose sums sit in totb[buf]
+    auto run_epilogue = [&](int64_t n0, int buf) {
+        const double* tot = totb + buf * T * (1 + RMAX);
+        double tot_mv[RMAX];
+        const int ln = lane < T ? lane : 0;
+#pragma unroll
+        for (int ro = 0; ro < RMAX; ++ro) tot_mv[ro] = tot[ln * (1 + RMAX) + 1 + ro];
+        double best_v = sbest[0];
+        long long best_i = reinterpret_cast<long long*>(sbest)[1];
+        gpfo_tile_epilogue<T>(gp, prog, io, n0, lane, tot[ln * (1 + RMAX)], tot_mv, best_v, best_i);
+        if (lane == 0) { sbest[0] = best_v; reinterpret_cast<long long*>(sbest)[1] = best_i; }
+    };
+
+    int par = 0;                                      // which half of xcb / totb belongs to the current tile
+    int64_t prev_n0 = -1;                             // first candidate of the tile whose epilogue is still due
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t n0 = tile * T;
-        __syncthreads();                              // previous tile done: xc, tot and the resident panel may be overwritten
-        if (tid < T * (1 + RMAX)) tot[tid] = 0.0;
-        for (int e = tid; e < T * D; e += C::THREADS) {
-            const int n = e / D, d = e - n * D;
-            double x = 0.0;
-            if (n0 + n < io.N) {
-                if (io.gen_A) {     // RandomDesign on the device: unit-cube draw, then generative_domain >> domain (design.py:55-70, 93-94)
-                    const double u = gpfo_uniform(io.gen_seed, (unsigned long long)(io.gen_first + n0 + n) * D + d);
-                    x = __dadd_rn(__dmul_rn(u, io.gen_A[d]), io.gen_b[d]);
-                } else {
-                    x = io.X[(size_t)(n0 + n) * D + d];
-                }
-            }
-            const double xt = __dadd_rn(__dmul_rn(x, gp.in_scale[d]), gp.in_shift[d]);
-            xc[d * T + n] = xt / gp.ell[d];
+        const double* xc = xcb + (size_t)par * DP * T;
+        double* tot = totb + par * T * (1 + RMAX);
+        if (TIM) t_mark = clock64();
+        // squared norms of this thread's two candidates (its generation tile's columns)
+        double x2a = 0.0, x2b = 0.0;
+        for (int d = 0; d < D; ++d) {
+            const double2 v = *reinterpret_cast<const double2*>(xc + d * T + gen_n0);
+            x2a = fma(v.x, v.x, x2a);
+            x2b = fma(v.y, v.y, x2b);
         }
-        __syncthreads();
-        if (tid < T) {
-            double s = 0.0;
-            for (int d = 0; d < D; ++d) s += xc[d * T + tid] * xc[d * T + tid];
-            x2[tid] = s;
-        }
-        __syncthreads();
+        if (TIM) t_pro += clock64() - t_mark;
 
         for (int p = 0; p < geom.nchunks; ++p) {
             const int nr = pg_chunk_rows(geom, p);
             const int row0 = p * geom.rbc;            // first row block of this chunk = first diagonal column block
             const int kp_end = row0 + nr;
             const bool full_chunk = nr == C::RBC;
-
-            double acc[RBW][NB][2];
-#pragma unroll
-            for (int r = 0; r < RBW; ++r)
-#pragma unroll
-                for (int nb = 0; nb < NB; ++nb) { acc[r][nb][0] = 0.0; acc[r][nb][1] = 0.0; }
+            const bool last_chunk = p + 1 == geom.nchunks;
 
             // ---- L^-1 ring.  Block (kp, row block rbl) lives at P(kp) + rbl * 64 doubles, where P advances by nr blocks per dense
             // column block and by nr - kd - 1 per diagonal one (pg_col_base in closed form).  src_next points at column block
@@ -191,36 +262,29 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             };
             auto ring_step = [&]() { ring_off = (ring_off == (QD - 1) * RQ * 64) ? 0 : ring_off + RQ * 64; };
 
-            // ---- K(X*,X) groups
+            // ---- K(X*,X) groups: this warp's 8 x 8 tile of dot products on the tensor pipe, then the covariance of its two elements
             auto gen_elems = [&](int g, double* __restrict__ dst) {
-                double dot[C::GEN_ITERS];
-                int jj[C::GEN_ITERS];
-#pragma unroll
-                for (int q = 0; q < C::GEN_ITERS; ++q) {
-                    const int ksl = (w + NW * q) / NB;
-                    const int j = (g * GK) * 8 + 4 * ksl + gen_jl;
-                    jj[q] = j < M ? j : M - 1;            // clamp: keeps the loads in range, result masked below
-                    dot[q] = 0.0;
-                }
+                const int jrow = (g * GK + gen_jb) * 8 + (lane >> 2);       // training point of this lane's A-fragment row = of its outputs
+                const int jc = jrow < M ? jrow : M - 1;                     // clamp: keeps the loads in range, result masked below
+                double d0 = 0.0, d1 = 0.0;
                 if (!(ABL & 1)) {
-                    for (int d = 0; d < D; ++d) {
-                        const double c = xc[d * T + gen_n];
-#pragma unroll
-                        for (int q = 0; q < C::GEN_ITERS; ++q) dot[q] = fma(__ldg(Xs + (size_t)jj[q] * D + d), c, dot[q]);
+                    const double* __restrict__ xrow = Xs + (size_t)jc * D + (lane & 3);
+                    const double* __restrict__ xcol = xc + (lane & 3) * T + 8 * gen_nb + (lane >> 2);
+                    for (int k = 0; k < DP; k += 4) {
+                        const double a = (k + (lane & 3) < D) ? __ldg(xrow + k) : 0.0;
+                        dmma884(d0, d1, a, xcol[k * T]);
                     }
                 }
-#pragma unroll
-                for (int q = 0; q < C::GEN_ITERS; ++q) {
-                    const int ksl = (w + NW * q) / NB;
-                    const int j = (g * GK) * 8 + 4 * ksl + gen_jl;
-                    double val;
-                    if (ABL & 1) val = 1e-3 * j;
-                    else {
-                        const double r2 = (-2.0 * dot[q] + __ldg(xn + jj[q])) + x2[gen_n];    // square_dist, expanded form
-                        val = kx_branchless<KIND>(variance, r2, tab32);
-                    }
-                    dst[(ksl * NB + gen_nb) * 32 + lane] = j < M ? val : 0.0;
+                double v0, v1;
+                if (ABL & 1) { v0 = 1e-3 * jrow; v1 = v0; }
+                else {
+                    const double xnj = __ldg(xn + jc);
+                    v0 = kx5<KIND>((-2.0 * d0 + xnj) + x2a, tabv);          // square_dist, expanded form
+                    v1 = kx5<KIND>((-2.0 * d1 + xnj) + x2b, tabv);
                 }
+                const bool in = jrow < M;
+                dst[gen_slot] = in ? v0 : 0.0;
+                dst[gen_slot + 4] = in ? v1 : 0.0;
             };
             auto gen_group = [&](int g) {
                 if (g < RG) {                             // resident panel (chunk 0 only): slot g is free since the tile barrier
@@ -236,6 +300,30 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                     gen_buf = (gen_buf + 1 == nbuf) ? 0 : gen_buf + 1;
                 }
             };
+
+            const int ngroups = (kp_end + GK - 1) / GK;
+            const int g_first = p == 0 ? 0 : RG;      // groups left of it are resident since chunk 0 of this tile
+
+            // ring prologue: KA column blocks ahead
+#pragma unroll
+            for (int a = 0; a < KA; ++a) {
+#pragma unroll
+                for (int qd = 0; qd < QPC; ++qd) { issue_quad(qd); ring_step(); }
+                advance_next();
+            }
+            // generation prologue (chunk 0: the first `la` groups)
+            if (TIM) t_mark = clock64();
+            for (int g = g_first; g < la && g < ngroups; ++g) gen_group(g);
+            if (TIM) { const long long t = clock64(); t_gen += t - t_mark; t_mark = t; }
+            // the previous tile's epilogue: warp 0 has delivered its share of the first groups, the other warps are contracting
+            if (p == 0 && w == 0 && prev_n0 >= 0) run_epilogue(prev_n0, par ^ 1);
+            if (TIM) t_epi += clock64() - t_mark;
+
+            double acc[RBW][NB][2];
+#pragma unroll
+            for (int r = 0; r < RBW; ++r)
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) { acc[r][nb][0] = 0.0; acc[r][nb][1] = 0.0; }
 
             // One column block: B fragments from the group, A fragments from the ring, up to RBW * 2 * NB DMMAs.
             // Row block r of this warp (global row block r * NW + w of the chunk) is active in column block kp iff
@@ -358,23 +446,12 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 advance_next();
             };
 
-            const int ngroups = (kp_end + GK - 1) / GK;
-            const int g_first = p == 0 ? 0 : RG;      // groups left of it are resident since chunk 0 of this tile
-
-            // ring prologue: KA column blocks ahead
-#pragma unroll
-            for (int a = 0; a < KA; ++a) {
-#pragma unroll
-                for (int qd = 0; qd < QPC; ++qd) { issue_quad(qd); ring_step(); }
-                advance_next();
-            }
-            // generation prologue (chunk 0: the first `la` groups)
-            for (int g = g_first; g < la && g < ngroups; ++g) gen_group(g);
-
             for (int g = 0; g < ngroups; ++g) {
                 const int gg = g + la;
                 const bool do_gen = gg >= g_first && gg < ngroups;
+                if (TIM) t_mark = clock64();
                 if (do_gen && gen_first) gen_group(gg);
+                if (TIM) { const long long t = clock64(); t_gen += t - t_mark; t_mark = t; }
                 // wait for group g
                 const double* kb;
                 if (g < RG) {
@@ -385,6 +462,7 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                     full_ph ^= 1u << use_buf;
                     kb = kstr + (size_t)use_buf * GS + lane;
                 }
+                if (TIM) { const double probe = kb[0]; if (probe == 123.456) t_gen += 1; const long long t = clock64(); t_wait += t - t_mark; t_mark = t; }
                 const int k0 = g * GK;
                 const int k1 = (k0 + GK < kp_end) ? k0 + GK : kp_end;
                 if (full_chunk && k1 + KA <= row0) {  // group and its refills in the dense part of a full chunk: no predicates
@@ -403,9 +481,12 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                     if (lane == 0) mbar_arrive(bar_empty + 8 * use_buf);
                     use_buf = (use_buf + 1 == nbuf) ? 0 : use_buf + 1;
                 }
+                if (TIM) { const long long t = clock64(); t_mma += t - t_mark; t_mark = t; }
                 if (do_gen && !gen_first) gen_group(gg);
+                if (TIM) { const long long t = clock64(); t_gen += t - t_mark; }
             }
             cp_async_wait<0>();
+            if (TIM) t_mark = clock64();
 
             // ---- chunk reduction (fixed order -> deterministic).  Warp w's slice red[w][T][1+RMAX] lives at the start of its
             // own, now drained, ring region; the next chunk's copies are issued only after the barriers below.
@@ -459,28 +540,31 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                         }
                 }
             }
-            __syncthreads();
+            __syncthreads();                              // every warp is past its column loop: xcb[par] and the panel are dead
             if (tid < T * (1 + RMAX)) {                  // thread (n, k): fixed warp order -> deterministic
                 const int n = tid / (1 + RMAX), k = tid - n * (1 + RMAX);
                 if (k <= R) {
-                    double a = tot[tid];
+                    double a = p == 0 ? 0.0 : tot[tid];
                     for (int ww = 0; ww < NW; ++ww) a += red[ww * RS + n * (1 + RMAX) + k];
                     tot[tid] = a;
                 }
+            } else if (last_chunk && tile + gridDim.x < ntiles) {
+                // the otherwise idle threads stage the next tile's candidates into the other buffer; the barrier below publishes them
+                stage_candidates(tile + gridDim.x, par ^ 1, T * (1 + RMAX), C::THREADS - T * (1 + RMAX));
             }
             __syncthreads();
+            if (TIM) { if (*reinterpret_cast<volatile double*>(tabv) == 123.456) t_gen += 1; t_red += clock64() - t_mark; }
         }
         res_par ^= 1u;
-        if (w == 0) {                                     // epilogue: lane n owns candidate n0 + n
-            double tot_mv[RMAX];
-            const int ln = lane < T ? lane : 0;
-#pragma unroll
-            for (int ro = 0; ro < RMAX; ++ro) tot_mv[ro] = tot[ln * (1 + RMAX) + 1 + ro];
-            double best_v = sbest[0];
-            long long best_i = reinterpret_cast<long long*>(sbest)[1];
-            gpfo_tile_epilogue<T>(gp, prog, io, n0, lane, tot[ln * (1 + RMAX)], tot_mv, best_v, best_i);
-            if (lane == 0) { sbest[0] = best_v; reinterpret_cast<long long*>(sbest)[1] = best_i; }
-        }
+        prev_n0 = n0;
+        par ^= 1;
+    }
+    if (TIM) t_mark = clock64();
+    if (w == 0 && prev_n0 >= 0) run_epilogue(prev_n0, par ^ 1);      // the last tile's epilogue
+    if (TIM) t_epi += clock64() - t_mark;
+    if (TIM && lane == 0 && io.debug) {
+        long long* o = io.debug + ((size_t)blockIdx.x * NW + w) * 8;
+        o[0] = clock64() - t_all; o[1] = t_gen; o[2] = t_mma; o[3] = t_wait; o[4] = t_pro; o[5] = t_red; o[6] = t_epi;
     }
     __syncthreads();
     if (tid == 0 && io.run_program) {
