@@ -196,7 +196,7 @@ int gpfo_ctx_destroy(gpfo_ctx* ctx) {
 
 // Relative cost of one large-batch pass over Mp training points with a given forward kernel: block-steps the kernel issues
 // (its last, ragged chunk is padded to whole quads of row blocks per warp in v5) over its measured DMMA efficiency on full
-// chunks (profiles/r02_v5_sweep_2_static_triangles.log: v20 77-82 %, v21 65-70 %, v12 51-75 %).
+// chunks (profiles/r02_v5_sweep_3_pipelined_tiles.log: v20 69-82 %, v21 55-72 %, v12 51-76 %).
 static double large_batch_cost(int variant, int Mp) {
     const int nrb = Mp / 8;
     if (variant == 12) return (double)nrb * (nrb + 1) / 2 / (Mp >= 1536 ? 0.74 : (Mp >= 768 ? 0.65 : 0.51));
@@ -211,7 +211,7 @@ static double large_batch_cost(int variant, int Mp) {
             steps += (double)rows_per_warp * 16 * (row0 + nr);
         }
     }
-    return steps / (variant == 20 ? (Mp >= 1536 ? 0.78 : 0.64) : (Mp >= 768 ? 0.67 : 0.50));
+    return steps / (variant == 20 ? (Mp >= 1536 ? 0.79 : 0.68) : (Mp >= 1536 ? 0.71 : (Mp >= 768 ? 0.68 : 0.55)));
 }
 
 static int effective_variant(const gpfo_ctx* ctx, int64_t N, int Mp) {
@@ -282,6 +282,23 @@ static int grad_split_wide(const gpfo_ctx* ctx, int64_t N, int nchunks) {
 
 static int ensure_partials(gpfo_ctx* ctx) {
     CK(ensure(&ctx->dpartials, &ctx->cap_partials, (size_t)4 * ctx->num_sms * 32 * (1 + GPFO_MAX_DIM)));
+    return GPFO_OK;
+}
+
+// Block stream of L^-1 with `rbc` row blocks per chunk, built on first use and cached in its slot; does not change which
+// layout the GP's device record points at.
+static int ensure_pack(gpfo_ctx* ctx, GpHost& g, int rbc, const double** packed, PackGeom* geom_out) {
+    const PackGeom geom = make_geom(g.Mp / 8, rbc, 0);
+    const int slot = rbc == 32 ? 0 : (rbc == 64 ? 1 : 2);
+    if (!g.packed_ready[slot] || g.packed_slot_rbc[slot] != rbc) {
+        CK(ensure(&g.dpacked_by[slot], &g.cap_packed_by[slot], (size_t)pg_total_blocks(geom) * 64));
+        gpfo_pack_linv(ctx->stream, g.dLinv, g.Mf, geom, g.dpacked_by[slot]);
+        CK(cudaGetLastError());
+        g.packed_ready[slot] = true;
+        g.packed_slot_rbc[slot] = rbc;
+    }
+    *packed = g.dpacked_by[slot];
+    *geom_out = geom;
     return GPFO_OK;
 }
 
@@ -674,12 +691,18 @@ static int launch_stored_a(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
     rc = ensure_parts(ctx, (int)(nslabs * ppg));
     if (rc != GPFO_OK) return rc;
     io.part_val = ctx->dpart_val; io.part_idx = ctx->dpart_idx;
+    // forward kernel of the pass: the resident-panel kernel where it beats the 64-candidate tiles (cost model of the
+    // large-batch forward), unless a kernel was pinned or the input is too wide for its shared memory
+    int mp_max = 0;
+    for (int g = 0; g < ctx->ngps; ++g) mp_max = std::max(mp_max, ctx->gps[g].Mp);
+    const bool v5_forward = ctx->variant == 0 && D <= gpfo_contract5_max_dim(20) && !getenv("GPFO_GRAD_FWD_V12") &&
+                            large_batch_cost(20, mp_max) < large_batch_cost(12, mp_max);
     size_t kx_need = 0;
-    for (int g = 0; g < ctx->ngps; ++g) {
+    for (int g = 0; g < ctx->ngps && !v5_forward; ++g) {
         const size_t cols = ((size_t)ctx->gps[g].Mp + 127) / 128 * 128;
         if (cols * Tt * (size_t)sgrid > kx_need) kx_need = cols * Tt * (size_t)sgrid;
     }
-    CK(ensure(&ctx->dkx_scratch, &ctx->cap_kx_scratch, kx_need));
+    if (kx_need) CK(ensure(&ctx->dkx_scratch, &ctx->cap_kx_scratch, kx_need));
     nparts = 0;
     for (int64_t k = 0; k < nslabs; ++k) {
         const int64_t n0 = k * slab_n;
@@ -704,7 +727,13 @@ static int launch_stored_a(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
             gio.a_stride = gpfo_contract_astore_stride(gh.Mp / 8);
             a_off += (size_t)slab_tiles * (size_t)gio.a_stride;
             if (k == 0) CK(cudaEventRecord(ctx->gp_ev[g][0], st));
-            CK(gpfo_contract_astore_launch(st, gh.kind, gh.ddev, ctx->dprog, gio, g_s, D));
+            if (v5_forward) {              // resident-panel forward (no K(X*,X) scratch), same A layout
+                rc = ensure_pack(ctx, ctx->gps[g], gpfo_contract_rbc(20), &gio.packed_o, &gio.geom_o);
+                if (rc != GPFO_OK) return rc;
+                CK(gpfo_contract5_astore_launch(st, gh.kind, gh.ddev, ctx->dprog, gio, ctx->num_sms, D));
+            } else {
+                CK(gpfo_contract_astore_launch(st, gh.kind, gh.ddev, ctx->dprog, gio, g_s, D));
+            }
             if (k == 0) CK(cudaEventRecord(ctx->gp_ev[g][1], st));
             ++launches;
         }

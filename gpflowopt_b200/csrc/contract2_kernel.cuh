@@ -54,7 +54,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     // SASS UBLKCP) issued by thread 0 and signalled on an mbarrier per group buffer, instead of four LDGSTS per thread
     constexpr bool BULK = (ABL & 1024) != 0;
     unsigned long long* kxbar = reinterpret_cast<unsigned long long*>(GRADM ? gsum + T * (1 + D) : gcm);   // [KXB]
-    static_assert(!GRADM || NW * C::RING_DOUBLES_PER_WARP + KXB * C::GROUP_SLOTS >= 8 * C::RBC * T,
+    static_assert(!GRADM || NW * C::RING_DOUBLES_PER_WARP + KXB * C::GROUP_SLOTS >= 8 * C::RBC * (T + 4),
                   "the u buffer of the gradient pass reuses the ring and the group buffers");
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
@@ -352,7 +352,9 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             if (GRADM) {
                 // ---- gradient pass: u_in = (sum_ro c_mu[n][ro] alpha[i][ro] + c_var[n] w_in) * dk_in/dr^2 into the (drained) ring
                 __syncthreads();                          // every warp is done reading its ring
-                double* ubuf = ring;                      // [8 * RBC][T]  (spills into the group buffers when S < NB)
+                constexpr int US = T + 4;                 // row stride of the u buffer: 4 mod 16 doubles, so that the A-fragment reads
+                                                          // of the reduction below (4 rows x 4 candidates per half-warp) hit 16 banks
+                double* ubuf = ring;                      // [8 * RBC][US]  (spills into the group buffers when S < NB)
                 const int rev = 8 * geom.nrb - 1;         // backward pass: stream row i' is training point rev - i'
 #pragma unroll
                 for (int r = 0; r < RBW; ++r) {
@@ -376,32 +378,38 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                                 const double r2 = (-2.0 * dot + __ldg(xn + gi)) + x2[n];
                                 u = coef * dk_dr2_branchless<KIND>(variance, r2, tab32);
                             }
-                            ubuf[il * T + n] = u;
+                            ubuf[il * US + n] = u;
                         }
                 }
                 __syncthreads();
-                for (int e = tid; e < T * (1 + D); e += C::THREADS) {     // thread (n, dd): fixed row order
-                    const int n = e / (1 + D), dd = e - n * (1 + D);
-                    // eight interleaved partial sums (rows il = 8q + k): the DFMA chain, not the loads, bounds this loop
-                    double a[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) a[k] = 0.0;
-                    a[0] = gsum[e];
-                    const int rows = 8 * nr;                              // a multiple of 8
-                    if (dd == 0) {
-                        for (int il = 0; il < rows; il += 8) {
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) a[k] += ubuf[(il + k) * T + n];
+                // ---- G[n][c'] += sum_i u[i][n] * Xa[i][c'],  Xa = [1, Xs]: a (T x rows) x (rows x (1+D)) product, done as 8 x 8
+                // tiles of DMMAs (one or a few tiles per warp: candidate block x column block) instead of T (1+D) scalar row
+                // loops -- with T (1+D) = 576 tasks on 512 threads the scalar form ran a second round on 64 threads.
+                // Two interleaved accumulator pairs (even / odd k-steps) keep the dependent DMMA chain short; row order fixed.
+                {
+                    const int ND = (1 + D + 7) / 8;       // column blocks of Xa
+                    const int rows = 8 * nr;              // a multiple of 8
+                    const int step = BWD ? -1 : 1;
+                    const int g0 = BWD ? rev - 8 * row0 : 8 * row0;             // training point of buffer row 0
+                    for (int q = w; q < NB * ND; q += NW) {
+                        const int nbq = q % NB, dbq = q / NB;
+                        const int cq = 8 * dbq + (lane >> 2);                   // column of Xa this lane feeds (B fragment: col = lane / 4)
+                        const double* __restrict__ up = ubuf + (lane & 3) * US + 8 * nbq + (lane >> 2);
+                        const bool is_one = cq == 0, is_x = cq >= 1 && cq <= D;
+                        const double* __restrict__ xp = Xs + (size_t)(g0 + step * (lane & 3)) * D + (is_x ? cq - 1 : 0);
+                        double e0 = 0.0, e1 = 0.0, o0 = 0.0, o1 = 0.0;
+                        for (int k = 0; k < rows; k += 8) {
+                            const double a0 = up[k * US], a1 = up[(k + 4) * US];
+                            const double b0 = is_one ? 1.0 : (is_x ? __ldg(xp + (ptrdiff_t)step * k * D) : 0.0);
+                            const double b1 = is_one ? 1.0 : (is_x ? __ldg(xp + (ptrdiff_t)step * (k + 4) * D) : 0.0);
+                            dmma884(e0, e1, a0, b0);
+                            dmma884(o0, o1, a1, b1);
                         }
-                    } else {
-                        const int step = BWD ? -D : D;
-                        const double* xp = Xs + (size_t)(BWD ? rev - 8 * row0 : 8 * row0) * D + dd - 1;
-                        for (int il = 0; il < rows; il += 8, xp += 8 * step) {
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) a[k] = fma(ubuf[(il + k) * T + n], __ldg(xp + k * step), a[k]);
-                        }
+                        // lane holds G[n = 8 nbq + lane / 4][c' = 8 dbq + 2 (lane % 4) + {0, 1}]; every element has one owner
+                        const int n = 8 * nbq + (lane >> 2), c0 = 8 * dbq + 2 * (lane & 3);
+                        if (c0 <= D) gsum[n * (1 + D) + c0] += e0 + o0;
+                        if (c0 + 1 <= D) gsum[n * (1 + D) + c0 + 1] += e1 + o1;
                     }
-                    gsum[e] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
                 }
                 __syncthreads();
                 continue;

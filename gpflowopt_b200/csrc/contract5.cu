@@ -23,6 +23,15 @@ cudaError_t gpfo_contract5_launch(cudaStream_t st, int variant, int kind, const 
     return launch5<8, 2, 2>(st, kind, d_gp, d_prog, io, grid, D);
 }
 
+// forward launch of the stored-A gradient pass (large batches): variant 20's tiling, A parked in the layout the backward launch
+// (contract2_kernel, 64-candidate tiles) reads; the grid walks 16-candidate tiles
+cudaError_t gpfo_contract5_astore_launch(cudaStream_t st, int kind, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io,
+                                         int num_sms, int D) {
+    const int64_t ntiles = (io.N + 15) / 16;
+    const int grid = (int)(ntiles < num_sms ? (ntiles > 0 ? ntiles : 1) : num_sms);
+    return launch5<8, 2, 2, 128>(st, kind, d_gp, d_prog, io, grid, D);
+}
+
 // largest input dimension the shared-memory budget of a variant allows (two streaming buffers at least)
 int gpfo_contract5_max_dim(int variant) {
     int D = GPFO_MAX_DIM;

@@ -487,6 +487,29 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             }
             cp_async_wait<0>();
             if (TIM) t_mark = clock64();
+            if (ABL & 128) {
+                // stored-A gradient pass: park A = L^-1 Kx of this chunk for the backward launch, which walks 64-candidate
+                // tiles: reversed row order, B-fragment group layout of contract2_kernel (8 column blocks of 8 candidate
+                // blocks per group); this tile fills candidate blocks NB * (tile % (8 / NB)) .. of 64-candidate tile tile / (8 / NB)
+                constexpr int TPB = 8 / NB;                 // tiles of this kernel per 64-candidate tile
+                double* const at = io.a_scratch + (size_t)(tile / TPB) * io.a_stride;
+                const int nb0 = (int)(tile % TPB) * NB;
+                const int i8 = 7 - (lane >> 2);
+#pragma unroll
+                for (int r = 0; r < RBW; ++r) {
+                    const int rbl = r * NW + w;
+                    if (rbl < nr) {
+                        const int rbrev = geom.nrb - 1 - (row0 + rbl);
+                        double* const o = at + (size_t)(rbrev >> 3) * (KPC * 2 * 8 * 32) +
+                                          (((rbrev & 7) * 2 + (i8 >> 2)) * 8 + nb0) * 32 + (i8 & 3) + 8 * (lane & 3);
+#pragma unroll
+                        for (int nb = 0; nb < NB; ++nb) {
+                            __stcg(o + nb * 32, acc[r][nb][0]);
+                            __stcg(o + nb * 32 + 4, acc[r][nb][1]);
+                        }
+                    }
+                }
+            }
 
             // ---- chunk reduction (fixed order -> deterministic).  Warp w's slice red[w][T][1+RMAX] lives at the start of its
             // own, now drained, ring region; the next chunk's copies are issued only after the barriers below.
