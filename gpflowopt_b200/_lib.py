@@ -17,7 +17,8 @@ MAX_GPS, MAX_SLOTS, MAX_OPS, MAX_PARAMS, MAX_DIM = 16, 16, 64, 64, 64
 EXPORTS = ["gpfo_version", "gpfo_ctx_create", "gpfo_ctx_destroy", "gpfo_last_error", "gpfo_status_string",
            "gpfo_gp_set", "gpfo_gp_count_set", "gpfo_gp_get_factor", "gpfo_program_set", "gpfo_cells_set",
            "gpfo_eval", "gpfo_predict", "gpfo_timings_get", "gpfo_set_variant", "gpfo_measure_dmma_peak",
-           "gpfo_measure_fp64_pipes", "gpfo_pareto_cells", "gpfo_eval_random", "gpfo_random_rows", "gpfo_ndtr_fast_host"]
+           "gpfo_measure_fp64_pipes", "gpfo_pareto_cells", "gpfo_eval_random", "gpfo_random_rows", "gpfo_ndtr_fast_host",
+           "gpfo_non_dominated_sort"]
 
 
 class Timings(ctypes.Structure):
@@ -77,6 +78,7 @@ def load():
                                      ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]
     lib.gpfo_random_rows.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, c_dp, c_dp, c_dp]
     lib.gpfo_ndtr_fast_host.argtypes = [c_dp, ctypes.c_int64, c_dp]
+    lib.gpfo_non_dominated_sort.argtypes = [c_dp, ctypes.c_int64, ctypes.c_int, c_dp]
     lib.gpfo_pareto_cells.argtypes = [c_dp, c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_double, c_dp, c_dp, ctypes.c_int64,
                                       ctypes.POINTER(ctypes.c_int64)]
     for name in EXPORTS:
@@ -96,6 +98,20 @@ def _f64(a, shape=None):
     if shape is not None:
         a = a.reshape(shape)
     return a
+
+
+def non_dominated_counts(Y):
+    """Dominance counts of gpflowopt/pareto.py:78-90 (native host code, csrc/pareto_host.cu); no GPU needed."""
+    lib = load()
+    Y = _f64(Y)
+    if Y.ndim != 2:
+        raise GpfoError(ERR_BAD_SHAPE, "objectives must be n x R")
+    out = np.zeros(Y.shape[0], dtype=np.int64)
+    st = lib.gpfo_non_dominated_sort(_ptr(Y) if Y.size else None, Y.shape[0], Y.shape[1], _ptr(out) if Y.size else None) \
+        if Y.shape[0] else OK
+    if st != OK:
+        raise GpfoError(st, "gpfo_non_dominated_sort failed")
+    return out
 
 
 def ndtr_fast_host(z):

@@ -176,6 +176,11 @@ int gpfo_measure_dmma_peak(gpfo_ctx* ctx, double* tflops);
 int gpfo_pareto_cells(const double* front, const int32_t* order, int P, int R, double threshold, int32_t* lb,
                       int32_t* ub, int64_t capacity, int64_t* count);
 
+/* Host-side setup of HVPoI / BO result assembly: dominance counts of the non-dominated sort.
+ * Replaces: pareto.non_dominated_sort (pareto.py:78-90; an n x n x R temporary in the reference).
+ *   Y          n x R objective rows;   dominance[i] receives the number of rows dominating row i (front: == 0). */
+int gpfo_non_dominated_sort(const double* Y, int64_t n, int R, int64_t* dominance);
+
 /* Host evaluation of the branch-free Normal CDF the HVPoI Phi table uses on the device (csrc/ndtr_fast.cuh; replaces
    tf.contrib.distributions.Normal.cdf at hvpoi.py:112-113).  Same source compiled for the host: lets the CPU tests pin its
    accuracy against scipy.special.ndtr without a GPU.  Needs no ctx. */

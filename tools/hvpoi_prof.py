@@ -9,10 +9,10 @@ from gpflowopt_b200 import _lib, synthetic, pareto            # noqa: E402
 from oracle import acq as oacq, gp as ogp                     # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
-M, D, R = 1024, 4, 3
+M, D, R = 1024, 6, 3
 ctx = _lib.Context(0)
 X = synthetic.candidates(M, D, seed=5)
-F = synthetic.dtlz2_objectives(X, R)
+F = synthetic.dtlz2_objectives(X, R, g_scale=0.4)
 h = synthetic.hypers(D, 1e-3)
 gps = [ogp.ScaledGPR(X, F[:, [j]], ogp.MATERN52, h["lengthscales"], h["variance"], h["noise_variance"]) for j in range(R)]
 for j, g in enumerate(gps):
