@@ -18,7 +18,7 @@ EXPORTS = ["gpfo_version", "gpfo_ctx_create", "gpfo_ctx_destroy", "gpfo_last_err
            "gpfo_gp_set", "gpfo_gp_count_set", "gpfo_gp_get_factor", "gpfo_program_set", "gpfo_cells_set",
            "gpfo_eval", "gpfo_predict", "gpfo_timings_get", "gpfo_set_variant", "gpfo_measure_dmma_peak",
            "gpfo_measure_fp64_pipes", "gpfo_pareto_cells", "gpfo_eval_random", "gpfo_random_rows", "gpfo_ndtr_fast_host",
-           "gpfo_non_dominated_sort"]
+           "gpfo_non_dominated_sort", "gpfo_select_variant"]
 
 
 class Timings(ctypes.Structure):
@@ -79,6 +79,7 @@ def load():
     lib.gpfo_random_rows.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, c_dp, c_dp, c_dp]
     lib.gpfo_ndtr_fast_host.argtypes = [c_dp, ctypes.c_int64, c_dp]
     lib.gpfo_non_dominated_sort.argtypes = [c_dp, ctypes.c_int64, ctypes.c_int, c_dp]
+    lib.gpfo_select_variant.argtypes = [vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int)]
     lib.gpfo_pareto_cells.argtypes = [c_dp, c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_double, c_dp, c_dp, ctypes.c_int64,
                                       ctypes.POINTER(ctypes.c_int64)]
     for name in EXPORTS:
@@ -168,6 +169,7 @@ class Context(object):
                                 "no CPU fallback)" % (device, self._lib.gpfo_status_string(st).decode()))
         self._h = h
         self.device = int(device)
+        self.variant = 0
         self.cum = dict(eval_ms=0.0, hot_kernel_ms=0.0, h2d_ms=0.0, launches=0, calls=0)   # running totals over gpfo_eval calls
 
     def close(self):
@@ -291,6 +293,13 @@ class Context(object):
 
     def set_variant(self, v):
         self._check(self._lib.gpfo_set_variant(self._h, int(v)))
+        self.variant = int(v)
+
+    def select_variant(self, n):
+        """Forward kernel the library would pick for a batch of n candidates (see gpfo_select_variant)."""
+        v = ctypes.c_int(0)
+        self._check(self._lib.gpfo_select_variant(self._h, int(n), ctypes.byref(v)))
+        return v.value
 
     def measure_fp64_pipes(self, mode):
         a, b = ctypes.c_double(0.0), ctypes.c_double(0.0)

@@ -1121,6 +1121,20 @@ int gpfo_set_variant(gpfo_ctx* ctx, int variant) {
     return GPFO_OK;
 }
 
+int gpfo_select_variant(gpfo_ctx* ctx, int64_t N, int* variant) {
+    if (!ctx || !variant || N < 0) return GPFO_ERR_STATE;
+    int mp_max = 0;
+    for (int g = 0; g < ctx->ngps; ++g) mp_max = std::max(mp_max, ctx->gps[g].Mp);
+    int v = effective_variant(ctx, N, mp_max);
+    if (v == 20 || v == 21) {
+        int D = 0;
+        for (int g = 0; g < ctx->ngps; ++g) D = std::max(D, ctx->gps[g].D);
+        if (D > gpfo_contract5_max_dim(v)) v = 12;
+    }
+    *variant = v;
+    return GPFO_OK;
+}
+
 int gpfo_measure_dmma_peak(gpfo_ctx* ctx, double* tflops) {
     if (!ctx || !tflops) return GPFO_ERR_STATE;
     cudaSetDevice(ctx->device);

@@ -78,7 +78,7 @@ def scatter_points(points):
     return (block if block.is_cuda else block.numpy()), lo, n
 
 
-def pipelined_argmax(n_total, d, produce, score, rounds=8):
+def pipelined_argmax(n_total, d, produce, score, rounds=8, on_chunk_rows=None):
     """The reference's single-stream candidate route under data parallelism (gpflowopt/design.py:55-70, 83-94;
     optim.py:152-164), pipelined: ONLY rank 0 produces rows -- in order, ``produce(first_row, count)`` returns rows
     [first_row, first_row + count) as a float64 ndarray, so successive ``np.random.rand`` draws form the reference's stream --
@@ -88,6 +88,7 @@ def pipelined_argmax(n_total, d, produce, score, rounds=8):
     index) and keeps a host copy of its best row.
 
     ``score(block) -> (best value, best local index)``; ``block`` is a CUDA tensor under NCCL, an ndarray otherwise.
+    ``on_chunk_rows(C)`` is called once on every rank, before the first score, with the rows per chunk.
     Returns (value, global index, row 1 x d) on every rank; index -1 when no row has a finite score."""
     td = _pg()
     if td is None or td.get_world_size() == 1:
@@ -103,6 +104,8 @@ def pipelined_argmax(n_total, d, produce, score, rounds=8):
     n_total, d = int(meta[0]), int(meta[1])
     rounds = max(1, min(int(rounds), -(-n_total // ws))) if n_total > 0 else 0
     C = -(-n_total // (ws * rounds)) if n_total > 0 else 0          # rows per chunk
+    if on_chunk_rows is not None:
+        on_chunk_rows(C)
     best = [0.0, -1, np.empty((0, d))]
 
     def fold(block, first_row, count):

@@ -178,6 +178,16 @@ class Engine(object):
         _, _, bv, bi = self.ctx.eval(X, want_values=False, want_grads=False)
         return bv, bi
 
+    def pin_variant_for(self, acq, n):
+        """Pins the forward kernel the library would choose for batches of ``n`` rows; returns the variant to restore.
+        Used when ONE candidate set is scored in several calls (pipelined multi-GPU route): with one kernel for all calls a
+        row's score does not depend on the call it lands in, so duplicates tie exactly and the lowest index wins."""
+        self.prepare(acq)
+        previous = self.ctx.variant
+        if previous == 0 and n > 0:
+            self.ctx.set_variant(self.ctx.select_variant(n))
+        return previous
+
     def argmax_random(self, acq, seed, first_row, n, lower, upper):
         """Best (value, LOCAL index) over rows first_row .. first_row+n-1 of the device-generated candidate stream."""
         self.prepare(acq)

@@ -141,7 +141,15 @@ class MCOptimizer(Optimizer):
                 n_total = held.shape[0] if held is not None else 0
             else:
                 produce, n_total = self._get_eval_rows, self._nsamples
-            best, idx, x = dist.pipelined_argmax(n_total, self.domain.size, produce, acq.argmax)
+            engine = acq._get_engine() if hasattr(acq, '_get_engine') else None
+            restore = []
+            try:
+                best, idx, x = dist.pipelined_argmax(
+                    n_total, self.domain.size, produce, acq.argmax,
+                    on_chunk_rows=(lambda rows: restore.append(engine.pin_variant_for(acq, rows))) if engine is not None else None)
+            finally:
+                if restore and engine is not None and engine.ctx is not None:
+                    engine.ctx.set_variant(restore[0])
             n_total = self._nsamples if not custom else int(dist.broadcast_int(n_total))
             objective.counter += n_total
             if idx < 0:

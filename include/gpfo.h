@@ -164,6 +164,12 @@ int gpfo_timings_get(const gpfo_ctx* ctx, gpfo_timings* out);
  * (gradient pass over the dense K^-1 stream for every batch size), GPFO_ASTORE_BUDGET_MB (bound of the stored-A scratch). */
 int gpfo_set_variant(gpfo_ctx* ctx, int variant);
 
+/* The forward kernel gpfo_eval would select for a batch of N candidates with the models registered now (what variant 0 =
+ * automatic resolves to).  A caller that scores one candidate set in several calls of different sizes (the pipelined multi-GPU
+ * route of MCOptimizer) pins this variant for all of them: per-candidate results are then bit-identical whatever the call a
+ * row lands in, so the first-occurrence argmax of optim.py:158 holds across calls. */
+int gpfo_select_variant(gpfo_ctx* ctx, int64_t N, int* variant);
+
 /* Measures this device's FP64 DMMA issue peak with a register-only mma.sync m8n8k4 loop; TFLOP/s. */
 int gpfo_measure_dmma_peak(gpfo_ctx* ctx, double* tflops);
 

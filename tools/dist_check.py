@@ -41,7 +41,19 @@ lo, hi = dist.shard_bounds(N, rank, world)
 shard_scores = joint.evaluate(cand[lo:hi])
 assert np.array_equal(shard_scores, scores[lo:hi]), "sharded scores differ from the single-GPU scores"
 best = int(np.argmax(scores))
-assert np.array_equal(res.x, cand[[best]]) and float(np.ravel(res.fun)[0]) == -scores[best, 0], (res.x, best)
+# the pipelined route scores the rows in chunks with ONE pinned kernel (chosen for the chunk size), the single-GPU call above with
+# the kernel chosen for all N rows: values agree to rounding (1e-13), the selected row is the same unless two rows tie that closely
+picked = np.flatnonzero(np.all(cand == res.x, axis=1))
+assert picked.size >= 1, "the returned point is not a row of the candidate matrix"
+assert abs(scores[picked[0], 0] - scores[best, 0]) <= 1e-12 * abs(scores[best, 0]), (picked, best)
+assert abs(float(np.ravel(res.fun)[0]) + scores[best, 0]) <= 1e-12 * abs(scores[best, 0]), (res.fun, scores[best, 0])
+# duplicates score identically under a pinned kernel whatever the batch they sit in (first-occurrence tie-break stays exact)
+ctx = joint._get_engine().ctx
+ctx.set_variant(ctx.select_variant(25000))
+a = joint.evaluate(cand[[17, N - 5]])
+b = joint.evaluate(np.vstack((cand[:3000], cand[[N - 5]])))
+ctx.set_variant(0)
+assert a[0, 0] == a[1, 0] == b[17, 0] == b[3000, 0], (a, b[17], b[3000])
 planted = joint.argmax(np.vstack((cand[:20], cand[N - 10:])))
 print("rank %d/%d ok: argmax row %d, value %.6e, nfev %d" % (rank, world, best, scores[best, 0], res.nfev), flush=True)
 td.destroy_process_group()
