@@ -63,23 +63,47 @@ split_final_grad_kernel(const GpDev* __restrict__ gpp, EvalIO io, int T, int D) 
 
 // ---- row-split launches (few candidates: the rows of the block stream are spread over the SMs) ----------------------
 // forward: T = 8 candidates per tile, 128-row chunks; grid = tiles * nsplit, then the finish kernel
-int gpfo_split_rbc() { return 16; }
+// Warps per CTA of the row-split launches = row blocks per chunk of their stream layout (one row block per warp).  Fewer warps
+// per CTA give more, smaller CTAs for the same rows (a tile of <= 8 candidates at M = 2048 on 64 SMs instead of 16) -- measured
+// SLOWER (profiles/r02_latency_split_nw.log: N = 1 gradients at M = 2048 0.212 / 0.204 / 0.272 ms for 16 / 8 / 4 warps):
+// every CTA generates the K(X*,X) panel left of its rows itself, so the panel generation, not the L^-1 stream, bounds a call.
+// 16 stays the default; GPFO_SPLIT_NW keeps the experiment reachable.
+static int split_nw() {
+    static const int nw = [] {
+        const char* e = getenv("GPFO_SPLIT_NW");
+        const int v = e ? atoi(e) : 16;
+        return (v == 4 || v == 8 || v == 16) ? v : 16;
+    }();
+    return nw;
+}
+int gpfo_split_rbc() { return split_nw(); }
 int gpfo_split_tile() { return 8; }
 cudaError_t gpfo_contract_split_launch(cudaStream_t st, int kind, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io,
                                        int D) {
     const int64_t ntiles = (io.N + 7) / 8;
-    cudaError_t e = launch2<16, 1, 1, 4, 16 + 2048>(st, kind, d_gp, d_prog, io, (int)(ntiles * io.nsplit), D);
+    const int grid = (int)(ntiles * io.nsplit);
+    cudaError_t e;
+    switch (split_nw()) {
+        case 16: e = launch2<16, 1, 1, 4, 16 + 2048>(st, kind, d_gp, d_prog, io, grid, D); break;
+        case 8: e = launch2<8, 1, 1, 4, 16 + 2048>(st, kind, d_gp, d_prog, io, grid, D); break;
+        default: e = launch2<4, 1, 1, 4, 16 + 2048>(st, kind, d_gp, d_prog, io, grid, D); break;
+    }
     if (e != cudaSuccess) return e;
     split_final_kernel<<<(unsigned)((io.N + 127) / 128), 128, 0, st>>>(d_gp, d_prog, io, 8);
     return cudaGetLastError();
 }
-// gradient pass: `wide` = 0: T = 8, 128-row chunks (its own dense stream layout); 1: T = 32 over the default K^-1 layout
+// gradient pass: `wide` = 0: T = 8, one row block per warp (its own dense stream layout); 1: T = 32 over the default K^-1 layout
 cudaError_t gpfo_contract_grad_split_launch(cudaStream_t st, int kind, const GpDev* d_gp, EvalIO io, int D, int wide) {
     const int T = wide ? 32 : 8;
     const int64_t ntiles = (io.N + T - 1) / T;
     const int grid = (int)(ntiles * io.nsplit);
-    cudaError_t e = wide ? launch2<16, 4, 4, 4, 4 + 16>(st, kind, d_gp, nullptr, io, grid, D)
-                         : launch2<16, 1, 1, 4, 4 + 16 + 2048>(st, kind, d_gp, nullptr, io, grid, D);
+    cudaError_t e;
+    if (wide) e = launch2<16, 4, 4, 4, 4 + 16>(st, kind, d_gp, nullptr, io, grid, D);
+    else switch (split_nw()) {
+        case 16: e = launch2<16, 1, 1, 4, 4 + 16 + 2048>(st, kind, d_gp, nullptr, io, grid, D); break;
+        case 8: e = launch2<8, 1, 1, 4, 4 + 16 + 2048>(st, kind, d_gp, nullptr, io, grid, D); break;
+        default: e = launch2<4, 1, 1, 4, 4 + 16 + 2048>(st, kind, d_gp, nullptr, io, grid, D); break;
+    }
     if (e != cudaSuccess) return e;
     split_final_grad_kernel<<<(unsigned)((io.N * D + 127) / 128), 128, 0, st>>>(d_gp, io, T, D);
     return cudaGetLastError();
