@@ -889,6 +889,15 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     if (generate && variant == 10) variant = 12;
     if ((variant == 20 || variant == 21) && (want_grad || D > gpfo_contract5_max_dim(variant)))
         variant = 12;     // the gradient pass parks A in the 64-candidate tile layout; very wide inputs exceed v5's shared memory
+    // Gradient batches from about 40 candidates per SM up take the stored-A pass (2 M^2 flop) as well: its forward launch walks
+    // 16-candidate tiles (all SMs busy from N = 16 SMs), and from there on even a partly filled wave of 64-candidate backward
+    // tiles costs less than the dense K^-1 pass (3 M^2 flop); measured in profiles/r02_grad_mid_stored_a.log.
+    // GPFO_ASTORE_MIN_N moves the threshold.
+    if (want_grad && ctx->variant == 0 && variant != 12) {
+        const char* e = getenv("GPFO_ASTORE_MIN_N");
+        const int64_t min_n = e ? atoll(e) : (int64_t)40 * ctx->num_sms;
+        if (N >= min_n && D <= gpfo_contract5_max_dim(20)) variant = 12;
+    }
     const bool use_cluster = variant == 10;
     const int rbc = gpfo_contract_rbc(variant);
     for (int g = 0; g < ctx->ngps; ++g) {
