@@ -86,7 +86,20 @@ struct gpfo_ctx {
     cudaEvent_t gp_ev[GPFO_MAX_GPS][2];        // per-GP event pair around the contraction launch (read after the final sync)
     gpfo_timings tm;
     int variant = 0;
+    // CUDA graphs of small calls (the N = 1 ... few hundred polish / setup calls of a BO iteration are launch bound: six kernel
+    // launches, four small copies and a dozen event records per call).  The whole enqueue sequence of a call shape is captured
+    // the second time the shape is seen and replayed afterwards; `epoch` changes with everything the sequence depends on.
+    struct GraphEntry { unsigned long long key[4]; cudaGraphExec_t exec; int launches; int variant; };
+    std::vector<GraphEntry> graphs;
+    unsigned long long epoch = 0;
+    bool capturing = false;
+    long long graph_replays = 0;
 };
+
+static void drop_graphs(gpfo_ctx* ctx) {
+    for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    ctx->graphs.clear();
+}
 
 static const char* k_status[] = {"ok", "matrix not positive definite", "bad shape", "CUDA error",
                                  "unsupported model or feature", "bad acquisition program", "invalid state"};
@@ -105,9 +118,13 @@ static int fail(gpfo_ctx* ctx, int code, const std::string& msg) {
     return code;
 }
 
+// Bumped whenever a device buffer is (re)allocated: cached CUDA graphs bake buffer addresses in, so they are keyed by it.
+static unsigned long long g_alloc_epoch = 0;
+
 template <typename T>
 static cudaError_t ensure(T** p, size_t* cap, size_t need) {
     if (*cap >= need && *p) return cudaSuccess;
+    ++g_alloc_epoch;
     if (*p) cudaFree(*p);
     *p = nullptr; *cap = 0;
     cudaError_t e = cudaMalloc((void**)p, need * sizeof(T));
@@ -180,6 +197,7 @@ int gpfo_ctx_destroy(gpfo_ctx* ctx) {
     if (!ctx) return GPFO_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    drop_graphs(ctx);
     for (int i = 0; i < GPFO_MAX_GPS; ++i) free_gp(ctx->gps[i]);
     cudaFree(ctx->dprog); cudaFree(ctx->dpf); cudaFree(ctx->dlb); cudaFree(ctx->dub); cudaFree(ctx->dcoff); cudaFree(ctx->dcbnd);
     cudaFree(ctx->dXc); cudaFree(ctx->dvalues); cudaFree(ctx->dmom_mean); cudaFree(ctx->dmom_var);
@@ -315,6 +333,7 @@ static int repack(gpfo_ctx* ctx, GpHost& g, int rbc) {
         g.packed_ready[slot] = true;
         g.packed_slot_rbc[slot] = rbc;
     }
+    ++ctx->epoch;
     g.packed_rbc = rbc;
     g.hdev.geom = geom;
     g.hdev.packed = g.dpacked_by[slot];
@@ -408,6 +427,7 @@ int gpfo_gp_set(gpfo_ctx* ctx, int gp_id, int64_t M64, int D, int R, const doubl
     if (!X || !Y || !lengthscales) return fail(ctx, GPFO_ERR_BAD_SHAPE, "null input");
     if (!(kern_variance > 0.0) || !(noise_variance >= 0.0)) return fail(ctx, GPFO_ERR_BAD_SHAPE, "variances must be positive");
     const int M = (int)M64;
+    ++ctx->epoch;
     GpHost& g = ctx->gps[gp_id];
     const int Mp = (M + 7) / 8 * 8, Mf = (M + FB - 1) / FB * FB;
     if ((size_t)Mf > g.cap_mf || (size_t)D > g.cap_d || (size_t)R > g.cap_r) {
@@ -482,6 +502,7 @@ int gpfo_gp_count_set(gpfo_ctx* ctx, int n_gps) {
     if (!ctx) return GPFO_ERR_STATE;
     if (n_gps < 0 || n_gps > GPFO_MAX_GPS) return fail(ctx, GPFO_ERR_BAD_SHAPE, "n_gps out of range");
     cudaSetDevice(ctx->device);
+    ++ctx->epoch;
     for (int i = n_gps; i < GPFO_MAX_GPS; ++i)
         if (ctx->gps[i].valid || ctx->gps[i].dL) free_gp(ctx->gps[i]);
     ctx->ngps = n_gps;
@@ -505,6 +526,7 @@ int gpfo_program_set(gpfo_ctx* ctx, const int32_t* ops, int nops, const double* 
     cudaSetDevice(ctx->device);
     if (nops < 1 || nops > GPFO_MAX_OPS || nparams < 0 || nparams > GPFO_MAX_PARAMS || !ops)
         return fail(ctx, GPFO_ERR_BAD_PROGRAM, "program size out of range");
+    ++ctx->epoch;
     ProgramDev p;
     memset(&p, 0, sizeof(p));
     int sp = 0, nslots = 0, hv = 0;
@@ -566,6 +588,7 @@ int gpfo_cells_set(gpfo_ctx* ctx, const double* pf_ext, int n_ext_rows, int R, c
     for (int64_t i = 0; i < C * R; ++i)
         if (lb[i] < 0 || lb[i] >= n_ext_rows || ub[i] < 0 || ub[i] >= n_ext_rows)
             return fail(ctx, GPFO_ERR_BAD_SHAPE, "cell index outside pf_ext");
+    ++ctx->epoch;
     cudaFree(ctx->dpf); cudaFree(ctx->dlb); cudaFree(ctx->dub); cudaFree(ctx->dcoff); cudaFree(ctx->dcbnd);
     ctx->dpf = nullptr; ctx->dlb = ctx->dub = ctx->dcoff = nullptr; ctx->dcbnd = nullptr; ctx->cells_set = false;
     CK(cudaMalloc((void**)&ctx->dpf, (size_t)n_ext_rows * R * sizeof(double)));
@@ -615,6 +638,7 @@ static int stage_candidates(gpfo_ctx* ctx, const double* X, int64_t N, int D, co
 
 static int ensure_parts(gpfo_ctx* ctx, int n) {
     if (ctx->cap_parts >= n) return GPFO_OK;
+    ++g_alloc_epoch;
     cudaFree(ctx->dpart_val); cudaFree(ctx->dpart_idx);
     ctx->dpart_val = nullptr; ctx->dpart_idx = nullptr; ctx->cap_parts = 0;
     CK(cudaMalloc((void**)&ctx->dpart_val, (size_t)n * sizeof(double)));
@@ -633,6 +657,7 @@ struct EvalPlan {
 // Two device buffers of the same size that grow together ([slot][N] moment / coefficient arrays).
 static int ensure_pair(gpfo_ctx* ctx, double** a, double** b, size_t* cap, size_t need) {
     if (*cap >= need) return GPFO_OK;
+    ++g_alloc_epoch;
     cudaFree(*a); cudaFree(*b);
     *a = *b = nullptr; *cap = 0;
     CK(cudaMalloc((void**)a, need * sizeof(double)));
@@ -800,7 +825,7 @@ static int launch_standard(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
                 gio.values = nullptr;
             }
         }
-        CK(cudaEventRecord(ctx->gp_ev[g][0], st));
+        if (!ctx->capturing) CK(cudaEventRecord(ctx->gp_ev[g][0], st));
         const int ns = generate ? 1 : split_count(ctx, N, gpfo_split_tile(), ctx->gps[g].geom_s.nchunks);
         if (ns > 1) {
             gio.packed_o = ctx->gps[g].dpacked_s; gio.geom_o = ctx->gps[g].geom_s;
@@ -816,7 +841,7 @@ static int launch_standard(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
             CK(gpfo_contract_launch(st, variant, ctx->gps[g].kind, ctx->gps[g].ddev, ctx->dprog, gio, grid, D));
             fwd_parts = grid;
         }
-        CK(cudaEventRecord(ctx->gp_ev[g][1], st));         // one event pair per GP: nothing waits on the host between launches
+        if (!ctx->capturing) CK(cudaEventRecord(ctx->gp_ev[g][1], st));   // one event pair per GP: nothing waits on the host between launches
         ++launches;
     }
     nparts = fwd_parts;
@@ -877,11 +902,13 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     if (!Xcand && !generate) return fail(ctx, GPFO_ERR_BAD_SHAPE, "null candidates");
     if (generate && want_grad) return fail(ctx, GPFO_ERR_UNSUPPORTED, "gradients of generated candidates are not supported");
     cudaStream_t st = ctx->stream;
-    const double* dX = nullptr;
-    if (!generate) rc = stage_candidates(ctx, Xcand, N, D, &dX);
-    else ctx->tm.h2d_ms = 0.0;
-    if (rc != GPFO_OK) return rc;
-    const bool host_in = !generate && (dX != Xcand);
+    // candidates: device pointers are read in place; host rows are copied to the device right before the launches (below)
+    const bool host_in = !generate && !is_device_ptr(Xcand);
+    const double* dX = generate ? nullptr : Xcand;
+    const size_t xbytes = (size_t)N * D * sizeof(double);
+    const bool stage_x = host_in && xbytes <= GPFO_STAGE_AREA;
+    if (host_in) { CK(ensure(&ctx->dXc, &ctx->cap_xc, (size_t)N * D)); dX = ctx->dXc; }
+    ctx->tm.h2d_ms = 0.0;
 
     int mp_max = 0;
     for (int g = 0; g < ctx->ngps; ++g) mp_max = std::max(mp_max, ctx->gps[g].Mp);
@@ -962,7 +989,6 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     float hot_ms = 0.f;
     rc = ensure_partials(ctx);
     if (rc != GPFO_OK) return rc;
-    CK(cudaEventRecord(ctx->ev[4], st));
     int nparts = grid;
     int slot_first = 0;
     if (hv)
@@ -976,32 +1002,93 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     pl.N = N; pl.D = D; pl.variant = variant; pl.grid = grid; pl.hv_grid = hv_grid; pl.pg_grid = pg_grid;
     pl.slot_first = slot_first; pl.use_cluster = use_cluster; pl.hv = hv; pl.want_grad = want_grad;
     pl.need_mom = need_mom; pl.generate = generate;
-    {
-        NvtxRange nvtx_eval("gpfo:eval");
-        rc = astore ? launch_stored_a(ctx, pl, io, &launches, &nparts, &hot_ms)
-                    : launch_standard(ctx, pl, io, &launches, &nparts, &hot_ms);
-        if (rc != GPFO_OK) return rc;
-    }
-    {
-        NvtxRange nvtx_argmax("gpfo:argmax");
-        gpfo_argmax_final(st, ctx->dpart_val, ctx->dpart_idx, nparts, ctx->dbest_val, ctx->dbest_idx);
-        CK(cudaGetLastError());
-    }
-    ++launches;
-    CK(cudaEventRecord(ctx->ev[5], st));
-    NvtxRange nvtx_download("gpfo:download");
-    // results
     const size_t vbytes = (size_t)N * sizeof(double), gbytes = (size_t)N * D * sizeof(double);
     char* const hv_stage = ctx->hstage + GPFO_STAGE_AREA, *const hg_stage = ctx->hstage + 2 * GPFO_STAGE_AREA;
     char* const hb_stage = ctx->hstage + 3 * GPFO_STAGE_AREA;
     const bool stage_v = out_values && !dev_out && vbytes <= GPFO_STAGE_AREA;
     const bool stage_g = want_grad && !dev_grads && gbytes <= GPFO_STAGE_AREA;
-    if (out_values && !dev_out)
-        CK(cudaMemcpyAsync(stage_v ? (void*)hv_stage : (void*)out_values, ctx->dvalues, vbytes, cudaMemcpyDeviceToHost, st));
-    if (want_grad && !dev_grads)
-        CK(cudaMemcpyAsync(stage_g ? (void*)hg_stage : (void*)out_grads, ctx->dgrads, gbytes, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hb_stage, ctx->dbest_val, 16, cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(ctx->ev[1], st));
+
+    // Everything the call puts on the stream, in order: candidate upload, kernels, final argmax, result download.
+    // `timed` = with the event records of the timing breakdown (not capturable into a graph).
+    auto enqueue = [&](bool timed) -> int {
+        if (host_in) {
+            NvtxRange nvtx_upload("gpfo:upload");
+            if (timed) CK(cudaEventRecord(ctx->ev[2], st));
+            CK(cudaMemcpyAsync(ctx->dXc, stage_x ? (const void*)ctx->hstage : (const void*)Xcand, xbytes, cudaMemcpyHostToDevice, st));
+            if (timed) CK(cudaEventRecord(ctx->ev[3], st));
+        }
+        if (timed) CK(cudaEventRecord(ctx->ev[4], st));
+        {
+            NvtxRange nvtx_eval("gpfo:eval");
+            const int rc2 = astore ? launch_stored_a(ctx, pl, io, &launches, &nparts, &hot_ms)
+                                   : launch_standard(ctx, pl, io, &launches, &nparts, &hot_ms);
+            if (rc2 != GPFO_OK) return rc2;
+        }
+        {
+            NvtxRange nvtx_argmax("gpfo:argmax");
+            gpfo_argmax_final(st, ctx->dpart_val, ctx->dpart_idx, nparts, ctx->dbest_val, ctx->dbest_idx);
+            CK(cudaGetLastError());
+        }
+        ++launches;
+        if (timed) CK(cudaEventRecord(ctx->ev[5], st));
+        NvtxRange nvtx_download("gpfo:download");
+        if (out_values && !dev_out)
+            CK(cudaMemcpyAsync(stage_v ? (void*)hv_stage : (void*)out_values, ctx->dvalues, vbytes, cudaMemcpyDeviceToHost, st));
+        if (want_grad && !dev_grads)
+            CK(cudaMemcpyAsync(stage_g ? (void*)hg_stage : (void*)out_grads, ctx->dgrads, gbytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hb_stage, ctx->dbest_val, 16, cudaMemcpyDeviceToHost, st));
+        if (timed) CK(cudaEventRecord(ctx->ev[1], st));
+        return GPFO_OK;
+    };
+
+    // ---- small calls: replay a captured graph of the sequence above (shape seen before, nothing it depends on changed)
+    static const bool graphs_off = getenv("GPFO_NO_GRAPHS") && atoi(getenv("GPFO_NO_GRAPHS")) != 0;
+    const bool graphable = !graphs_off && !generate && host_in && stage_x && !astore && N <= 1024 &&
+                           (!out_values || stage_v) && (!want_grad || stage_g);
+    bool replayed = false;
+    if (stage_x) memcpy(ctx->hstage, Xcand, xbytes);
+    if (graphable) {
+        const unsigned long long key[4] = {(unsigned long long)N, (unsigned long long)D | (want_grad ? 256ull : 0ull) | (out_values ? 512ull : 0ull),
+                                           ctx->epoch, g_alloc_epoch};
+        gpfo_ctx::GraphEntry* hit = nullptr;
+        for (auto& g : ctx->graphs)
+            if (g.key[0] == key[0] && g.key[1] == key[1] && g.key[2] == key[2] && g.key[3] == key[3]) { hit = &g; break; }
+        if (hit && !hit->exec) {                           // second sighting: capture and instantiate
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+                ctx->capturing = true;
+                const int rc2 = enqueue(false);
+                ctx->capturing = false;
+                const cudaError_t e = cudaStreamEndCapture(st, &graph);
+                if (rc2 == GPFO_OK && e == cudaSuccess && graph &&
+                    cudaGraphInstantiate(&hit->exec, graph, 0) == cudaSuccess) {
+                    hit->launches = launches; hit->variant = variant;
+                } else {
+                    hit->exec = nullptr;
+                    cudaGetLastError();
+                }
+                if (graph) cudaGraphDestroy(graph);
+                launches = 0;
+            }
+        }
+        if (hit && hit->exec) {
+            CK(cudaEventRecord(ctx->ev[4], st));
+            CK(cudaGraphLaunch(hit->exec, st));
+            CK(cudaEventRecord(ctx->ev[1], st));
+            launches = hit->launches;
+            replayed = true;
+            ++ctx->graph_replays;
+        } else if (!hit) {
+            if (ctx->graphs.size() >= 32) drop_graphs(ctx);
+            gpfo_ctx::GraphEntry ge;
+            memcpy(ge.key, key, sizeof(key)); ge.exec = nullptr; ge.launches = 0; ge.variant = variant;
+            ctx->graphs.push_back(ge);
+        }
+    }
+    if (!replayed) {
+        rc = enqueue(true);
+        if (rc != GPFO_OK) return rc;
+    }
     CK(cudaStreamSynchronize(st));
     if (stage_v) memcpy(out_values, hv_stage, vbytes);
     if (stage_g) memcpy(out_grads, hg_stage, gbytes);
@@ -1011,6 +1098,14 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     memcpy(&hidx, hb_stage + 8, sizeof(long long));
     if (best_value) *best_value = hbest;
     if (best_index) *best_index = (int64_t)hidx;
+    if (replayed) {                                        // one event pair around the whole graph: copies and kernels together
+        float gms = 0.f;
+        cudaEventElapsedTime(&gms, ctx->ev[4], ctx->ev[1]);
+        ctx->tm.h2d_ms = 0.0; ctx->tm.eval_ms = gms; ctx->tm.d2h_ms = 0.0; ctx->tm.hot_kernel_ms = 0.0;
+        ctx->tm.launches = launches;
+        ctx->tm.variant = variant;
+        return GPFO_OK;
+    }
     float ms = 0.f;
     if (host_in) { cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->tm.h2d_ms = ms; }
     cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->tm.eval_ms = ms;
@@ -1126,6 +1221,7 @@ int gpfo_set_variant(gpfo_ctx* ctx, int variant) {
     bool ok = false;
     for (int k : known) ok = ok || k == variant;
     if (!ok) return fail(ctx, GPFO_ERR_BAD_SHAPE, "unknown kernel variant");
+    ++ctx->epoch;
     ctx->variant = variant;
     return GPFO_OK;
 }
