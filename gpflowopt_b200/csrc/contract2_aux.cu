@@ -83,7 +83,11 @@ cudaError_t gpfo_contract_split_launch(cudaStream_t st, int kind, const GpDev* d
     const int64_t ntiles = (io.N + 7) / 8;
     const int grid = (int)(ntiles * io.nsplit);
     cudaError_t e;
-    switch (split_nw()) {
+    // ring depth of the L^-1 stream: 8 stages (profiles/r02_latency_split_depth.log: N = 1 gradients at M = 4096 0.419 -> 0.390 ms,
+    // no change at M <= 2048); GPFO_SPLIT_S=4 restores round 1's depth
+    static const int deep = getenv("GPFO_SPLIT_S") ? atoi(getenv("GPFO_SPLIT_S")) : 8;
+    if (split_nw() == 16 && deep == 8) e = launch2<16, 1, 1, 8, 16 + 2048>(st, kind, d_gp, d_prog, io, grid, D);
+    else switch (split_nw()) {
         case 16: e = launch2<16, 1, 1, 4, 16 + 2048>(st, kind, d_gp, d_prog, io, grid, D); break;
         case 8: e = launch2<8, 1, 1, 4, 16 + 2048>(st, kind, d_gp, d_prog, io, grid, D); break;
         default: e = launch2<4, 1, 1, 4, 16 + 2048>(st, kind, d_gp, d_prog, io, grid, D); break;
@@ -98,7 +102,9 @@ cudaError_t gpfo_contract_grad_split_launch(cudaStream_t st, int kind, const GpD
     const int64_t ntiles = (io.N + T - 1) / T;
     const int grid = (int)(ntiles * io.nsplit);
     cudaError_t e;
+    static const int deep = getenv("GPFO_SPLIT_S") ? atoi(getenv("GPFO_SPLIT_S")) : 8;
     if (wide) e = launch2<16, 4, 4, 4, 4 + 16>(st, kind, d_gp, nullptr, io, grid, D);
+    else if (split_nw() == 16 && deep == 8) e = launch2<16, 1, 1, 8, 4 + 16 + 2048>(st, kind, d_gp, nullptr, io, grid, D);
     else switch (split_nw()) {
         case 16: e = launch2<16, 1, 1, 4, 4 + 16 + 2048>(st, kind, d_gp, nullptr, io, grid, D); break;
         case 8: e = launch2<8, 1, 1, 4, 4 + 16 + 2048>(st, kind, d_gp, nullptr, io, grid, D); break;
