@@ -21,7 +21,8 @@ SOURCES = ["api.cu", "factor.cu", "contract.cu", "contract2.cu", "contract2_aux.
 EXPERIMENT_SOURCES = ["contract2_prof.cu", "contract3.cu", "contract4.cu"]
 EXPERIMENTS = os.environ.get("GPFO_BUILD_EXPERIMENTS", "0") not in ("", "0")
 HEADERS = [os.path.join(CSRC, "gpfo_internal.cuh"), os.path.join(CSRC, "contract_common.cuh"), os.path.join(CSRC, "contract2_kernel.cuh"),
-           os.path.join(CSRC, "contract5_kernel.cuh"), os.path.join(HERE, "..", "include", "gpfo.h")]
+           os.path.join(CSRC, "contract5_kernel.cuh"), os.path.join(CSRC, "contract5_mma.inc"), os.path.join(CSRC, "contract5_bwd_kernel.cuh"),
+           os.path.join(CSRC, "ndtr_fast.cuh"), os.path.join(HERE, "..", "include", "gpfo.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "--expt-extended-lambda"] + (["-DGPFO_BUILD_EXPERIMENTS=1"] if EXPERIMENTS else [])
 STAMP = os.path.join(OBJ, ".flavour")

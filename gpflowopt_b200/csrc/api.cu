@@ -44,6 +44,8 @@ struct GpHost {
     double* dpacked_rt = nullptr; size_t cap_packed_rt = 0;
     PackGeom geom_rt;
     bool rt_ready = false;
+    double* dpacked_rt5 = nullptr; size_t cap_packed_rt5 = 0;   // the same stream in 1024-row chunks (tall-chunk backward kernel)
+    PackGeom geom_rt5;
     size_t cap_mf = 0, cap_d = 0, cap_r = 0, cap_alpha = 0, cap_kinv = 0;
     GpDev hdev;
     GpDev* ddev = nullptr;
@@ -189,7 +191,7 @@ static void free_gp(GpHost& g) {
 #ifdef GPFO_BUILD_EXPERIMENTS
     cudaFree(g.dpacked_c[0]); cudaFree(g.dpacked_c[1]);
 #endif
-    cudaFree(g.dpacked_s); cudaFree(g.dpacked_kinv_s); cudaFree(g.dpacked_rt);
+    cudaFree(g.dpacked_s); cudaFree(g.dpacked_kinv_s); cudaFree(g.dpacked_rt); cudaFree(g.dpacked_rt5);
     g = GpHost();
 }
 
@@ -398,11 +400,14 @@ static int ensure_rt(gpfo_ctx* ctx, GpHost& g) {
     if (g.rt_ready) return GPFO_OK;
     cudaStream_t st = ctx->stream;
     g.geom_rt = make_geom(g.Mp / 8, gpfo_contract_bwd_rbc(), 0);
+    g.geom_rt5 = make_geom(g.Mp / 8, gpfo_contract_rbc(20), 0);
     CK(ensure(&g.dpacked_rt, &g.cap_packed_rt, (size_t)pg_total_blocks(g.geom_rt) * 64));
+    CK(ensure(&g.dpacked_rt5, &g.cap_packed_rt5, (size_t)pg_total_blocks(g.geom_rt5) * 64));
     double* tmp = nullptr;
     CK(cudaMalloc((void**)&tmp, (size_t)g.Mf * g.Mf * sizeof(double)));
     gpfo_reverse_transpose(st, g.dLinv, g.Mf, g.Mp, tmp);
     gpfo_pack_linv(st, tmp, g.Mf, g.geom_rt, g.dpacked_rt);
+    gpfo_pack_linv(st, tmp, g.Mf, g.geom_rt5, g.dpacked_rt5);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(tmp);
@@ -722,6 +727,11 @@ static int launch_stored_a(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
     for (int g = 0; g < ctx->ngps; ++g) mp_max = std::max(mp_max, ctx->gps[g].Mp);
     const bool v5_forward = ctx->variant == 0 && D <= gpfo_contract5_max_dim(20) && !getenv("GPFO_GRAD_FWD_V12") &&
                             large_batch_cost(20, mp_max) < large_batch_cost(12, mp_max);
+    // ... and then the backward launch in the same tiling (A in 16-candidate tiles, bulk copies), GPFO_GRAD_BWD_V2=1 keeps round
+    // 1's 64-candidate backward kernel (comparisons)
+    // (measured, profiles/r02_grad_bench_tall_backward.log: 71.3 / 78.0 / 84.0 % of peak at M = 2048 / 4096 / 8192 against
+    // 70.9 / 74.9 / 75.1 %; at M = 1024, one all-triangle chunk whose register-resident epilogue weighs more, 58 % against 62 %)
+    const bool v5_backward = v5_forward && mp_max >= 1536 && gpfo_contract5_bwd_ok(D) && !getenv("GPFO_GRAD_BWD_V2");
     size_t kx_need = 0;
     for (int g = 0; g < ctx->ngps && !v5_forward; ++g) {
         const size_t cols = ((size_t)ctx->gps[g].Mp + 127) / 128 * 128;
@@ -755,7 +765,8 @@ static int launch_stored_a(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
             if (v5_forward) {              // resident-panel forward (no K(X*,X) scratch), same A layout
                 rc = ensure_pack(ctx, ctx->gps[g], gpfo_contract_rbc(20), &gio.packed_o, &gio.geom_o);
                 if (rc != GPFO_OK) return rc;
-                CK(gpfo_contract5_astore_launch(st, gh.kind, gh.ddev, ctx->dprog, gio, ctx->num_sms, D));
+                if (v5_backward) gio.a_stride = gpfo_contract5_astore_stride(gh.Mp / 8);
+                CK(gpfo_contract5_astore_launch(st, gh.kind, gh.ddev, ctx->dprog, gio, ctx->num_sms, D, v5_backward ? 1 : 0));
             } else {
                 CK(gpfo_contract_astore_launch(st, gh.kind, gh.ddev, ctx->dprog, gio, g_s, D));
             }
@@ -783,6 +794,11 @@ static int launch_stored_a(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
             gio.a_scratch = ctx->da_scratch + a_off;
             gio.a_stride = gpfo_contract_astore_stride(gh.Mp / 8);
             a_off += (size_t)slab_tiles * (size_t)gio.a_stride;
+            if (v5_backward) {
+                gio.packed_o = gh.dpacked_rt5; gio.geom_o = gh.geom_rt5;
+                gio.a_stride = gpfo_contract5_astore_stride(gh.Mp / 8);
+                CK(gpfo_contract5_bwd_launch(st, gh.kind, gh.ddev, gio, ctx->num_sms, D));
+            } else
             CK(gpfo_contract_bwd_launch(st, gh.kind, gh.ddev, gio, g_s, D));
             ++launches;
         }

@@ -236,32 +236,8 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             const bool full_chunk = nr == C::RBC;
             const bool last_chunk = p + 1 == geom.nchunks;
 
-            // ---- L^-1 ring.  Block (kp, row block rbl) lives at P(kp) + rbl * 64 doubles, where P advances by nr blocks per dense
-            // column block and by nr - kd - 1 per diagonal one (pg_col_base in closed form).  src_next points at column block
-            // kp_next = (column block being consumed) + KA, already offset to this warp and lane.
-            const double* __restrict__ src_next = packed + pg_chunk_base(geom, p) * 64 + (int64_t)w * 64 + 2 * lane;
-            int kp_next = 0;
-            int ring_off = 0;                         // doubles: quad slot being consumed (and then refilled)
-            // row blocks r < r_hi of this warp exist in this chunk (r * NW + w < nr)
-            const int r_hi = nr > w ? (nr - w + NW - 1) / NW : 0;
-            auto issue_quad = [&](int qd) {           // ring prologue: quad qd of column block kp_next into slot ring_off
-                if (kp_next < kp_end) {
-                    const int t = kp_next - row0 - w + (NW - 1);
-                    const int n_lo = t > 0 ? t / NW : 0;
-                    const unsigned dst = myring_s + ring_off * 8;
-#pragma unroll
-                    for (int i = 0; i < RQ; ++i)
-                        if (qd * RQ + i >= n_lo && qd * RQ + i < r_hi) cp5<ABL>(dst + i * 512, src_next + (qd * RQ + i) * (NW * 64));
-                }
-                cp_async_commit();
-            };
-            auto advance_next = [&]() {
-                const int kd = kp_next - row0;
-                src_next += (kd < 0 ? nr : nr - kd - 1) * 64;
-                ++kp_next;
-            };
-            auto ring_step = [&]() { ring_off = (ring_off == (QD - 1) * RQ * 64) ? 0 : ring_off + RQ * 64; };
-
+            double acc[RBW][NB][2];                  // zeroed right before the column loop (after the deferred epilogue)
+#include "contract5_mma.inc"                          // L^-1 ring + column-block bodies (shared with the backward kernel)
             // ---- K(X*,X) groups: this warp's 8 x 8 tile of dot products on the tensor pipe, then the covariance of its two elements
             auto gen_elems = [&](int g, double* __restrict__ dst) {
                 const int jrow = (g * GK + gen_jb) * 8 + (lane >> 2);       // training point of this lane's A-fragment row = of its outputs
@@ -319,132 +295,10 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             if (p == 0 && w == 0 && prev_n0 >= 0) run_epilogue(prev_n0, par ^ 1);
             if (TIM) t_epi += clock64() - t_mark;
 
-            double acc[RBW][NB][2];
 #pragma unroll
             for (int r = 0; r < RBW; ++r)
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) { acc[r][nb][0] = 0.0; acc[r][nb][1] = 0.0; }
-
-            // One column block: B fragments from the group, A fragments from the ring, up to RBW * 2 * NB DMMAs.
-            // Row block r of this warp (global row block r * NW + w of the chunk) is active in column block kp iff
-            // r_lo(kp) <= r < r_hi, r_lo(kp) = ceil((kp - row0 - w) / NW) clamped at 0: warp-uniform, zero left of the diagonal,
-            // and constant over 16 consecutive diagonal column blocks.
-            //
-            // mma_static<RLO, NEXT_DENSE>: FULL chunks (r_hi == RBW).  Rows RLO .. RBW-1 are active, rows below RLO do not
-            // exist in the instruction stream.  (A predicated-off DMMA still occupies the FP64 tensor pipe for its 16 cycles
-            // -- measured: 1.5 x the useful pipe time with `@P DMMA` in the triangles, profiles/r02_v5_first_*.csv -- so the
-            // triangles are specialised at compile time and dispatched by a warp-uniform switch instead.)
-            // NEXT_DENSE: the column block the ring is refilled for is dense as well: unconditional copies.
-            auto mma_static = [&](const double* __restrict__ kbk, auto rlo_tag, auto next_tag) {
-                constexpr int RLO = decltype(rlo_tag)::value;
-                constexpr bool NEXT_DENSE = decltype(next_tag)::value;
-                double bf[2][NB];
-                if (RLO < RBW) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h)
-#pragma unroll
-                        for (int nb = 0; nb < NB; ++nb) bf[h][nb] = kbk[(h * NB + nb) * 32];
-                }
-                // first row block the NEXT column block (kp_next) keeps: RLO or RLO + 1; none at all past the chunk's end
-                bool has_next = true, keep_first = true;
-                if (!NEXT_DENSE) {
-                    has_next = kp_next < kp_end;
-                    keep_first = (kp_next - row0 - w) <= RLO * NW;                 // ceil((kp_next - row0 - w) / NW) <= RLO
-                }
-#pragma unroll
-                for (int qd = 0; qd < QPC; ++qd) {
-                    if ((qd + 1) * RQ <= RLO) {           // no row block of this quad is left: keep the group count in step
-                        cp_async_commit();
-                        ring_step();
-                        continue;
-                    }
-                    cp_async_wait<QD - 1>();              // this thread's copies of the quad have landed
-                    const unsigned slot = myring_s + ring_off * 8;
-                    double2 a[RQ];
-#pragma unroll
-                    for (int i = 0; i < RQ; ++i)
-                        if (qd * RQ + i >= RLO) a[i] = lds128(slot + i * 512);
-                    // refill the slot just read for column block kp + KA (the loads above precede these asynchronous
-                    // writes in program order; their data returns long before a copy can land)
-#pragma unroll
-                    for (int i = 0; i < RQ; ++i) {
-                        const int r = qd * RQ + i;
-                        if (r > RLO) { if (NEXT_DENSE || has_next) cp5<ABL>(slot + i * 512, src_next + r * (NW * 64)); }
-                        else if (r == RLO) { if (NEXT_DENSE || (has_next && keep_first)) cp5<ABL>(slot + i * 512, src_next + r * (NW * 64)); }
-                    }
-                    cp_async_commit();
-#pragma unroll
-                    for (int h = 0; h < 2; ++h)
-#pragma unroll
-                        for (int i = 0; i < RQ; ++i)
-                            if (qd * RQ + i >= RLO) {
-#pragma unroll
-                                for (int nb = 0; nb < NB; ++nb)
-                                    dmma884v(acc[qd * RQ + i][nb][0], acc[qd * RQ + i][nb][1], h == 0 ? a[i].x : a[i].y, bf[h][nb]);
-                            }
-                    ring_step();
-                }
-                advance_next();
-            };
-            auto mma_diag = [&](const double* __restrict__ kbk, int kp) {      // full chunk, diagonal column block: dispatch on r_lo
-                const int t = kp - row0 - w + (NW - 1);
-                const int r_lo = t > 0 ? t / NW : 0;
-                switch (r_lo) {
-                    case 0: mma_static(kbk, std::integral_constant<int, 0>(), std::false_type()); break;
-                    case 1: mma_static(kbk, std::integral_constant<int, (1 < RBW ? 1 : RBW)>(), std::false_type()); break;
-                    case 2: mma_static(kbk, std::integral_constant<int, (2 < RBW ? 2 : RBW)>(), std::false_type()); break;
-                    case 3: mma_static(kbk, std::integral_constant<int, (3 < RBW ? 3 : RBW)>(), std::false_type()); break;
-                    case 4: mma_static(kbk, std::integral_constant<int, (4 < RBW ? 4 : RBW)>(), std::false_type()); break;
-                    case 5: mma_static(kbk, std::integral_constant<int, (5 < RBW ? 5 : RBW)>(), std::false_type()); break;
-                    case 6: mma_static(kbk, std::integral_constant<int, (6 < RBW ? 6 : RBW)>(), std::false_type()); break;
-                    case 7: mma_static(kbk, std::integral_constant<int, (7 < RBW ? 7 : RBW)>(), std::false_type()); break;
-                    default: mma_static(kbk, std::integral_constant<int, RBW>(), std::false_type()); break;
-                }
-            };
-            // ragged last chunk (r_hi < RBW for some warps): generic bounds, predicated (slower; at most one chunk per tile)
-            auto mma_ragged = [&](const double* __restrict__ kbk, int kp) {
-                double bf[2][NB];
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int nb = 0; nb < NB; ++nb) bf[h][nb] = kbk[(h * NB + nb) * 32];
-                int r_lo, n_lo;
-                { const int t = kp - row0 - w + (NW - 1); r_lo = t > 0 ? t / NW : 0; }
-                { const int t = kp_next - row0 - w + (NW - 1); n_lo = kp_next < kp_end ? (t > 0 ? t / NW : 0) : RBW; }
-#pragma unroll
-                for (int qd = 0; qd < QPC; ++qd) {
-                    if (qd * RQ >= r_hi || (qd + 1) * RQ <= r_lo) {       // no row block of this quad exists here (and none next)
-                        cp_async_commit();
-                        ring_step();
-                        continue;
-                    }
-                    cp_async_wait<QD - 1>();
-                    const unsigned slot = myring_s + ring_off * 8;
-                    double2 a[RQ];
-#pragma unroll
-                    for (int i = 0; i < RQ; ++i) {
-                        if (qd * RQ + i >= r_lo && qd * RQ + i < r_hi) a[i] = lds128(slot + i * 512);
-                        else a[i] = make_double2(0.0, 0.0);
-                    }
-#pragma unroll
-                    for (int i = 0; i < RQ; ++i)
-                        if (qd * RQ + i >= n_lo && qd * RQ + i < r_hi)
-                            cp5<ABL>(slot + i * 512, src_next + (qd * RQ + i) * (NW * 64));
-                    cp_async_commit();
-#pragma unroll
-                    for (int h = 0; h < 2; ++h)
-#pragma unroll
-                        for (int i = 0; i < RQ; ++i) {
-                            if (qd * RQ + i >= r_lo && qd * RQ + i < r_hi) {
-#pragma unroll
-                                for (int nb = 0; nb < NB; ++nb)
-                                    dmma884v(acc[qd * RQ + i][nb][0], acc[qd * RQ + i][nb][1], h == 0 ? a[i].x : a[i].y, bf[h][nb]);
-                            }
-                        }
-                    ring_step();
-                }
-                advance_next();
-            };
 
             for (int g = 0; g < ngroups; ++g) {
                 const int gg = g + la;
@@ -491,7 +345,10 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 // stored-A gradient pass: park A = L^-1 Kx of this chunk for the backward launch, which walks 64-candidate
                 // tiles: reversed row order, B-fragment group layout of contract2_kernel (8 column blocks of 8 candidate
                 // blocks per group); this tile fills candidate blocks NB * (tile % (8 / NB)) .. of 64-candidate tile tile / (8 / NB)
-                constexpr int TPB = 8 / NB;                 // tiles of this kernel per 64-candidate tile
+                // (bit 512: the tall-chunk backward kernel reads 16-candidate tiles: NB candidate blocks per group, own tile stride)
+                constexpr bool NATIVE = (ABL & 512) != 0;
+                constexpr int TPB = NATIVE ? 1 : 8 / NB;    // tiles of this kernel per tile of the backward launch
+                constexpr int NBB = NATIVE ? NB : 8;        // candidate blocks per group in the scratch layout
                 double* const at = io.a_scratch + (size_t)(tile / TPB) * io.a_stride;
                 const int nb0 = (int)(tile % TPB) * NB;
                 const int i8 = 7 - (lane >> 2);
@@ -500,8 +357,8 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                     const int rbl = r * NW + w;
                     if (rbl < nr) {
                         const int rbrev = geom.nrb - 1 - (row0 + rbl);
-                        double* const o = at + (size_t)(rbrev >> 3) * (KPC * 2 * 8 * 32) +
-                                          (((rbrev & 7) * 2 + (i8 >> 2)) * 8 + nb0) * 32 + (i8 & 3) + 8 * (lane & 3);
+                        double* const o = at + (size_t)(rbrev >> 3) * (KPC * 2 * NBB * 32) +
+                                          (((rbrev & 7) * 2 + (i8 >> 2)) * NBB + nb0) * 32 + (i8 & 3) + 8 * (lane & 3);
 #pragma unroll
                         for (int nb = 0; nb < NB; ++nb) {
                             __stcg(o + nb * 32, acc[r][nb][0]);

@@ -353,7 +353,10 @@ int gpfo_contract3_clusters(int64_t N, int num_sms);
 // contract5.cu (resident-panel kernel)
 int gpfo_contract5_max_dim(int variant);
 cudaError_t gpfo_contract5_astore_launch(cudaStream_t st, int kind, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io,
-                                         int num_sms, int D);
+                                         int num_sms, int D, int native);
+cudaError_t gpfo_contract5_bwd_launch(cudaStream_t st, int kind, const GpDev* d_gp, EvalIO io, int num_sms, int D);
+int gpfo_contract5_bwd_ok(int D);
+long long gpfo_contract5_astore_stride(int nrb);
 // Kinv = Linv^T Linv (Mf x Mf, full symmetric) and alpha = Linv^T V, for the gradient pass
 void gpfo_kinv_alpha(cudaStream_t st, const double* dLinv, int Mf, const double* dV, int R, double* dKinv, double* dalpha);
 void gpfo_prepare_inputs(cudaStream_t st, const double* dX, int M, int Mp, int D, const double* d_ell,
