@@ -729,9 +729,10 @@ static int launch_stored_a(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
                             large_batch_cost(20, mp_max) < large_batch_cost(12, mp_max);
     // ... and then the backward launch in the same tiling (A in 16-candidate tiles, bulk copies), GPFO_GRAD_BWD_V2=1 keeps round
     // 1's 64-candidate backward kernel (comparisons)
-    // (measured, profiles/r02_grad_bench_tall_backward.log: 71.3 / 78.0 / 84.0 % of peak at M = 2048 / 4096 / 8192 against
-    // 70.9 / 74.9 / 75.1 %; at M = 1024, one all-triangle chunk whose register-resident epilogue weighs more, 58 % against 62 %)
-    const bool v5_backward = v5_forward && mp_max >= 1536 && gpfo_contract5_bwd_ok(D) && !getenv("GPFO_GRAD_BWD_V2");
+    // (measured, profiles/r02_grad_bench_tall_backward.log: stored-A total 63.1 / 75.2 / 79.9 / 85.1 % of peak at M = 1024 / 2048 /
+    // 4096 / 8192 against 62.0 / 70.9 / 74.9 / 75.1 % with the 64-candidate backward kernel)
+    static const int bwd5_min_m = getenv("GPFO_BWD5_MIN_M") ? atoi(getenv("GPFO_BWD5_MIN_M")) : 1024;
+    const bool v5_backward = v5_forward && mp_max >= bwd5_min_m && gpfo_contract5_bwd_ok(D) && !getenv("GPFO_GRAD_BWD_V2");
     size_t kx_need = 0;
     for (int g = 0; g < ctx->ngps && !v5_forward; ++g) {
         const size_t cols = ((size_t)ctx->gps[g].Mp + 127) / 128 * 128;
@@ -938,7 +939,11 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     // GPFO_ASTORE_MIN_N moves the threshold.
     if (want_grad && ctx->variant == 0 && variant != 12) {
         const char* e = getenv("GPFO_ASTORE_MIN_N");
-        const int64_t min_n = e ? atoll(e) : (int64_t)40 * ctx->num_sms;
+        // both launches of the pass on 16-candidate tiles (tall-chunk kernels): worth it from one wave of such tiles
+        // (profiles/r02_grad_mid_stored_a.log: x1.0-1.6 over the dense pass for N = 2.4e3 ... 4.7e3, x1.3-1.8 from 1.2e4)
+        const bool tall = mp_max >= 1024 && D <= gpfo_contract5_max_dim(20) && gpfo_contract5_bwd_ok(D) &&
+                          large_batch_cost(20, mp_max) < large_batch_cost(12, mp_max);
+        const int64_t min_n = e ? atoll(e) : (int64_t)(tall ? 16 : 40) * ctx->num_sms;
         if (N >= min_n && D <= gpfo_contract5_max_dim(20)) variant = 12;
     }
     const bool use_cluster = variant == 10;

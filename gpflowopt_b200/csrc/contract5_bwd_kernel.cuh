@@ -31,8 +31,8 @@ struct Contract5BwdCfg {
         return ((size_t)F::NW * F::RING_DOUBLES_PER_WARP + (size_t)(F::RG + nbuf) * F::GROUP_SLOTS + 2 * (size_t)DP * F::T +
                 2 * F::T * (RMAX + 2) + (size_t)F::T * (1 + D) + 34) * sizeof(double) + (size_t)(F::RG + 2 * F::NBUF_MAX) * 8;
     }
-    // per-warp partial tiles of one chunk epilogue live in the drained ring: NB * ceil((1+D)/8) tiles of 64 doubles per warp
-    static bool fits(int D) { return NB * ((1 + D + 7) / 8) * 64 <= F::RING_DOUBLES_PER_WARP; }
+        // the chunk epilogue keeps four column blocks of Xa = [1, Xs] per pass
+    static bool fits(int D) { return (1 + D + 7) / 8 <= 4; }
 };
 
 template <int RBW, int NB, int QD, int KIND, int ABL = 0>
@@ -208,79 +208,89 @@ contract5_bwd_kernel(const GpDev* __restrict__ gpp, EvalIO io, int nbuf) {
             }
             cp_async_wait<0>();
 
-            // ---- chunk epilogue, in registers.  acc[r][nb][c] = W[i'][n], i' = 8 (row0 + r NW + w) + lane / 4,
-            // n = 8 nb + 2 (lane % 4) + c; training point gi = rev - i'.
-            double* const part = ring + (size_t)w * C::RING_DOUBLES_PER_WARP;      // this warp's partial tiles (drained ring)
+            // ---- chunk epilogue.  acc[r][nb][c] = W[i'][n], i' = 8 (row0 + r NW + w) + lane / 4, n = 8 nb + 2 (lane % 4) + c;
+            // training point gi = rev - i'.  One pass per candidate block nb: the warp parks that half of its accumulators in its
+            // own (drained) ring region and walks its row blocks in a compact loop -- no 16-fold unrolled body, no spills.
+            double* const wreg = ring + (size_t)w * C::RING_DOUBLES_PER_WARP;      // this warp's 4 KB: accumulators, then partial tiles
             // shuffle sources that turn an accumulator-layout tile into B fragments: lane l' needs element
             // (row 4h + l' % 4, column l' / 4), held by lane 4 (4h + l' % 4) + (l' / 4) / 2 in register c = (l' / 4) % 2
             const int src0 = 4 * (lane & 3) + (lane >> 3), src1 = src0 + 16;
             const bool odd = ((lane >> 2) & 1) != 0;
-            for (int db = 0; db < ND; db += 2) {          // two column blocks of Xa per sweep over the rows (D <= 14: one sweep)
+            const int nrw = nr > w ? (nr - w + NW - 1) / NW : 0;                   // row blocks of this warp in the chunk
 #pragma unroll
-                for (int nb = 0; nb < NB; ++nb) {
-                    double gt[2][2];                      // G^T partial tiles [column block db + q][c] of candidate block nb
-                    gt[0][0] = gt[0][1] = gt[1][0] = gt[1][1] = 0.0;
-                    const double* gn0 = gc + (8 * nb + 2 * (lane & 3)) * (RMAX + 2);        // this lane's two candidates
+            for (int nb = 0; nb < NB; ++nb) {
+                static_assert(RBW * 2 * 32 <= C::RING_DOUBLES_PER_WARP, "a candidate block's accumulators fit the warp's ring region");
 #pragma unroll
-                    for (int r = 0; r < RBW; ++r) {
-                        const int rbl = r * NW + w;
-                        if (rbl >= nr) continue;          // warp-uniform
-                        const int gs = 8 * (row0 + rbl);  // first stream row of the block
-                        const int gi = rev - (gs + (lane >> 2));                   // accumulator-layout row of this lane
-                        // dot products Xs_gi . xc_n on the tensor pipe, in the accumulator layout
-                        double d0 = 0.0, d1 = 0.0;
-                        {
-                            const double* __restrict__ xrow = Xs + (size_t)gi * D + (lane & 3);
-                            const double* __restrict__ xcol = xc + (lane & 3) * T + 8 * nb + (lane >> 2);
-                            for (int k = 0; k < DP; k += 4) {
-                                const double a = (k + (lane & 3) < D) ? __ldg(xrow + k) : 0.0;
-                                dmma884(d0, d1, a, xcol[k * T]);
-                            }
+                for (int r = 0; r < RBW; ++r)
+                    *reinterpret_cast<double2*>(wreg + (r * 32 + lane) * 2) = make_double2(acc[r][nb][0], acc[r][nb][1]);
+                __syncwarp();
+                const double* gn0 = gc + (8 * nb + 2 * (lane & 3)) * (RMAX + 2);            // this lane's two candidates
+                const double cv0 = gn0[RMAX], cv1 = gn0[RMAX + 2 + RMAX], x20 = gn0[RMAX + 1], x21 = gn0[RMAX + 2 + RMAX + 1];
+                const double* __restrict__ xcol = xc + (lane & 3) * T + 8 * nb + (lane >> 2);
+                double gt[4][2];                          // G^T partial tiles [column block of Xa][c] (ND <= 4)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { gt[q][0] = 0.0; gt[q][1] = 0.0; }
+#pragma unroll 4
+                for (int r = 0; r < nrw; ++r) {
+                    const int gs = 8 * (row0 + r * NW + w);                        // first stream row of the block
+                    const int gi = rev - (gs + (lane >> 2));                       // accumulator-layout row of this lane
+                    // dot products Xs_gi . xc_n on the tensor pipe, in the accumulator layout
+                    double d0 = 0.0, d1 = 0.0;
+                    {
+                        const double* __restrict__ xrow = Xs + (size_t)gi * D + (lane & 3);
+                        for (int k = 0; k < DP; k += 4) {
+                            const double a = (k + (lane & 3) < D) ? __ldg(xrow + k) : 0.0;
+                            dmma884(d0, d1, a, xcol[k * T]);
                         }
-                        const double xnj = __ldg(xn + gi);
-                        double u0 = gn0[RMAX] * acc[r][nb][0], u1 = gn0[RMAX + 2 + RMAX] * acc[r][nb][1];
-                        for (int ro = 0; ro < R; ++ro) {
-                            const double al = __ldg(gp.alpha + (size_t)gi * R + ro);
-                            u0 = fma(gn0[ro], al, u0);
-                            u1 = fma(gn0[RMAX + 2 + ro], al, u1);
-                        }
-                        u0 *= dk_dr2_branchless<KIND>(variance, (-2.0 * d0 + xnj) + gn0[RMAX + 1], tab32);
-                        u1 *= dk_dr2_branchless<KIND>(variance, (-2.0 * d1 + xnj) + gn0[RMAX + 2 + RMAX + 1], tab32);
+                    }
+                    const double xnj = __ldg(xn + gi);
+                    const double2 av = *reinterpret_cast<const double2*>(wreg + (r * 32 + lane) * 2);
+                    double u0 = cv0 * av.x, u1 = cv1 * av.y;
+                    for (int ro = 0; ro < R; ++ro) {
+                        const double al = __ldg(gp.alpha + (size_t)gi * R + ro);
+                        u0 = fma(gn0[ro], al, u0);
+                        u1 = fma(gn0[RMAX + 2 + ro], al, u1);
+                    }
+                    u0 *= dk_dr2_branchless<KIND>(variance, (-2.0 * d0 + xnj) + x20, tab32);
+                    u1 *= dk_dr2_branchless<KIND>(variance, (-2.0 * d1 + xnj) + x21, tab32);
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int src = h ? src1 : src0;
-                            const double v0 = __shfl_sync(0xffffffffu, u0, src), v1 = __shfl_sync(0xffffffffu, u1, src);
-                            const double b = odd ? v1 : v0;
-                            // A fragments of the G^T product: Xa^T[c'][i], c' = 8 (db + q) + lane / 4, i = 4 h + lane % 4
-                            const int gk = rev - (gs + 4 * h + (lane & 3));
+                    for (int h = 0; h < 2; ++h) {
+                        const int src = h ? src1 : src0;
+                        const double v0 = __shfl_sync(0xffffffffu, u0, src), v1 = __shfl_sync(0xffffffffu, u1, src);
+                        const double b = odd ? v1 : v0;
+                        // A fragments of the G^T product: Xa^T[c'][i], c' = 8 q + lane / 4, i = 4 h + lane % 4
+                        const double* __restrict__ xk = Xs + (size_t)(rev - (gs + 4 * h + (lane & 3))) * D;
 #pragma unroll
-                            for (int q = 0; q < 2; ++q) {
-                                const int cq = 8 * (db + q) + (lane >> 2);
-                                const double xa = cq == 0 ? 1.0 : ((cq <= D) ? __ldg(Xs + (size_t)gk * D + cq - 1) : 0.0);
-                                if (q == 0 || db + 1 < ND) dmma884(gt[q][0], gt[q][1], xa, b);
+                        for (int q = 0; q < 4; ++q) {
+                            if (q < ND) {                 // warp-uniform
+                                const int cq = 8 * q + (lane >> 2);
+                                const double xa = cq == 0 ? 1.0 : ((cq <= D) ? __ldg(xk + cq - 1) : 0.0);
+                                dmma884(gt[q][0], gt[q][1], xa, b);
                             }
                         }
                     }
-                    // gt[q] holds G^T[c' = 8 (db + q) + lane / 4][n = 8 nb + 2 (lane % 4) + c]
-#pragma unroll
-                    for (int q = 0; q < 2; ++q)
-                        if (db + q < ND) {
-                            double* o = part + ((db + q) * NB + nb) * 64 + (lane >> 2) * 8 + 2 * (lane & 3);
-                            o[0] = gt[q][0]; o[1] = gt[q][1];
-                        }
                 }
+                __syncwarp();                             // every lane has read its accumulators back: the region is free
+                // gt[q] holds G^T[c' = 8 q + lane / 4][n = 8 nb + 2 (lane % 4) + c]
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (q < ND) {
+                        double* o = wreg + q * 64 + (lane >> 2) * 8 + 2 * (lane & 3);
+                        o[0] = gt[q][0]; o[1] = gt[q][1];
+                    }
+                __syncthreads();                          // (first pass: also every warp past its column loop)
+                for (int e = tid; e < 8 * (1 + D); e += C::THREADS) {              // thread (n, c') of this candidate block: fixed warp order
+                    const int nl = e / (1 + D), cq = e - nl * (1 + D);
+                    const int off = (cq >> 3) * 64 + (cq & 7) * 8 + nl;
+                    const int ge = (8 * nb + nl) * (1 + D) + cq;
+                    double a = gsum[ge];
+                    for (int ww = 0; ww < NW; ++ww) a += ring[(size_t)ww * C::RING_DOUBLES_PER_WARP + off];
+                    gsum[ge] = a;
+                }
+                if (nb == NB - 1 && last_chunk && tile + gridDim.x < ntiles && tid >= C::THREADS / 2)
+                    stage_tile(tile + gridDim.x, par ^ 1, C::THREADS / 2, C::THREADS / 2);
+                __syncthreads();
             }
-            __syncthreads();                              // every warp past its column loop and its partial tiles written
-            for (int e = tid; e < T * (1 + D); e += C::THREADS) {           // thread (n, c'): fixed warp order -> deterministic
-                const int n = e / (1 + D), cq = e - n * (1 + D);
-                const int off = ((cq >> 3) * NB + (n >> 3)) * 64 + (cq & 7) * 8 + (n & 7);
-                double a = gsum[e];
-                for (int ww = 0; ww < NW; ++ww) a += ring[(size_t)ww * C::RING_DOUBLES_PER_WARP + off];
-                gsum[e] = a;
-            }
-            if (last_chunk && tile + gridDim.x < ntiles && tid >= C::THREADS / 2)
-                stage_tile(tile + gridDim.x, par ^ 1, C::THREADS / 2, C::THREADS / 2);
-            __syncthreads();
         }
         // d acq / d x_d = 2 a_d / l_d * (xs_d * G[n][0] - G[n][1 + d])
         for (int e = tid; e < T * D; e += C::THREADS) {

@@ -29,7 +29,7 @@ def main():
                     wr.writerow([li, h, u, v])
     src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
     srows = list(csv.reader(src.splitlines()))
-    body = [r for r in srows[2:] if len(r) > 5]
+    body = [r for r in srows[2:] if len(r) > 5 and (r[2] or '0').isdigit()]      # (a report with several launches repeats its header rows)
     tot = sum(int(r[2] or 0) for r in body) or 1
     ranked = sorted(range(len(body)), key=lambda i: -int(body[i][2] or 0))[:60]
     with open(out + '.hot_sass.csv', 'w', newline='') as f:
