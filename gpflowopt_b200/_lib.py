@@ -18,7 +18,7 @@ EXPORTS = ["gpfo_version", "gpfo_ctx_create", "gpfo_ctx_destroy", "gpfo_last_err
            "gpfo_gp_set", "gpfo_gp_count_set", "gpfo_gp_get_factor", "gpfo_program_set", "gpfo_cells_set",
            "gpfo_eval", "gpfo_predict", "gpfo_timings_get", "gpfo_set_variant", "gpfo_measure_dmma_peak",
            "gpfo_measure_fp64_pipes", "gpfo_pareto_cells", "gpfo_eval_random", "gpfo_random_rows", "gpfo_ndtr_fast_host",
-           "gpfo_non_dominated_sort", "gpfo_select_variant"]
+           "gpfo_non_dominated_sort", "gpfo_select_variant", "gpfo_mt19937_design_rows"]
 
 
 class Timings(ctypes.Structure):
@@ -80,6 +80,7 @@ def load():
     lib.gpfo_ndtr_fast_host.argtypes = [c_dp, ctypes.c_int64, c_dp]
     lib.gpfo_non_dominated_sort.argtypes = [c_dp, ctypes.c_int64, ctypes.c_int, c_dp]
     lib.gpfo_select_variant.argtypes = [vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int)]
+    lib.gpfo_mt19937_design_rows.argtypes = [c_dp, ctypes.POINTER(ctypes.c_int32), ctypes.c_int64, ctypes.c_int, c_dp, c_dp, c_dp]
     lib.gpfo_pareto_cells.argtypes = [c_dp, c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_double, c_dp, c_dp, ctypes.c_int64,
                                       ctypes.POINTER(ctypes.c_int64)]
     for name in EXPORTS:
@@ -99,6 +100,27 @@ def _f64(a, shape=None):
     if shape is not None:
         a = a.reshape(shape)
     return a
+
+
+def numpy_stream_design_rows(n, scale, shift, out=None):
+    """``np.random.rand(n, D) * scale + shift`` drawn natively from -- and advancing -- NumPy's global legacy RandomState
+    (csrc/pareto_host.cu::gpfo_mt19937_design_rows): the same bytes, about 4 x faster.  Returns None when the global generator
+    is not the MT19937 RandomState (then the caller falls back to NumPy)."""
+    state = np.random.get_state()
+    if state[0] != 'MT19937':
+        return None
+    lib = load()
+    scale, shift = _f64(scale).ravel(), _f64(shift).ravel()
+    key = np.ascontiguousarray(state[1], dtype=np.uint32).copy()
+    pos = ctypes.c_int32(int(state[2]))
+    if out is None:
+        out = np.empty((int(n), scale.size))
+    assert out.shape == (int(n), scale.size) and out.dtype == np.float64 and out.flags.c_contiguous
+    st = lib.gpfo_mt19937_design_rows(_ptr(key), ctypes.byref(pos), int(n), scale.size, _ptr(scale), _ptr(shift), _ptr(out) if n else None)
+    if st != OK:
+        raise GpfoError(st, "gpfo_mt19937_design_rows failed")
+    np.random.set_state((state[0], key, pos.value) + tuple(state[3:]))
+    return out
 
 
 def non_dominated_counts(Y):

@@ -123,3 +123,55 @@ extern "C" int gpfo_non_dominated_sort(const double* Y, int64_t n, int R, int64_
     }
     return GPFO_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Candidate rows of RandomDesign (gpflowopt/design.py:55-70, 83-94) for the multi-GPU Monte-Carlo route, where rank 0 alone
+// draws the reference's single np.random stream: n x D doubles of np.random.rand -- MT19937, 53-bit doubles
+// (a >> 5, b >> 6 of two consecutive 32-bit outputs: (a * 2^26 + b) / 2^53) -- continued from the caller's RandomState
+// (key[624], pos as np.random.get_state() returns them; both are updated so that np.random.set_state resumes the stream),
+// with the design's diagonal map x * scale[d] + shift[d] applied in the same pass.  Bit-identical to
+// np.random.rand(n, D) * scale + shift; about 4 x faster than NumPy's generator plus two more passes over the array, which
+// at 1e7 x 16 is what bounds the wall time of BASELINE configs[2] on 8 GPUs.
+// ------------------------------------------------------------------------------------------------------------------------
+static inline void mt19937_refill(uint32_t* mt) {
+    const int N = 624, Mm = 397;
+    const uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, MAT = 0x9908b0dfu;
+    int kk = 0;
+    for (; kk < N - Mm; ++kk) {
+        const uint32_t y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
+        mt[kk] = mt[kk + Mm] ^ (y >> 1) ^ ((y & 1u) ? MAT : 0u);
+    }
+    for (; kk < N - 1; ++kk) {
+        const uint32_t y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
+        mt[kk] = mt[kk + (Mm - N)] ^ (y >> 1) ^ ((y & 1u) ? MAT : 0u);
+    }
+    const uint32_t y = (mt[N - 1] & UPPER) | (mt[0] & LOWER);
+    mt[N - 1] = mt[Mm - 1] ^ (y >> 1) ^ ((y & 1u) ? MAT : 0u);
+}
+static inline uint32_t mt19937_temper(uint32_t y) {
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+extern "C" int gpfo_mt19937_design_rows(uint32_t* key, int32_t* pos, int64_t n, int D, const double* scale, const double* shift,
+                                        double* out) {
+    if (!key || !pos || !out || n < 0 || D < 1 || *pos < 0 || *pos > 624) return GPFO_ERR_BAD_SHAPE;
+    int p = *pos;
+    const int64_t total = n * D;
+    int d = 0;
+    for (int64_t e = 0; e < total; ++e) {
+        if (p >= 624) { mt19937_refill(key); p = 0; }
+        const uint32_t a = mt19937_temper(key[p++]) >> 5;
+        if (p >= 624) { mt19937_refill(key); p = 0; }
+        const uint32_t b = mt19937_temper(key[p++]) >> 6;
+        double v = (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);   // division by 2^53 == multiplication by 2^-53, exactly
+        if (scale) v = v * scale[d];                 // separate roundings, as NumPy's multiply then add (this translation unit is
+        if (shift) v = v + shift[d];                 // host code compiled for baseline x86-64: no FMA contraction)
+        out[e] = v;
+        if (++d == D) d = 0;
+    }
+    *pos = p;
+    return GPFO_OK;
+}

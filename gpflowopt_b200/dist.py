@@ -78,6 +78,14 @@ def scatter_points(points):
     return (block if block.is_cuda else block.numpy()), lo, n
 
 
+def _produce_into(produce, first, count, out):
+    """``produce(first, count, out=out)`` when the producer takes a destination buffer, ``produce(first, count)`` otherwise."""
+    try:
+        return produce(first, count, out=out)
+    except TypeError:
+        return produce(first, count)
+
+
 def pipelined_argmax(n_total, d, produce, score, rounds=8, on_chunk_rows=None):
     """The reference's single-stream candidate route under data parallelism (gpflowopt/design.py:55-70, 83-94;
     optim.py:152-164), pipelined: ONLY rank 0 produces rows -- in order, ``produce(first_row, count)`` returns rows
@@ -117,15 +125,26 @@ def pipelined_argmax(n_total, d, produce, score, rounds=8, on_chunk_rows=None):
             best[:] = [v, first_row + i, np.array(row.cpu().numpy() if hasattr(row, 'cpu') else row, dtype=np.float64)]
 
     worker = None
+    staging = None
     for q in range(rounds):
         first = q * ws * C                                             # first global row of this round
         out = torch.empty((C, d), dtype=torch.float64, device=dev)
         chunks = None
         if rank == 0:
             count = max(0, min(n_total - first, ws * C))
-            full = torch.zeros((ws * C, d), dtype=torch.float64, device=dev)
-            if count > 0:
-                full[:count] = torch.from_numpy(np.ascontiguousarray(produce(first, count), dtype=np.float64)).to(dev)
+            if dev.type == "cuda":                  # rows are produced straight into a pinned staging buffer (reused every round)
+                if staging is None:
+                    staging = torch.empty((ws * C, d), dtype=torch.float64, pin_memory=True)
+                rows = _produce_into(produce, first, count, staging.numpy()[:count]) if count > 0 else None
+                if rows is not None and rows is not staging.numpy() and not np.shares_memory(rows, staging.numpy()):
+                    staging.numpy()[:count] = rows
+                if count < ws * C:
+                    staging.numpy()[count:] = 0.0
+                full = staging.to(dev, non_blocking=True)
+            else:
+                full = torch.zeros((ws * C, d), dtype=torch.float64, device=dev)
+                if count > 0:
+                    full[:count] = torch.from_numpy(np.ascontiguousarray(produce(first, count), dtype=np.float64))
             chunks = list(full.split(C))
         td.scatter(out, scatter_list=chunks, src=0)
         mine = first + rank * C

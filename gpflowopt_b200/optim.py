@@ -97,17 +97,26 @@ class MCOptimizer(Optimizer):
     def _get_eval_points(self):
         return RandomDesign(self._nsamples, self.domain).generate()
 
-    def _get_eval_rows(self, first_row, count):
-        """Rows [first_row, first_row + count) of the candidate set, for the pipelined multi-GPU route.  Successive calls
+    def _get_eval_rows(self, first_row, count, out=None):
+        """Rows [first_row, first_row + count) of the candidate set, for the pipelined multi-GPU route (written into ``out``,
+        e.g. a pinned staging buffer, when one is given).  Successive calls
         continue np.random's stream, so the chunks concatenate to exactly what one ``_get_eval_points()`` call draws: the same
         ``np.random.rand`` numbers through the same diagonal map (gpflowopt/design.py:55-70, 83-94).  The two ``in domain``
         asserts of ``Design.generate`` are not repeated per chunk: U[0, 1) mapped affinely onto the box is inside it by
         construction, and at 1e7 x 16 those two passes cost more host time than the draw itself."""
         design = RandomDesign(count, self.domain)
         scale, shift = (design.generative_domain >> self.domain).diagonal()
+        if type(design).create_design is RandomDesign.create_design:
+            from ._lib import numpy_stream_design_rows
+            X = numpy_stream_design_rows(count, scale, shift, out)     # np.random's own stream, drawn natively (same bytes)
+            if X is not None:
+                return X
         X = design.create_design()
         np.multiply(X, scale, out=X)               # in place: the same products and sums, without two more N x D temporaries
         np.add(X, shift, out=X)
+        if out is not None:
+            out[...] = X
+            return out
         return X
 
     def _optimize_device_rng(self, objective, acq):
@@ -188,7 +197,7 @@ class CandidateOptimizer(MCOptimizer):
     def _get_eval_points(self):
         return self.candidates
 
-    def _get_eval_rows(self, first_row, count):
+    def _get_eval_rows(self, first_row, count, out=None):
         return self.candidates[first_row:first_row + count]
 
     @property

@@ -187,6 +187,12 @@ int gpfo_pareto_cells(const double* front, const int32_t* order, int P, int R, d
  *   Y          n x R objective rows;   dominance[i] receives the number of rows dominating row i (front: == 0). */
 int gpfo_non_dominated_sort(const double* Y, int64_t n, int R, int64_t* dominance);
 
+/* Host-side candidate source of the multi-GPU Monte-Carlo route: n x D doubles of np.random.rand (MT19937, 53-bit) continued from
+ * the caller's RandomState (key[624], *pos as np.random.get_state() returns them; both updated), mapped x * scale[d] + shift[d]
+ * (either may be NULL) in the same pass.  Replaces: RandomDesign.generate (design.py:55-70, 83-94), bit for bit. */
+int gpfo_mt19937_design_rows(uint32_t* key, int32_t* pos, int64_t n, int D, const double* scale, const double* shift,
+                             double* out);
+
 /* Host evaluation of the branch-free Normal CDF the HVPoI Phi table uses on the device (csrc/ndtr_fast.cuh; replaces
    tf.contrib.distributions.Normal.cdf at hvpoi.py:112-113).  Same source compiled for the host: lets the CPU tests pin its
    accuracy against scipy.special.ndtr without a GPU.  Needs no ctx. */

@@ -94,3 +94,26 @@ def test_fast_normal_cdf_of_the_hvpoi_kernel(libgpfo):
     for zz in (-35.0, -20.0, -8.3, -1.0, -0.3, 0.3, 1.0, 5.0):
         true = float(mp.ncdf(mp.mpf(zz)))
         assert abs(_lib.ndtr_fast_host([zz])[0] - true) <= 2e-14 * true + 3e-17
+
+
+def test_native_numpy_stream_design_rows_are_np_random_rand(libgpfo):
+    """gpfo_mt19937_design_rows continues np.random's global MT19937 stream: the rows equal RandomDesign.generate() on the same
+    seed bit for bit (any chunking, odd stream positions, a buffer handed in) and np.random resumes where NumPy itself would
+    (gpflowopt/design.py:55-70, 83-94)."""
+    from gpflowopt_b200.design import RandomDesign
+    from gpflowopt_b200.domain import ContinuousParameter
+    from gpflowopt_b200.optim import MCOptimizer
+    dom = np.sum([ContinuousParameter("x%d" % i, -5 + i, 10 + 0.37 * i) for i in range(5)])
+    for seed, sizes in ((0, (4000,)), (3, (1, 7, 1000, 2992)), (12345, (311, 312, 313, 3064))):
+        np.random.seed(seed)
+        np.random.rand(seed % 3 + 1)                         # odd / even position inside the 624-word block
+        ref = RandomDesign(sum(sizes), dom).generate()
+        after_ref = np.random.rand(4)
+        np.random.seed(seed)
+        np.random.rand(seed % 3 + 1)
+        opt = MCOptimizer(dom, sum(sizes))
+        buf = np.empty((sizes[0], 5))
+        rows = [opt._get_eval_rows(0, sizes[0], out=buf).copy()] + [opt._get_eval_rows(0, k) for k in sizes[1:]]
+        assert np.array_equal(np.vstack(rows), ref)
+        assert np.array_equal(np.random.rand(4), after_ref)
+        assert ref in dom
