@@ -273,6 +273,10 @@ def sub_config3_constrained(torch, td, gpfo, world, rank, barrier):
            "flop_per_candidate": 2 * M3 * (M3 + 1)}
     winners = {}
     for key, opt in (("host_candidates", MCOptimizer(dom, N3)), ("device_rng", MCOptimizer(dom, N3, device_rng=True))):
+        # warm-up on a small candidate set (as the W warm-up steps of the headline): the first scatter of a process pays NCCL's
+        # lazy point-to-point connection set-up (about 1.1 s on 8 GPUs, once per process, not per BO iteration)
+        np.random.seed(1)
+        MCOptimizer(dom, 65536, device_rng=(key == "device_rng")).optimize(_InverseAcquisition(joint, False))
         np.random.seed(4321)
         ctx.reset_cum()
         barrier()

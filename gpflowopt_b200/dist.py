@@ -126,7 +126,10 @@ def pipelined_argmax(n_total, d, produce, score, rounds=8, on_chunk_rows=None):
 
     worker = None
     staging = None
+    import os, time
+    debug = os.environ.get("GPFO_DIST_DEBUG") and rank == 0
     for q in range(rounds):
+        t_round = time.perf_counter()
         first = q * ws * C                                             # first global row of this round
         out = torch.empty((C, d), dtype=torch.float64, device=dev)
         chunks = None
@@ -140,19 +143,29 @@ def pipelined_argmax(n_total, d, produce, score, rounds=8, on_chunk_rows=None):
                     staging.numpy()[:count] = rows
                 if count < ws * C:
                     staging.numpy()[count:] = 0.0
+                t_prod = time.perf_counter()
                 full = staging.to(dev, non_blocking=True)
             else:
                 full = torch.zeros((ws * C, d), dtype=torch.float64, device=dev)
                 if count > 0:
                     full[:count] = torch.from_numpy(np.ascontiguousarray(produce(first, count), dtype=np.float64))
             chunks = list(full.split(C))
+        t_sc0 = time.perf_counter()
         td.scatter(out, scatter_list=chunks, src=0)
+        if debug:
+            torch.cuda.synchronize() if dev.type == "cuda" else None
+            print("round %d: produce %.3f s, h2d issue %.3f s, scatter %.3f s" % (
+                q, (t_prod if dev.type == "cuda" else t_sc0) - t_round, t_sc0 - (t_prod if dev.type == "cuda" else t_sc0),
+                time.perf_counter() - t_sc0), flush=True)
         mine = first + rank * C
         count = max(0, min(n_total - mine, C))
         block = out if out.is_cuda else out.numpy()
         if rank == 0:                                                 # score while the next round is being produced
             if worker is not None:
+                t_j = time.perf_counter()
                 worker.join()
+                if debug:
+                    print("          join of the previous scoring thread %.3f s" % (time.perf_counter() - t_j), flush=True)
             worker = threading.Thread(target=fold, args=(block, mine, count))
             worker.start()
         else:
