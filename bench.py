@@ -348,12 +348,17 @@ def sub_config5_sweep(gpfo, peak):
         Xc = synthetic.candidates(n, D)
         acq.argmax(Xc[:65536])
         ctx = acq._get_engine().ctx
-        acq.argmax(Xc)
-        t = ctx.timings()
+        t = tg = None
+        for _ in range(3):                               # best of three (the first call after host-side set-up sees ramping clocks)
+            acq.argmax(Xc)
+            if t is None or ctx.timings()["eval_ms"] < t["eval_ms"]:
+                t = ctx.timings()
         tf = n * Ms * (Ms + 1.0) / (t["hot_kernel_ms"] * 1e-3) / 1e12
-        acq.evaluate_with_gradients(Xc[:ng])
-        acq.evaluate_with_gradients(Xc[:ng])
-        tg = ctx.timings()
+        acq.evaluate_with_gradients(Xc[:ng])            # builds the gradient-pass state of the model (lazily, once)
+        for _ in range(3):
+            acq.evaluate_with_gradients(Xc[:ng])
+            if tg is None or ctx.timings()["eval_ms"] < tg["eval_ms"]:
+                tg = ctx.timings()
         tfg = ng * 2.0 * Ms * (Ms + 1.0) / (tg["eval_ms"] * 1e-3) / 1e12
         rows.append({"M": Ms, "values": {"candidates": n, "eval_ms": t["eval_ms"], "value": n / (t["eval_ms"] * 1e-3),
                                          "tflops": tf, "frac_of_dmma_peak": tf / peak, "kernel_variant": int(t["variant"])},
@@ -361,7 +366,7 @@ def sub_config5_sweep(gpfo, peak):
                                    "tflops_algorithmic_2M2": tfg, "frac_of_dmma_peak": tfg / peak}})
         acq._get_engine().close()
     return {"workload": "EI, Matern52-ARD, D=8, M sweep, values and evaluate_with_gradients on one GPU (BASELINE configs[4])",
-            "unit": UNIT, "rows": rows}
+            "unit": UNIT, "timing": "device time (gpfo_timings.eval_ms), best of 3 calls", "rows": rows}
 
 
 _REAL_STDOUT = None
