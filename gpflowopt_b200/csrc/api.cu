@@ -23,6 +23,7 @@ struct GpHost {
     bool valid = false;
     int M = 0, Mp = 0, Mf = 0, D = 0, R = 0, kind = 0, slot0 = 0;
     double *dX = nullptr, *dell = nullptr, *dXs = nullptr, *dxn = nullptr, *dY = nullptr, *dV = nullptr;
+    double* dXsT = nullptr;                                 // Xs transposed (D x Mf): coalesced K(X*,X) generation of the latency path
     double *dL = nullptr, *dLinv = nullptr;
     double* dpacked_by[3] = {nullptr, nullptr, nullptr};    // forward block streams: [0] 256-, [1] 512-, [2] 1024-row chunks (or other)
     size_t cap_packed_by[3] = {0, 0, 0};
@@ -75,6 +76,9 @@ struct gpfo_ctx {
     double* dgrads = nullptr; size_t cap_grads = 0;
     double* dkx_scratch = nullptr; size_t cap_kx_scratch = 0;
     double* dpartials = nullptr; size_t cap_partials = 0;    // row-split partial sums
+    double* dthin = nullptr; size_t cap_thin = 0;            // latency path: partial sums of all its concurrent launches
+    cudaStream_t stream2 = nullptr;                          // latency path: the gradient contractions run next to the forward ones
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     double* da_scratch = nullptr; size_t cap_a_scratch = 0;  // stored-A gradient pass: A = L^-1 Kx of one slab of tiles
     double* dgen = nullptr;                                  // 2 * GPFO_MAX_DIM doubles: affine map of the device candidate generator
     bool gen_active = false; unsigned long long gen_seed = 0; long long gen_first = 0;
@@ -172,6 +176,9 @@ int gpfo_ctx_create(int device, gpfo_ctx** out) {
     memset(&ctx->hprog, 0, sizeof(ctx->hprog));
     memset(&ctx->cells, 0, sizeof(ctx->cells));
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
     for (int i = 0; i < 2 * GPFO_MAX_GPS && ok; ++i) ok = cudaEventCreate(&ctx->gp_ev[i / 2][i % 2]) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&ctx->dprog, sizeof(ProgramDev)) == cudaSuccess;
@@ -185,7 +192,7 @@ int gpfo_ctx_create(int device, gpfo_ctx** out) {
 }
 
 static void free_gp(GpHost& g) {
-    cudaFree(g.dX); cudaFree(g.dell); cudaFree(g.dXs); cudaFree(g.dxn); cudaFree(g.dY); cudaFree(g.dV);
+    cudaFree(g.dX); cudaFree(g.dell); cudaFree(g.dXs); cudaFree(g.dXsT); cudaFree(g.dxn); cudaFree(g.dY); cudaFree(g.dV);
     cudaFree(g.dL); cudaFree(g.dLinv); cudaFree(g.dpacked_by[0]); cudaFree(g.dpacked_by[1]); cudaFree(g.dpacked_by[2]); cudaFree(g.ddev);
     cudaFree(g.dalpha); cudaFree(g.dpacked_kinv);
 #ifdef GPFO_BUILD_EXPERIMENTS
@@ -204,7 +211,10 @@ int gpfo_ctx_destroy(gpfo_ctx* ctx) {
     cudaFree(ctx->dprog); cudaFree(ctx->dpf); cudaFree(ctx->dlb); cudaFree(ctx->dub); cudaFree(ctx->dcoff); cudaFree(ctx->dcbnd);
     cudaFree(ctx->dXc); cudaFree(ctx->dvalues); cudaFree(ctx->dmom_mean); cudaFree(ctx->dmom_var);
     cudaFree(ctx->dcmu); cudaFree(ctx->dcva); cudaFree(ctx->dgrads); cudaFree(ctx->dkx_scratch); cudaFree(ctx->dgen);
-    cudaFree(ctx->dpartials); cudaFree(ctx->da_scratch);
+    cudaFree(ctx->dpartials); cudaFree(ctx->da_scratch); cudaFree(ctx->dthin);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     cudaFree(ctx->dpart_val); cudaFree(ctx->dpart_idx); cudaFree(ctx->dbest_val); cudaFreeHost(ctx->hstage);
     cudaFree(ctx->dflag);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
@@ -441,6 +451,7 @@ int gpfo_gp_set(gpfo_ctx* ctx, int gp_id, int64_t M64, int D, int R, const doubl
         CK(ensure(&g.dX, &c, (size_t)Mf * D)); c = 0;
         CK(ensure(&g.dell, &c, (size_t)D)); c = 0;
         CK(ensure(&g.dXs, &c, (size_t)Mf * D)); c = 0;
+        CK(ensure(&g.dXsT, &c, (size_t)Mf * D)); c = 0;
         CK(ensure(&g.dxn, &c, (size_t)Mf)); c = 0;
         CK(ensure(&g.dY, &c, (size_t)Mf * R)); c = 0;
         CK(ensure(&g.dV, &c, (size_t)Mf * R)); c = 0;
@@ -481,6 +492,7 @@ int gpfo_gp_set(gpfo_ctx* ctx, int gp_id, int64_t M64, int D, int R, const doubl
     CK(cudaMemcpyAsync(g.dY, Y, (size_t)M * R * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(g.dell, ell, (size_t)D * sizeof(double), cudaMemcpyHostToDevice, st));
     gpfo_prepare_inputs(st, g.dX, M, Mf, D, g.dell, g.dXs, g.dxn);
+    gpfo_transpose_inputs(st, g.dXs, Mf, D, g.dXsT);
     CK(cudaGetLastError());
     int rc = gpfo_factor_device(st, M, Mf, D, R, kernel_kind, kern_variance, noise_variance, g.dXs, g.dxn, g.dL,
                                 g.dLinv, g.dY, g.dV, ctx->dflag, &ctx->err);
@@ -488,6 +500,7 @@ int gpfo_gp_set(gpfo_ctx* ctx, int gp_id, int64_t M64, int D, int R, const doubl
     g.hdev.M = M; g.hdev.Mp = Mp; g.hdev.D = D; g.hdev.R = R; g.hdev.kind = kernel_kind; g.hdev.slot0 = slot0;
     g.hdev.variance = kern_variance;
     g.hdev.Xs = g.dXs; g.hdev.xn = g.dxn; g.hdev.V = g.dV;
+    g.hdev.XsT = g.dXsT; g.hdev.ldT = Mf;
     g.geom_s = make_geom(Mp / 8, gpfo_split_rbc(), 0);
     CK(ensure(&g.dpacked_s, &g.cap_packed_s, (size_t)pg_total_blocks(g.geom_s) * 64));
     gpfo_pack_linv(st, g.dLinv, g.Mf, g.geom_s, g.dpacked_s);
@@ -657,6 +670,8 @@ struct EvalPlan {
     int64_t N;
     int D, variant, grid, hv_grid, pg_grid, slot_first;
     bool use_cluster, hv, want_grad, need_mom, generate;
+    bool thin = false;              // latency path (launch_thin)
+    double* best_direct = nullptr;  // latency path: where a single-block finish kernel leaves the (value, index) record
 };
 
 // Two device buffers of the same size that grow together ([slot][N] moment / coefficient arrays).
@@ -805,6 +820,94 @@ static int launch_stored_a(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
         }
     }
     *launches_out = launches; *nparts_out = nparts; *hot_ms_out = hot_ms;
+    return GPFO_OK;
+}
+
+// Latency path, a handful of candidates (every GP's forward -- and gradient -- launch would be a row-split one): all contraction
+// launches are independent of each other (the gradient launches leave raw sums, the program's partials are applied by the
+// finish kernel), so the gradient ones go to a second stream, and ONE finish kernel replaces the per-GP finish kernels, the
+// program-gradient kernel and, for up to 32 candidates, the argmax kernel.  Reference call site: the N = 1 L-BFGS-B polish
+// evaluations of optim.py:252-276 through acquisition.py:256-257.
+// One tile (<= 8 candidates) whose K(X*,X) fits one shared-memory panel: thin.cu's 16-row kernels (any M); beyond, while a row
+// split applies, the row-split DMMA kernels (contract2_aux.cu), which amortise their per-chunk work over 128 rows.
+static bool thin_rows16(const gpfo_ctx* ctx, int64_t N) {
+    if (N > gpfo_thin_max_n()) return false;
+    for (int g = 0; g < ctx->ngps; ++g)
+        if (ctx->gps[g].Mp > gpfo_thin_panel_cols(N)) return false;     // K(X*,X) of the call must fit one shared-memory panel
+    return true;
+}
+static int thin_ns(const gpfo_ctx* ctx, int64_t N, const PackGeom& geom) {
+    return thin_rows16(ctx, N) ? gpfo_thin_nsplit(N, ctx->num_sms, geom.nrb) : split_count(ctx, N, gpfo_split_tile(), geom.nchunks);
+}
+static bool thin_applies(const gpfo_ctx* ctx, int64_t N, bool hv, bool generate, bool want_grad) {
+    static const bool off = getenv("GPFO_NO_THIN") && atoi(getenv("GPFO_NO_THIN")) != 0;
+    if (off || ctx->variant != 0 || hv || generate) return false;
+    if (thin_rows16(ctx, N)) return true;
+    for (int g = 0; g < ctx->ngps; ++g) {
+        if (split_count(ctx, N, gpfo_split_tile(), ctx->gps[g].geom_s.nchunks) <= 1) return false;
+        if (want_grad && split_count(ctx, N, gpfo_split_tile(), ctx->gps[g].geom_kinv_s.nchunks) <= 1) return false;
+    }
+    return true;
+}
+static size_t thin_partials(const gpfo_ctx* ctx, int64_t N, int D, bool want_grad) {
+    const size_t ntiles = (size_t)((N + 7) / 8);
+    size_t need = 0;
+    for (int g = 0; g < ctx->ngps; ++g) {
+        need += ntiles * thin_ns(ctx, N, ctx->gps[g].geom_s) * 8 * (1 + RMAX_KERNEL);
+        if (want_grad) need += ntiles * thin_ns(ctx, N, ctx->gps[g].geom_kinv_s) * 8 * (size_t)(1 + ctx->gps[g].R) * (1 + D);
+    }
+    return need;
+}
+static int launch_thin(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* launches_out, int* nparts_out) {
+    cudaStream_t st = ctx->stream, st2 = ctx->stream2;
+    const int64_t N = pl.N;
+    const int D = pl.D;
+    const size_t ntiles = (size_t)((N + 7) / 8);
+    const bool rows16 = thin_rows16(ctx, N);
+    ThinFinalArgs a;
+    memset(&a, 0, sizeof(a));
+    a.ngps = ctx->ngps; a.D = D; a.want_grad = pl.want_grad ? 1 : 0; a.best_out = pl.best_direct;
+    int launches = 0;
+    size_t off = 0;
+    if (pl.want_grad) {
+        CK(cudaEventRecord(ctx->ev_fork, st));
+        CK(cudaStreamWaitEvent(st2, ctx->ev_fork, 0));
+    }
+    for (int g = 0; g < ctx->ngps; ++g) {
+        const GpHost& gh = ctx->gps[g];
+        EvalIO gio = io;
+        gio.write_moments = 0; gio.run_program = 0;
+        gio.packed_o = gh.dpacked_s; gio.geom_o = gh.geom_s;
+        gio.nsplit = thin_ns(ctx, N, gh.geom_s);
+        gio.partials = ctx->dthin + off;
+        a.gp[g] = gh.ddev; a.part_f[g] = gio.partials; a.ns_f[g] = gio.nsplit;
+        a.R[g] = gh.R; a.slot0[g] = gh.slot0;
+        off += ntiles * gio.nsplit * 8 * (1 + RMAX_KERNEL);
+        if (!ctx->capturing) CK(cudaEventRecord(ctx->gp_ev[g][0], st));
+        if (rows16) CK(gpfo_thin_contract_launch(st, gh.kind, gh.ddev, gio, D, 0));
+        else CK(gpfo_thin_forward_launch(st, gh.kind, gh.ddev, gio, D));
+        if (!ctx->capturing) CK(cudaEventRecord(ctx->gp_ev[g][1], st));
+        ++launches;
+    }
+    if (pl.want_grad) {
+        for (int g = 0; g < ctx->ngps; ++g) {
+            const GpHost& gh = ctx->gps[g];
+            EvalIO gio = io;
+            gio.packed_o = gh.dpacked_kinv_s; gio.geom_o = gh.geom_kinv_s;
+            gio.nsplit = thin_ns(ctx, N, gh.geom_kinv_s);
+            gio.partials = ctx->dthin + off;
+            a.part_g[g] = gio.partials; a.ns_g[g] = gio.nsplit;
+            off += ntiles * gio.nsplit * 8 * (size_t)(1 + gh.R) * (1 + D);
+            if (rows16) CK(gpfo_thin_contract_launch(st2, gh.kind, gh.ddev, gio, D, 1));
+            else CK(gpfo_thin_grad_launch(st2, gh.kind, gh.ddev, gio, D));
+            ++launches;
+        }
+        CK(cudaEventRecord(ctx->ev_join, st2));
+        CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    }
+    CK(gpfo_thin_final_launch(st, ctx->dprog, io, a));
+    ++launches;
+    *launches_out = launches; *nparts_out = gpfo_thin_final_grid(N);
     return GPFO_OK;
 }
 
@@ -999,8 +1102,10 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
 #endif
     const int hv_grid = hv ? gpfo_hvpoi_grid(N, ctx->num_sms, ctx->cells.n_ext, ctx->cells.R, want_grad ? 1 : 0) : 1;
     const int pg_grid = gpfo_program_grad_grid(N, ctx->num_sms);
+    const bool thin = !astore && thin_applies(ctx, N, hv, generate, want_grad);
     int max_parts = grid > hv_grid ? grid : hv_grid;
     if (pg_grid > max_parts) max_parts = pg_grid;
+    if (thin && gpfo_thin_final_grid(N) > max_parts) max_parts = gpfo_thin_final_grid(N);
     if (max_parts < ctx->num_sms) max_parts = ctx->num_sms;      // row-split finish kernel: <= num_sms / 2 * 8 / 128 blocks
     rc = ensure_parts(ctx, max_parts);
     if (rc != GPFO_OK) return rc;
@@ -1028,11 +1133,27 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     char* const hb_stage = ctx->hstage + 3 * GPFO_STAGE_AREA;
     const bool stage_v = out_values && !dev_out && vbytes <= GPFO_STAGE_AREA;
     const bool stage_g = want_grad && !dev_grads && gbytes <= GPFO_STAGE_AREA;
+    // latency path: the finish kernel writes the results to the pinned (device-mapped) staging areas itself -- no copy nodes
+    // behind a call of a few microseconds' worth of kernels (GPFO_THIN_COPIES=1 keeps the copies).  The candidates still
+    // arrive by a copy: read in place by every CTA of the contraction launches they cost 9-18 us of serialised PCIe reads
+    // (profiles/r02_thin_phase_stamps.log).
+    static const bool thin_copies = getenv("GPFO_THIN_COPIES") && atoi(getenv("GPFO_THIN_COPIES")) != 0;
+    pl.thin = thin;
+    const bool direct = pl.thin && !thin_copies;
+    const bool direct_x = false, direct_v = direct && stage_v, direct_g = direct && stage_g;
+    const bool direct_b = direct && gpfo_thin_final_grid(N) == 1;
+    if (pl.thin) {
+        CK(ensure(&ctx->dthin, &ctx->cap_thin, thin_partials(ctx, N, D, want_grad)));
+        if (direct_x) io.X = reinterpret_cast<const double*>(ctx->hstage);
+        if (direct_v) io.values = reinterpret_cast<double*>(hv_stage);
+        if (direct_g) io.grads = reinterpret_cast<double*>(hg_stage);
+        if (direct_b) pl.best_direct = reinterpret_cast<double*>(hb_stage);
+    }
 
     // Everything the call puts on the stream, in order: candidate upload, kernels, final argmax, result download.
     // `timed` = with the event records of the timing breakdown (not capturable into a graph).
     auto enqueue = [&](bool timed) -> int {
-        if (host_in) {
+        if (host_in && !direct_x) {
             NvtxRange nvtx_upload("gpfo:upload");
             if (timed) CK(cudaEventRecord(ctx->ev[2], st));
             CK(cudaMemcpyAsync(ctx->dXc, stage_x ? (const void*)ctx->hstage : (const void*)Xcand, xbytes, cudaMemcpyHostToDevice, st));
@@ -1041,23 +1162,24 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
         if (timed) CK(cudaEventRecord(ctx->ev[4], st));
         {
             NvtxRange nvtx_eval("gpfo:eval");
-            const int rc2 = astore ? launch_stored_a(ctx, pl, io, &launches, &nparts, &hot_ms)
-                                   : launch_standard(ctx, pl, io, &launches, &nparts, &hot_ms);
+            const int rc2 = pl.thin ? launch_thin(ctx, pl, io, &launches, &nparts)
+                            : astore ? launch_stored_a(ctx, pl, io, &launches, &nparts, &hot_ms)
+                                     : launch_standard(ctx, pl, io, &launches, &nparts, &hot_ms);
             if (rc2 != GPFO_OK) return rc2;
         }
-        {
+        if (!direct_b) {
             NvtxRange nvtx_argmax("gpfo:argmax");
             gpfo_argmax_final(st, ctx->dpart_val, ctx->dpart_idx, nparts, ctx->dbest_val, ctx->dbest_idx);
             CK(cudaGetLastError());
+            ++launches;
         }
-        ++launches;
         if (timed) CK(cudaEventRecord(ctx->ev[5], st));
         NvtxRange nvtx_download("gpfo:download");
-        if (out_values && !dev_out)
+        if (out_values && !dev_out && !direct_v)
             CK(cudaMemcpyAsync(stage_v ? (void*)hv_stage : (void*)out_values, ctx->dvalues, vbytes, cudaMemcpyDeviceToHost, st));
-        if (want_grad && !dev_grads)
+        if (want_grad && !dev_grads && !direct_g)
             CK(cudaMemcpyAsync(stage_g ? (void*)hg_stage : (void*)out_grads, ctx->dgrads, gbytes, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(hb_stage, ctx->dbest_val, 16, cudaMemcpyDeviceToHost, st));
+        if (!direct_b) CK(cudaMemcpyAsync(hb_stage, ctx->dbest_val, 16, cudaMemcpyDeviceToHost, st));
         if (timed) CK(cudaEventRecord(ctx->ev[1], st));
         return GPFO_OK;
     };
@@ -1128,7 +1250,7 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
         return GPFO_OK;
     }
     float ms = 0.f;
-    if (host_in) { cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->tm.h2d_ms = ms; }
+    if (host_in && !direct_x) { cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->tm.h2d_ms = ms; }
     cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->tm.eval_ms = ms;
     cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[1]); ctx->tm.d2h_ms = ms;
     hot_ms = 0.f;

@@ -47,14 +47,19 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     constexpr bool BWD = (ABL & 32) != 0;
     constexpr bool ASTORE = (ABL & 128) != 0;
     constexpr bool GRADM = DENSEM || BWD;
+    // ABL bit 4096 = RAWP (latency path, with DENSEM + SPLIT): the launch does not wait for the program's partials
+    // d acq / d (mean, var) -- it runs next to the forward launch -- and leaves the (1 + R) sums
+    // sum_i w_in dk_in [1, Xs_i]  and  sum_i alpha_i,ro dk_in [1, Xs_i]  apart; thin_final_kernel combines them linearly.
+    constexpr bool RAWP = (ABL & 4096) != 0;
+    constexpr int GT = RAWP ? T * (1 + RMAX) : T;                    // rows of the u buffer columns / of gsum
     double* gcm = tab32 + 34;                                        // [T][RMAX]  (d acq/d mean_ro) / out_scale_ro
     double* gcv = gcm + T * RMAX;                                    // [T]        -2 sum_ro (d acq/d var_ro) / out_scale_ro^2
-    double* gsum = gcv + T;                                          // [T][1+D]   sum_i u_in [1, Xs_i]
+    double* gsum = gcv + T;                                          // [GT][1+D]  sum_i u_in [1, Xs_i]
     // ABL bit 1024 = BULK: groups re-read from the scratch arrive by one 1-D bulk copy (cp.async.bulk, the TMA engine;
     // SASS UBLKCP) issued by thread 0 and signalled on an mbarrier per group buffer, instead of four LDGSTS per thread
     constexpr bool BULK = (ABL & 1024) != 0;
-    unsigned long long* kxbar = reinterpret_cast<unsigned long long*>(GRADM ? gsum + T * (1 + D) : gcm);   // [KXB]
-    static_assert(!GRADM || NW * C::RING_DOUBLES_PER_WARP + KXB * C::GROUP_SLOTS >= 8 * C::RBC * (T + 4),
+    unsigned long long* kxbar = reinterpret_cast<unsigned long long*>(GRADM ? gsum + GT * (1 + D) : gcm);   // [KXB]
+    static_assert(!GRADM || NW * C::RING_DOUBLES_PER_WARP + KXB * C::GROUP_SLOTS >= 8 * C::RBC * (GT + 4),
                   "the u buffer of the gradient pass reuses the ring and the group buffers");
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
@@ -99,8 +104,8 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
         __syncthreads();
         if (tid < T * (1 + RMAX)) tot[tid] = 0.0;
         if (GRADM) {
-            for (int e = tid; e < T * (1 + D); e += C::THREADS) gsum[e] = 0.0;
-            if (tid < T) {
+            for (int e = tid; e < GT * (1 + D); e += C::THREADS) gsum[e] = 0.0;
+            if (!RAWP && tid < T) {
                 const int64_t n = n0 + tid;
                 double cv = 0.0;
 #pragma unroll
@@ -352,7 +357,7 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             if (GRADM) {
                 // ---- gradient pass: u_in = (sum_ro c_mu[n][ro] alpha[i][ro] + c_var[n] w_in) * dk_in/dr^2 into the (drained) ring
                 __syncthreads();                          // every warp is done reading its ring
-                constexpr int US = T + 4;                 // row stride of the u buffer: 4 mod 16 doubles, so that the A-fragment reads
+                constexpr int US = GT + 4;                // row stride of the u buffer: 4 mod 16 doubles, so that the A-fragment reads
                                                           // of the reduction below (4 rows x 4 candidates per half-warp) hit 16 banks
                 double* ubuf = ring;                      // [8 * RBC][US]  (spills into the group buffers when S < NB)
                 const int rev = 8 * geom.nrb - 1;         // backward pass: stream row i' is training point rev - i'
@@ -368,6 +373,19 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                         for (int c = 0; c < 2; ++c) {
                             const int n = 8 * nb + 2 * (lane & 3) + c;
                             double u = 0.0;
+                            if (RAWP) {
+                                double dk = 0.0;
+                                if (rbl < nr) {
+                                    double dot = 0.0;
+                                    for (int d = 0; d < D; ++d) dot = fma(__ldg(Xs + (size_t)gi * D + d), xc[d * T + n], dot);
+                                    const double r2 = (-2.0 * dot + __ldg(xn + gi)) + x2[n];
+                                    dk = dk_dr2_branchless<KIND>(variance, r2, tab32);
+                                }
+                                ubuf[il * US + n] = acc[r][nb][c] * dk;
+                                for (int ro = 0; ro < R; ++ro)
+                                    ubuf[il * US + T * (1 + ro) + n] = rbl < nr ? __ldg(gp.alpha + (size_t)gi * R + ro) * dk : 0.0;
+                                continue;
+                            }
                             if (rbl < nr) {
                                 double coef = gcv[n] * acc[r][nb][c];
                                 for (int ro = 0; ro < R; ++ro) coef = fma(gcm[n * RMAX + ro], __ldg(gp.alpha + (size_t)gi * R + ro), coef);
@@ -391,8 +409,9 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                     const int rows = 8 * nr;              // a multiple of 8
                     const int step = BWD ? -1 : 1;
                     const int g0 = BWD ? rev - 8 * row0 : 8 * row0;             // training point of buffer row 0
-                    for (int q = w; q < NB * ND; q += NW) {
-                        const int nbq = q % NB, dbq = q / NB;
+                    const int NBQ = RAWP ? NB * (1 + R) : NB;     // 8-wide column blocks of the u buffer
+                    for (int q = w; q < NBQ * ND; q += NW) {
+                        const int nbq = q % NBQ, dbq = q / NBQ;
                         const int cq = 8 * dbq + (lane >> 2);                   // column of Xa this lane feeds (B fragment: col = lane / 4)
                         const double* __restrict__ up = ubuf + (lane & 3) * US + 8 * nbq + (lane >> 2);
                         const bool is_one = cq == 0, is_x = cq >= 1 && cq <= D;
@@ -500,8 +519,9 @@ contract2_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             if (TIM) t_red += clock64() - t_mark;
         }
         if (SPLIT) {
-            double* part = io.partials + ((size_t)tile * nsplit + split) * (size_t)(T * (GRADM ? 1 + D : 1 + RMAX));
-            if (GRADM) for (int e = tid; e < T * (1 + D); e += C::THREADS) part[e] = gsum[e];
+            const int gt = RAWP ? T * (1 + R) : T;
+            double* part = io.partials + ((size_t)tile * nsplit + split) * (size_t)(GRADM ? gt * (1 + D) : T * (1 + RMAX));
+            if (GRADM) for (int e = tid; e < gt * (1 + D); e += C::THREADS) part[e] = gsum[e];
             else if (tid < T * (1 + RMAX)) part[tid] = tot[tid];
             continue;
         }
@@ -553,7 +573,8 @@ static inline cudaError_t launch2_kind(cudaStream_t st, const GpDev* d_gp, const
     using C = Contract2Cfg<NW, RBW, NB, S>;
     const size_t smem = ((size_t)NW * C::RING_DOUBLES_PER_WARP + ((ABL & 2048) ? 32 : ((ABL & (8 | 32)) ? 3 : 2)) * C::GROUP_SLOTS +
                          (size_t)D * C::T + C::T + C::T * (1 + RMAX) + 2 * ((C::T + 31) / 32) + 34 +
-                         ((ABL & (4 | 32)) ? C::T * RMAX + C::T + C::T * (1 + (size_t)D) : 0) + ((ABL & 1024) ? 4 : 0)) * sizeof(double);
+                         ((ABL & (4 | 32)) ? C::T * RMAX + C::T + ((ABL & 4096) ? 1 + RMAX : 1) * C::T * (1 + (size_t)D) : 0) +
+                         ((ABL & 1024) ? 4 : 0)) * sizeof(double);
     auto kern = contract2_kernel<NW, RBW, NB, S, KIND, ABL>;
     static size_t smem_set[16] = {0};              // per instantiation and device: the opt-in is sticky, raise it only when needed
     int dev = 0;

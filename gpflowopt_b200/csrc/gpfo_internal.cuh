@@ -96,6 +96,8 @@ struct GpDev {
     const double* Xs;           // Mp x D, training inputs divided by lengthscales (rows >= M are zero)
     const double* xn;           // Mp, squared norms of the rows of Xs
     const double* V;            // Mp x R, L^-1 Y (rows >= M are zero)
+    const double* XsT;          // D x ldT, Xs transposed (thin.cu: lane = training point, coalesced)
+    int ldT;
     const double* packed;       // block stream of L^-1
     PackGeom geom;
 #ifdef GPFO_BUILD_EXPERIMENTS
@@ -409,3 +411,23 @@ int gpfo_split_rbc();
 int gpfo_split_tile();
 cudaError_t gpfo_contract_split_launch(cudaStream_t st, int kind, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io, int D);
 cudaError_t gpfo_contract_grad_split_launch(cudaStream_t st, int kind, const GpDev* d_gp, EvalIO io, int D, int wide);
+// latency path for a handful of candidates (contract2_aux.cu): forward and gradient contractions side by side, one finish kernel
+struct ThinFinalArgs {
+    const GpDev* gp[GPFO_MAX_GPS];
+    const double* part_f[GPFO_MAX_GPS];     // forward partials of GP g:  [tile][ns_f][8][1 + RMAX]
+    const double* part_g[GPFO_MAX_GPS];     // gradient partials of GP g: [tile][ns_g][8 (1 + R)][1 + D]
+    int ns_f[GPFO_MAX_GPS], ns_g[GPFO_MAX_GPS];
+    int R[GPFO_MAX_GPS], slot0[GPFO_MAX_GPS];
+    int ngps, D, want_grad;
+    double* best_out;                       // (value, index) record of the call when one block covers it; may be host-mapped
+};
+cudaError_t gpfo_thin_forward_launch(cudaStream_t st, int kind, const GpDev* d_gp, EvalIO io, int D);
+cudaError_t gpfo_thin_grad_launch(cudaStream_t st, int kind, const GpDev* d_gp, EvalIO io, int D);
+int gpfo_thin_final_grid(int64_t N);
+// thin.cu: contraction kernels for one tile of <= 8 candidates spread over all SMs (16 rows of the block stream per CTA)
+int gpfo_thin_nsplit(int64_t N, int num_sms, int nrb);
+int64_t gpfo_thin_max_n();
+int gpfo_thin_panel_cols(int64_t N);
+void gpfo_transpose_inputs(cudaStream_t st, const double* dXs, int rows, int D, double* dXsT);
+cudaError_t gpfo_thin_contract_launch(cudaStream_t st, int kind, const GpDev* d_gp, EvalIO io, int D, int grad);
+cudaError_t gpfo_thin_final_launch(cudaStream_t st, const ProgramDev* d_prog, EvalIO io, const ThinFinalArgs& a);

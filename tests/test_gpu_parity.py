@@ -526,6 +526,63 @@ def test_row_split_small_batches(ctx, M, D):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# latency path (a handful of candidates: 16-row contraction kernels on two streams + one finish kernel; row-split DMMA
+# kernels + the same finish kernel up to N = 592): every candidate-count class (NV = 1 / 4 / 8, several tiles, the hand-over
+# to the row-split kernels at N = 64 / 65), two GPs with different kernels and M, a multi-output GP, repeated calls (the third
+# call of a shape replays a CUDA graph with a forked second stream) and evaluate == evaluate_with_gradients[0] bitwise.
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M1,M2,D", [(50, 37, 3), (300, 120, 5), (1100, 515, 8)])
+def test_latency_path_small_calls(ctx, M1, M2, D):
+    g1, lo, up = _model(M1, D, "matern52", scaled=True)
+    g2, _, _ = _model(M2, D, "rbf", seed=77, scaled=True)
+    for i, g in enumerate((g1, g2)):
+        upload_oracle_gp(ctx, i, g, slot0=i)
+    ctx.gp_count_set(2)
+    try:
+        f1 = float(np.min(g1.predict(g1.input_transform.backward(g1.Xs))[0])) + 0.05
+        ei1, pof2, lcb2 = oacq.Leaf('ei', g1, f1), oacq.Leaf('pof', g2, 2.5), oacq.Leaf('lcb', g2, 1.5)
+        ctx.program_set([[_lib.OP_EI, 0, 0, 0], [_lib.OP_POF, 1, 0, 1], [_lib.OP_LCB, 1, 0, 2], [_lib.OP_SUM, 2, 0, 0],
+                         [_lib.OP_PROD, 2, 0, 0], [_lib.OP_SCALE, 0, 0, 3]], [f1, 2.5, 1.5, 0.25])
+        node = oacq.Agg('prod', [ei1, oacq.Agg('sum', [pof2, lcb2])], scale=0.25)
+        for N in (1, 2, 4, 5, 8, 9, 31, 64, 65, 130):
+            Xc = _cands(N, D, lo, up, seed=100 + N)
+            rv, rg = node.value_and_grad(Xc)
+            for rep in range(3):                                  # plain, capture, replay
+                vals, grads, bv, bi = ctx.eval(Xc, want_grads=True)
+                assert_parity(vals, rv, what="latency path value N=%d rep %d" % (N, rep))
+                assert_parity(grads, rg, what="latency path grad N=%d rep %d" % (N, rep))
+                assert bi == int(np.argmax(vals)) and bv == vals[bi, 0]
+                v_only, _, bv2, bi2 = ctx.eval(Xc)
+                np.testing.assert_array_equal(v_only, vals)
+                assert (bv2, bi2) == (bv, bi)
+    finally:
+        ctx.gp_count_set(1)
+
+
+def test_latency_path_multi_output_slots(ctx):
+    """The latency path on a 3-output GP plus a 1-output GP: same rows as a 400-row call through the standard kernels."""
+    D = 3
+    X, Y = synthetic.training_set(80, D, constraint=True)
+    Y3 = np.hstack((Y, (Y[:, [0]] * Y[:, [1]])))
+    h = synthetic.hypers(D)
+    upload_oracle_gp(ctx, 0, oracle_gp(X, Y3, ogp.RBF, h), slot0=0)
+    upload_oracle_gp(ctx, 1, oracle_gp(X, Y[:, [1]], ogp.MATERN32, h), slot0=3)
+    ctx.gp_count_set(2)
+    try:
+        ctx.program_set([[_lib.OP_EI, 2, 0, 0], [_lib.OP_POF, 3, 0, 1], [_lib.OP_PROD, 2, 0, 0], [_lib.OP_MEAN, 1, 0, 0],
+                         [_lib.OP_SUM, 2, 0, 0]], [0.1, 0.0])
+        Xc = synthetic.candidates(700, D)
+        vals, grads, _, _ = ctx.eval(Xc, want_grads=True)        # 700 rows: beyond every small-call path
+        for N in (1, 3, 8, 20, 64, 100):
+            v, g, bv, bi = ctx.eval(Xc[:N], want_grads=True)
+            assert_parity(v, vals[:N], tol=1e-11, what="latency path vs standard kernels, value N=%d" % N)
+            assert_parity(g, grads[:N], tol=1e-10, what="latency path vs standard kernels, grad N=%d" % N)
+            assert bi == int(np.argmax(v)) and bv == v[bi, 0]
+    finally:
+        ctx.gp_count_set(1)
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # stored-A gradient pass (large batches, N >= 64 * 4 * SMs): forward launches park A = L^-1 Kx, backward launches
 # contract it with the reversed transposed stream.  Checked against the oracle on a row subset, against the dense
 # K^-1 pass on every row, across several slabs, for a two-GP product and for HVPoI.

@@ -21,7 +21,7 @@ for M, D in ((20, 2), (512, 8), (2048, 8), (4096, 16)):
     kern = gpfo.RBF(D, variance=h["variance"], lengthscales=h["lengthscales"], ARD=True) if M == 20 else \
         gpfo.Matern52(D, variance=h["variance"], lengthscales=h["lengthscales"], ARD=True)
     acq = ExpectedImprovement(gpfo.GPR(X, Y, kern, noise_variance=h["noise_variance"]))
-    for N in (1, 32, 1000):
+    for N in (1, 4, 8, 32, 1000):
         Xc = synthetic.candidates(N, D)
         tv = bench(lambda: acq.evaluate(Xc))
         tg = bench(lambda: acq.evaluate_with_gradients(Xc))
@@ -30,6 +30,22 @@ for M, D in ((20, 2), (512, 8), (2048, 8), (4096, 16)):
         t = ctx.timings()
         print("M=%5d D=%2d N=%5d: evaluate %.3f ms, evaluate_with_gradients %.3f ms (device %.3f ms, %d launches)" % (
             M, D, N, tv, tg, t["eval_ms"], t["launches"]), flush=True)
+
+# ---- EI x PoF (two GPs, BASELINE configs[2] model) at M = 4096, D = 16: the polish call of a constrained BO iteration ----
+from gpflowopt_b200.acquisition import ProbabilityOfFeasibility                       # noqa: E402
+M, D = 4096, 16
+X, Y = synthetic.training_set(M, D, constraint=True)
+h = synthetic.hypers(D)
+mk = lambda y: gpfo.GPR(X, y, gpfo.Matern52(D, variance=h["variance"], lengthscales=h["lengthscales"], ARD=True), noise_variance=h["noise_variance"])
+joint = ExpectedImprovement(mk(Y[:, [0]])) * ProbabilityOfFeasibility(mk(Y[:, [1]]))
+for N in (1, 8):
+    Xc = synthetic.candidates(N, D)
+    tv = bench(lambda: joint.evaluate(Xc))
+    tg = bench(lambda: joint.evaluate_with_gradients(Xc))
+    joint.evaluate_with_gradients(Xc)
+    t = joint._get_engine().ctx.timings()
+    print("EI x PoF M=%5d D=%2d N=%5d: evaluate %.3f ms, evaluate_with_gradients %.3f ms (device %.3f ms, %d launches)" % (
+        M, D, N, tv, tg, t["eval_ms"], t["launches"]), flush=True)
 
 # ---- one BO inner optimisation (BASELINE configs[1] model): MC stage + polish, reference-style vs batched multi-start ----
 from gpflowopt_b200.bo import _InverseAcquisition                                   # noqa: E402
