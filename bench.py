@@ -369,6 +369,42 @@ def sub_config5_sweep(gpfo, peak):
             "unit": UNIT, "timing": "device time (gpfo_timings.eval_ms), best of 3 calls", "rows": rows}
 
 
+def sub_polish_latency(gpfo):
+    """The N = 1 calls an L-BFGS-B polish makes (reference optim.py:214-224 through acquisition.py:256-257): wall clock of
+    Acquisition.evaluate / evaluate_with_gradients of one candidate through the public API, host arrays in and out."""
+    from gpflowopt_b200 import synthetic
+    from gpflowopt_b200.acquisition import ExpectedImprovement, ProbabilityOfFeasibility
+
+    def wall_ms(f, reps=200):
+        for _ in range(5):
+            f()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            f()
+        return (time.perf_counter() - t0) / reps * 1e3
+
+    rows = []
+    for name, Ms, Ds, joint in (("EI", 2048, 8, False), ("EI x PoF", 4096, 16, True)):
+        X, Y = synthetic.training_set(Ms, Ds, constraint=joint)
+        h = synthetic.hypers(Ds)
+        mk = lambda y: gpfo.GPR(X, y, gpfo.Matern52(Ds, variance=h["variance"], lengthscales=h["lengthscales"], ARD=True),
+                                noise_variance=h["noise_variance"])
+        acq = ExpectedImprovement(mk(Y[:, [0]]))
+        if joint:
+            acq = acq * ProbabilityOfFeasibility(mk(Y[:, [1]]))
+        x = synthetic.candidates(1, Ds)
+        rec = {"acquisition": name, "M": Ms, "D": Ds, "N": 1,
+               "evaluate_ms": wall_ms(lambda: acq.evaluate(x)),
+               "evaluate_with_gradients_ms": wall_ms(lambda: acq.evaluate_with_gradients(x))}
+        t = acq._get_engine().ctx.timings()
+        rec["device_ms"] = t["eval_ms"]
+        rec["launches"] = int(t["launches"])
+        rows.append(rec)
+        acq._get_engine().close()
+    return {"workload": "one candidate through Acquisition.evaluate / evaluate_with_gradients (the L-BFGS-B polish calls)",
+            "timing": "wall clock per call, mean of 200, host ndarray in and out", "rows": rows}
+
+
 _REAL_STDOUT = None
 
 
@@ -568,6 +604,7 @@ def main():
             if world == 1:                                # single-GPU records and bars: once, in the N = 1 run
                 out["configs"]["configs[3]"] = sub_config4_hvpoi(gpfo)
                 out["configs"]["configs[4]"] = sub_config5_sweep(gpfo, fp64_peak)
+                out["polish_latency"] = sub_polish_latency(gpfo)
                 out["bars"] = gpu_library_bars(torch, fp64_peak)
                 if not args.no_cpu_baseline:
                     out["bars"].update(cpu_side_bars())
