@@ -44,8 +44,9 @@ void gpfo_argmax_final(cudaStream_t st, const double* part_val, const long long*
 //   (10, 13, 14, 4x and 12x exist only in builds with GPFO_BUILD_EXPERIMENTS=1)
 struct VarInfo { int rbc, tile; };
 static VarInfo var_info(int v) {
-    if (v == 20 || (v >= 22 && v <= 27) || v == 30 || v == 32 || v == 34) return {128, 16};
-    if (v == 21 || v == 28 || v == 31 || v == 33 || v == 35) return {64, 32};
+    if (v == 20 || (v >= 22 && v <= 27) || v == 30 || v == 32 || v == 34 || v == 36) return {128, 16};
+    if (v == 29) return {64, 16};
+    if (v == 21 || v == 28 || v == 31 || v == 33 || v == 35 || (v >= 37 && v <= 39)) return {64, 32};
     if (v == 12 || v == 13 || v == 14 || (v >= 120 && v <= 129)) return {32, 64};
     if (v == 5) return {64, 16};
     if (v == 6) return {64, 8};
@@ -57,7 +58,8 @@ int gpfo_contract_tile(int variant) { return var_info(variant).tile; }
 int gpfo_contract_grid(int variant, int64_t N, int num_sms) {
     const int T = gpfo_contract_tile(variant);
     const int64_t ntiles = (N + T - 1) / T;
-    return (int)(ntiles < num_sms ? (ntiles > 0 ? ntiles : 1) : num_sms);
+    const int ctas = variant == 29 ? 2 * num_sms : num_sms;          // 29: 8-warp CTAs, two per SM
+    return (int)(ntiles < ctas ? (ntiles > 0 ? ntiles : 1) : ctas);
 }
 
 cudaError_t gpfo_contract2_launch(cudaStream_t st, int variant, int kind, const GpDev* d_gp, const ProgramDev* d_prog,
@@ -72,7 +74,7 @@ cudaError_t gpfo_contract_ws_launch(cudaStream_t st, int kind, const GpDev* d_gp
 
 cudaError_t gpfo_contract_launch(cudaStream_t st, int variant, int kind, const GpDev* d_gp, const ProgramDev* d_prog,
                                  EvalIO io, int grid, int D) {
-    if (variant >= 20 && variant <= 35) return gpfo_contract5_launch(st, variant, kind, d_gp, d_prog, io, grid, D);
+    if (variant >= 20 && variant <= 39) return gpfo_contract5_launch(st, variant, kind, d_gp, d_prog, io, grid, D);
 #ifdef GPFO_BUILD_EXPERIMENTS
     if (variant == 13) return gpfo_contract_ws_launch(st, kind, d_gp, d_prog, io, grid, D);
 #else

@@ -33,13 +33,13 @@
 #include <type_traits>
 #include "contract_common.cuh"
 
-template <int RBW, int NB, int QD>
+template <int RBW, int NB, int QD, int NWARPS = 16>
 struct Contract5Cfg {
-    static constexpr int NW = 16;
+    static constexpr int NW = NWARPS;                       // warps per CTA: 16 (one CTA per SM) or 8 (two CTAs per SM, half-height chunks)
     static constexpr int THREADS = 32 * NW;
     static constexpr int T = 8 * NB;                        // candidates per tile
     static constexpr int RBC = NW * RBW;                    // row blocks per chunk
-    static constexpr int GK = 16 / NB;                      // column blocks per K(X*,X) group: every group is 8 KB
+    static constexpr int GK = NW / NB;                      // column blocks per K(X*,X) group: 8 KB (16 warps) / 4 KB (8 warps)
     static constexpr int GROUP_SLOTS = GK * 2 * NB * 32;    // doubles per group (1024)
     static constexpr int GEN_ITERS = GROUP_SLOTS / THREADS; // covariance elements per thread and group (2)
     static constexpr int RG = RBC / GK;                     // groups of the resident panel (16 -> 128 KB)
@@ -113,10 +113,10 @@ __device__ __forceinline__ void mbar_wait_par(unsigned bar_s, unsigned parity) {
 // ABL (profiling builds only, GPFO_BUILD_EXPERIMENTS): bit 0 = K(X*,X) elements are constants (no generation arithmetic),
 // bit 1 = no L^-1 copies (the ring is never filled), bit 2 = no mbarrier hand-off of the groups (wrong results; timing only),
 // bit 3 = per-warp phase cycle counters
-template <int RBW, int NB, int QD, int KIND, int ABL = 0>
-__global__ void __launch_bounds__(512, 1)
+template <int RBW, int NB, int QD, int KIND, int ABL = 0, int NWARPS = 16>
+__global__ void __launch_bounds__(32 * NWARPS, 16 / NWARPS)
 contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ prog, EvalIO io, int nbuf) {
-    using C = Contract5Cfg<RBW, NB, QD>;
+    using C = Contract5Cfg<RBW, NB, QD, NWARPS>;
     constexpr int T = C::T, NW = C::NW, GK = C::GK, RQ = C::RQ, QPC = C::QPC, RG = C::RG, KA = C::KA;
     constexpr int GS = C::GROUP_SLOTS;
     extern __shared__ __align__(16) double smem[];
@@ -262,6 +262,33 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 dst[gen_slot] = in ? v0 : 0.0;
                 dst[gen_slot + 4] = in ? v1 : 0.0;
             };
+            // two resident groups at once: four independent covariance chains per thread instead of two (the chain of ~25
+            // dependent FP64 instructions per element is what a generating warp waits on: `wait` is the top stall reason)
+            auto gen_pair = [&](int g) {
+                const int jrow0 = (g * GK + gen_jb) * 8 + (lane >> 2), jrow1 = jrow0 + 8 * GK;
+                const int jc0 = jrow0 < M ? jrow0 : M - 1, jc1 = jrow1 < M ? jrow1 : M - 1;
+                double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+                const double* __restrict__ xrow0 = Xs + (size_t)jc0 * D + (lane & 3);
+                const double* __restrict__ xrow1 = Xs + (size_t)jc1 * D + (lane & 3);
+                const double* __restrict__ xcol = xc + (lane & 3) * T + 8 * gen_nb + (lane >> 2);
+                for (int k = 0; k < DP; k += 4) {
+                    const bool ink = k + (lane & 3) < D;
+                    const double a0 = ink ? __ldg(xrow0 + k) : 0.0, a1 = ink ? __ldg(xrow1 + k) : 0.0;
+                    const double b = xcol[k * T];
+                    dmma884(d0, d1, a0, b);
+                    dmma884(e0, e1, a1, b);
+                }
+                const double xn0 = __ldg(xn + jc0), xn1 = __ldg(xn + jc1);
+                const double v0 = kx5<KIND>((-2.0 * d0 + xn0) + x2a, tabv), v1 = kx5<KIND>((-2.0 * d1 + xn0) + x2b, tabv);
+                const double u0 = kx5<KIND>((-2.0 * e0 + xn1) + x2a, tabv), u1 = kx5<KIND>((-2.0 * e1 + xn1) + x2b, tabv);
+                double* __restrict__ dst0 = kres + (size_t)g * GS;
+                dst0[gen_slot] = jrow0 < M ? v0 : 0.0;
+                dst0[gen_slot + 4] = jrow0 < M ? v1 : 0.0;
+                dst0[GS + gen_slot] = jrow1 < M ? u0 : 0.0;
+                dst0[GS + gen_slot + 4] = jrow1 < M ? u1 : 0.0;
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(bar_res + 8 * g); mbar_arrive(bar_res + 8 * (g + 1)); }
+            };
             auto gen_group = [&](int g) {
                 if (g < RG) {                             // resident panel (chunk 0 only): slot g is free since the tile barrier
                     gen_elems(g, kres + (size_t)g * GS);
@@ -289,7 +316,12 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             }
             // generation prologue (chunk 0: the first `la` groups)
             if (TIM) t_mark = clock64();
-            for (int g = g_first; g < la && g < ngroups; ++g) gen_group(g);
+            constexpr bool PAIR = (ABL & 256) == 0;       // (bit 256, profiling builds: one group at a time, as before)
+            // PAIR: resident groups are generated two at a time, at even steps (needs the default lookahead of two groups and
+            // an even group count, i.e. whole pairs inside the panel; otherwise the single-group schedule below)
+            const bool pair = PAIR && p == 0 && la == 2 && (ngroups & 1) == 0;
+            if (pair) gen_pair(0);
+            else for (int g = g_first; g < la && g < ngroups; ++g) gen_group(g);
             if (TIM) { const long long t = clock64(); t_gen += t - t_mark; t_mark = t; }
             // the previous tile's epilogue: warp 0 has delivered its share of the first groups, the other warps are contracting
             if (p == 0 && w == 0 && prev_n0 >= 0) run_epilogue(prev_n0, par ^ 1);
@@ -302,8 +334,10 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
 
             for (int g = 0; g < ngroups; ++g) {
                 const int gg = g + la;
-                const bool do_gen = gg >= g_first && gg < ngroups;
+                const bool do_gen = pair ? false : (gg >= g_first && gg < ngroups);
+                const bool do_pair = pair && (g & 1) == 0 && gg < ngroups;
                 if (TIM) t_mark = clock64();
+                if (do_pair && gen_first) gen_pair(gg);
                 if (do_gen && gen_first) gen_group(gg);
                 if (TIM) { const long long t = clock64(); t_gen += t - t_mark; t_mark = t; }
                 // wait for group g
@@ -324,8 +358,10 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                     for (int kp = k0; kp < k1; ++kp)
                         mma_static(kb + (kp - k0) * (2 * NB * 32), std::integral_constant<int, 0>(), std::true_type());
                 } else if (full_chunk) {
+                    if (ABL & 1024) {                 // (profiling build: the per-column-block dispatch this replaced)
 #pragma unroll 1
-                    for (int kp = k0; kp < k1; ++kp) mma_diag(kb + (kp - k0) * (2 * NB * 32), kp);
+                        for (int kp = k0; kp < k1; ++kp) mma_diag(kb + (kp - k0) * (2 * NB * 32), kp);
+                    } else mma_diag_run(kb, k0, k1);
                 } else {
 #pragma unroll 1
                     for (int kp = k0; kp < k1; ++kp) mma_ragged(kb + (kp - k0) * (2 * NB * 32), kp);
@@ -337,6 +373,7 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 }
                 if (TIM) { const long long t = clock64(); t_mma += t - t_mark; t_mark = t; }
                 if (do_gen && !gen_first) gen_group(gg);
+                if (do_pair && !gen_first) gen_pair(gg);
                 if (TIM) { const long long t = clock64(); t_gen += t - t_mark; }
             }
             cp_async_wait<0>();
@@ -453,14 +490,17 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     }
 }
 
-template <int RBW, int NB, int QD, int KIND, int ABL = 0>
+template <int RBW, int NB, int QD, int KIND, int ABL = 0, int NWARPS = 16>
 static inline cudaError_t launch5_kind(cudaStream_t st, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io, int grid, int D) {
-    using C = Contract5Cfg<RBW, NB, QD>;
+    using C = Contract5Cfg<RBW, NB, QD, NWARPS>;
     int nbuf = C::NBUF_MAX;
+    // (8 warps: two CTAs share the SM's 227 KB, and each CTA's 1 KB reserve)
+    const size_t budget = NWARPS == 16 ? (size_t)227 * 1024 : (size_t)(227 * 1024) / 2 - 1024;
+    while (nbuf > 2 && C::smem_bytes(D, nbuf) > budget) --nbuf;
     while (nbuf >= 2 && C::smem_bytes(D, nbuf) > (size_t)227 * 1024) --nbuf;
     if (nbuf < 2) return cudaErrorInvalidConfiguration;
     const size_t smem = C::smem_bytes(D, nbuf);
-    auto kern = contract5_kernel<RBW, NB, QD, KIND, ABL>;
+    auto kern = contract5_kernel<RBW, NB, QD, KIND, ABL, NWARPS>;
     static size_t smem_set[16] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -473,11 +513,11 @@ static inline cudaError_t launch5_kind(cudaStream_t st, const GpDev* d_gp, const
     return cudaGetLastError();
 }
 
-template <int RBW, int NB, int QD, int ABL = 0>
+template <int RBW, int NB, int QD, int ABL = 0, int NWARPS = 16>
 static inline cudaError_t launch5(cudaStream_t st, int kind, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io, int grid, int D) {
     switch (kind) {
-        case GPFO_KERN_RBF: return launch5_kind<RBW, NB, QD, GPFO_KERN_RBF, ABL>(st, d_gp, d_prog, io, grid, D);
-        case GPFO_KERN_MATERN52: return launch5_kind<RBW, NB, QD, GPFO_KERN_MATERN52, ABL>(st, d_gp, d_prog, io, grid, D);
-        default: return launch5_kind<RBW, NB, QD, GPFO_KERN_MATERN32, ABL>(st, d_gp, d_prog, io, grid, D);
+        case GPFO_KERN_RBF: return launch5_kind<RBW, NB, QD, GPFO_KERN_RBF, ABL, NWARPS>(st, d_gp, d_prog, io, grid, D);
+        case GPFO_KERN_MATERN52: return launch5_kind<RBW, NB, QD, GPFO_KERN_MATERN52, ABL, NWARPS>(st, d_gp, d_prog, io, grid, D);
+        default: return launch5_kind<RBW, NB, QD, GPFO_KERN_MATERN32, ABL, NWARPS>(st, d_gp, d_prog, io, grid, D);
     }
 }
