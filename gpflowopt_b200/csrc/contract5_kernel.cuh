@@ -55,7 +55,7 @@ struct Contract5Cfg {
     static int dpad(int D) { return (D + 3) / 4 * 4; }     // input dimension rounded up to whole DMMA k-steps (zero padded)
     static size_t smem_bytes(int D, int nbuf) {
         return ((size_t)NW * RING_DOUBLES_PER_WARP + (size_t)(RG + nbuf) * GROUP_SLOTS + 2 * (size_t)dpad(D) * T +
-                2 * T * (1 + RMAX) + 2 + 66) * sizeof(double) + (size_t)(RG + 2 * NBUF_MAX) * 8;
+                2 * T * (1 + RMAX) + 2 + 258) * sizeof(double) + (size_t)(RG + 2 * NBUF_MAX) * 8;
     }
 };
 
@@ -70,37 +70,47 @@ __device__ __forceinline__ double2 lds128(unsigned addr) {                      
 }
 template <int ABL>
 __device__ __forceinline__ void cp5(unsigned smem_dst, const void* gmem_src) { if (!(ABL & 2)) cp_async16(smem_dst, gmem_src); }
-// variance * exp(x) for x <= 0 with the table tabv[i] = variance * 2^(i/64): k = round(64 x / ln 2), x = k ln2/64 + r,
-// |r| <= ln2/128, degree-5 Taylor (truncation 3.5e-17 relative).  10 FP64 instructions.
-__device__ __forceinline__ double exp_neg_tab64(double x, const double* __restrict__ tabv) {
-    x = fmax(x, -708.0);
+// K(X*,X) generation arithmetic.  Every FP64 instruction of a generating warp queues behind the other warps' 16-cycle DMMAs on
+// the shared pipe, so the forms below are instruction-count-minimal (20 FP64 instructions per Matern52 element, was 24):
+//  * the kernel's constants are folded into the squared distance: the caller passes  a = c (r^2 + 1e-12)  (c = 5 / 3 for
+//    Matern52 / Matern32, so that sqrt(a) = sqrt(c) r is the exponent itself) or  a = -r^2 / 2  (RBF), built from pre-scaled
+//    row norms and tile norms in the same two instructions the plain r^2 took;
+//  * exp: table of variance * 2^(i/256) (2 KB), k = round(256 x / ln 2), x = k ln2/256 + r, |r| <= ln2/512, degree-4 Taylor
+//    (truncation 3.8e-17 relative); the clamp that keeps 2^(k/256) a normal number is an integer max on the exponent (ALU
+//    pipe) instead of an fmax on the argument; the sign of the argument rides on the FMA operands.  9 FP64 instructions.
+template <bool NEG>      // NEG: variance * exp(-x) for x >= 0;  else variance * exp(x) for x <= 0
+__device__ __forceinline__ double exp_tab256(double x, const double* __restrict__ tabv) {
     const double magic = 6755399441055744.0;                 // 1.5 * 2^52
-    const double t = fma(x, 92.332482616893656, magic);      // 64 / ln 2
+    const double t = fma(x, NEG ? -369.3299304675746 : 369.3299304675746, magic);      // 256 / ln 2
     const double kf = t - magic;
-    double r = fma(kf, -1.0830424696249145e-02, x);          // ln2/64 (head)
-    r = fma(kf, -3.6235106526217448e-19, r);                 // ln2/64 (tail)
-    double p = 8.3333333333333332e-03;                       // 1/5!
-    p = fma(p, r, 4.1666666666666664e-02);
+    double r = fma(kf, -0.00270760617331689, NEG ? -x : x);  // ln2/256, head (31 significant bits: exact product)
+    r = fma(kf, -7.453964567463233e-13, r);                  // ln2/256, tail
+    double p = 4.1666666666666664e-02;                       // 1/4!
     p = fma(p, r, 1.6666666666666666e-01);
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    const int k = __double2loint(t);
-    p *= tabv[k & 63];
-    return __hiloint2double(__double2hiint(p) + ((k >> 6) << 20), __double2loint(p));
+    const int lo = __double2loint(t), hi = __double2hiint(t);
+    p *= tabv[lo & 255];
+    int e = (int)__funnelshift_r((unsigned)lo, (unsigned)hi, 8);   // floor(k / 256): bits 8..39 of the mantissa 2^51 + k
+    e = e > -900 ? e : -900;                                 // far tail: ~1e-271 instead of a wrapped exponent
+    return __hiloint2double(__double2hiint(p) + (int)((unsigned)e << 20), __double2loint(p));
 }
-// covariance from the squared distance, variance included through the table (forms of contract_common.cuh::kx_branchless)
+// multipliers of (dot product, row norm, tile norm) and the additive constant that turn them into the argument `a` above
+template <int KIND> struct Kx5Scale {
+    static constexpr double c = KIND == GPFO_KERN_MATERN52 ? 5.0 : 3.0;
+    static constexpr double kd = KIND == GPFO_KERN_RBF ? 1.0 : -2.0 * c;
+    static constexpr double kn = KIND == GPFO_KERN_RBF ? -0.5 : c;
+    static constexpr double k0 = KIND == GPFO_KERN_RBF ? 0.0 : c * 1e-12;
+};
+// covariance (variance included through the table) from a = kd * dot + kn * |Xs_j|^2 + (kn * |xc|^2 + k0);
+// the forms of contract_common.cuh::kx_branchless with the constants moved into `a`
 template <int KIND>
-__device__ __forceinline__ double kx5(double r2, const double* __restrict__ tabv) {
-    if (KIND == GPFO_KERN_RBF) return exp_neg_tab64(-0.5 * fmax(r2, 0.0), tabv);
-    const double x = r2 + 1e-12;                             // euclid_dist: sqrt(r2 + 1e-12); square(r) == x to 1 ulp
-    const double r = fast_sqrt_pos(x);
-    if (KIND == GPFO_KERN_MATERN52) {
-        const double s5 = 2.2360679774997898;
-        return fma(5.0 / 3.0, x, fma(s5, r, 1.0)) * exp_neg_tab64(-s5 * r, tabv);
-    }
-    const double s3 = 1.7320508075688772;
-    return fma(s3, r, 1.0) * exp_neg_tab64(-s3 * r, tabv);
+__device__ __forceinline__ double kx5(double a, const double* __restrict__ tabv) {
+    if (KIND == GPFO_KERN_RBF) return exp_tab256<false>(fmin(a, 0.0), tabv);
+    const double r = fast_sqrt_pos(a);                       // sqrt(c) * euclid_dist
+    if (KIND == GPFO_KERN_MATERN52) return fma(1.0 / 3.0, a, r + 1.0) * exp_tab256<true>(r, tabv);     // 1 + sqrt5 r + 5 r^2 / 3
+    return (r + 1.0) * exp_tab256<true>(r, tabv);
 }
 __device__ __forceinline__ void mbar_wait_par(unsigned bar_s, unsigned parity) {
     asm volatile(
@@ -128,8 +138,8 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     double* xcb = kstr + (size_t)nbuf * GS;                          // [2][DP][T]        candidates of this / the next tile
     double* totb = xcb + 2 * (size_t)DP * T;                         // [2][T][1+RMAX]    colsum(A^2), A^T V of this / the previous tile
     double* sbest = totb + 2 * T * (1 + RMAX);                       // [2] best value, best index (as bits)
-    double* tabv = sbest + 2;                                        // [64] variance * 2^(i/64) (+2 pad)
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(tabv + 66);   // full_res[RG], full_str[4], empty_str[4]
+    double* tabv = sbest + 2;                                        // [256] variance * 2^(i/256) (+2 pad)
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(tabv + 258);   // full_res[RG], full_str[4], empty_str[4]
     static_assert(T <= 32, "one epilogue warp");
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -156,7 +166,7 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     const int la = (ABL & 32) ? 1 : (nbuf >= 3 ? 2 : 1);   // groups are generated `la` steps ahead of use
 
     if (tid == 0) { sbest[0] = 0.0; reinterpret_cast<long long*>(sbest)[1] = -1; }
-    if (tid < 64) tabv[tid] = gp.variance * exp2(tid * (1.0 / 64.0));
+    for (int e = tid; e < 256; e += C::THREADS) tabv[e] = gp.variance * exp2(e * (1.0 / 256.0));
     if (tid < 2 * T * (1 + RMAX)) totb[tid] = 0.0;
     if (tid == 0) {
         for (int b = 0; b < RG; ++b) mbar_init(bar_res + 8 * b, NW);
@@ -227,6 +237,8 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             x2a = fma(v.x, v.x, x2a);
             x2b = fma(v.y, v.y, x2b);
         }
+        x2a = fma(Kx5Scale<KIND>::kn, x2a, Kx5Scale<KIND>::k0);      // the tile's share of the covariance argument (kx5)
+        x2b = fma(Kx5Scale<KIND>::kn, x2b, Kx5Scale<KIND>::k0);
         if (TIM) t_pro += clock64() - t_mark;
 
         for (int p = 0; p < geom.nchunks; ++p) {
@@ -254,9 +266,9 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 double v0, v1;
                 if (ABL & 1) { v0 = 1e-3 * jrow; v1 = v0; }
                 else {
-                    const double xnj = __ldg(xn + jc);
-                    v0 = kx5<KIND>((-2.0 * d0 + xnj) + x2a, tabv);          // square_dist, expanded form
-                    v1 = kx5<KIND>((-2.0 * d1 + xnj) + x2b, tabv);
+                    const double xnj = Kx5Scale<KIND>::kn * __ldg(xn + jc);
+                    v0 = kx5<KIND>(fma(Kx5Scale<KIND>::kd, d0, xnj) + x2a, tabv);          // square_dist, expanded form, scaled
+                    v1 = kx5<KIND>(fma(Kx5Scale<KIND>::kd, d1, xnj) + x2b, tabv);
                 }
                 const bool in = jrow < M;
                 dst[gen_slot] = in ? v0 : 0.0;
@@ -278,9 +290,10 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                     dmma884(d0, d1, a0, b);
                     dmma884(e0, e1, a1, b);
                 }
-                const double xn0 = __ldg(xn + jc0), xn1 = __ldg(xn + jc1);
-                const double v0 = kx5<KIND>((-2.0 * d0 + xn0) + x2a, tabv), v1 = kx5<KIND>((-2.0 * d1 + xn0) + x2b, tabv);
-                const double u0 = kx5<KIND>((-2.0 * e0 + xn1) + x2a, tabv), u1 = kx5<KIND>((-2.0 * e1 + xn1) + x2b, tabv);
+                constexpr double KD = Kx5Scale<KIND>::kd;
+                const double xn0 = Kx5Scale<KIND>::kn * __ldg(xn + jc0), xn1 = Kx5Scale<KIND>::kn * __ldg(xn + jc1);
+                const double v0 = kx5<KIND>(fma(KD, d0, xn0) + x2a, tabv), v1 = kx5<KIND>(fma(KD, d1, xn0) + x2b, tabv);
+                const double u0 = kx5<KIND>(fma(KD, e0, xn1) + x2a, tabv), u1 = kx5<KIND>(fma(KD, e1, xn1) + x2b, tabv);
                 double* __restrict__ dst0 = kres + (size_t)g * GS;
                 dst0[gen_slot] = jrow0 < M ? v0 : 0.0;
                 dst0[gen_slot + 4] = jrow0 < M ? v1 : 0.0;
