@@ -26,6 +26,8 @@ cudaError_t gpfo_contract5_launch(cudaStream_t st, int variant, int kind, const 
     if (variant == 38) return launch5<4, 4, 2, 1>(st, kind, d_gp, d_prog, io, grid, D);      // 38 / 39: ablations of 21 (no generation / no L^-1 copies)
     if (variant == 39) return launch5<4, 4, 2, 2>(st, kind, d_gp, d_prog, io, grid, D);
 #endif
+    // tiles of several chunks (M > 1024): row slots balanced over the schedulers (ABL bit 4096, contract5_kernel.cuh)
+    if (io.geom_o.nchunks > 1) return launch5<8, 2, 2, 4096>(st, kind, d_gp, d_prog, io, grid, D);
     return launch5<8, 2, 2>(st, kind, d_gp, d_prog, io, grid, D);
 }
 
@@ -36,7 +38,10 @@ cudaError_t gpfo_contract5_astore_launch(cudaStream_t st, int kind, const GpDev*
                                          int num_sms, int D, int native) {
     const int64_t ntiles = (io.N + 15) / 16;
     const int grid = (int)(ntiles < num_sms ? (ntiles > 0 ? ntiles : 1) : num_sms);
-    if (native) return launch5<8, 2, 2, 128 + 512>(st, kind, d_gp, d_prog, io, grid, D);
+    if (native) {
+        if (io.geom_o.nchunks > 1) return launch5<8, 2, 2, 128 + 512 + 4096>(st, kind, d_gp, d_prog, io, grid, D);
+        return launch5<8, 2, 2, 128 + 512>(st, kind, d_gp, d_prog, io, grid, D);
+    }
     return launch5<8, 2, 2, 128>(st, kind, d_gp, d_prog, io, grid, D);
 }
 

@@ -54,6 +54,7 @@ contract5_bwd_kernel(const GpDev* __restrict__ gpp, EvalIO io, int nbuf) {
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(tab32 + 34);
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int wr = w;                                 // row slot of the warp (contract5_mma.inc); no triangle balancing here
     const GpDev& gp = *gpp;
     const int M = gp.M, R = gp.R;
     const double variance = gp.variance;

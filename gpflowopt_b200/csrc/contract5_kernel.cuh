@@ -143,6 +143,13 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
     static_assert(T <= 32, "one epilogue warp");
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    // Row slot of the warp: its row blocks are r * NW + wr of the chunk.  Warps w, w + 4, w + 8, ... share a scheduler, and in
+    // a triangle row block b carries b + 1 column blocks of work, so with wr = w scheduler 3 gets more DMMAs than scheduler 0
+    // in every triangle.  Reversing every second group of four makes the slots of a scheduler's warps sum to the same value
+    // ({s, 7 - s, 8 + s, 15 - s}).  Measured (profiles/r02_v5_pair_run_lean.log): +0.5 / +0.8 points at M = 2048 / 4096, but
+    // -1.5 / -0.4 at M = 512 / 1024, where a tile is a single triangle -- so only tiles of several chunks are dealt this way.
+    // (ABL bit 4096, chosen at launch by the chunk count: a run-time choice here costs more than it gains.)
+    const int wr = ((ABL & 4096) && ((w >> 2) & 1)) ? (w | 3) - (w & 3) : w;
     const GpDev& gp = *gpp;
     const int M = gp.M, R = gp.R;
     const double* __restrict__ Xs = gp.Xs;
@@ -404,7 +411,7 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 const int i8 = 7 - (lane >> 2);
 #pragma unroll
                 for (int r = 0; r < RBW; ++r) {
-                    const int rbl = r * NW + w;
+                    const int rbl = r * NW + wr;
                     if (rbl < nr) {
                         const int rbrev = geom.nrb - 1 - (row0 + rbl);
                         double* const o = at + (size_t)(rbrev >> 3) * (KPC * 2 * NBB * 32) +
@@ -449,7 +456,7 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                     for (int nb = 0; nb < NB; ++nb) { mv[nb][0] = 0.0; mv[nb][1] = 0.0; }
 #pragma unroll
                     for (int r = 0; r < RBW; ++r) {
-                        const int rbl = r * NW + w;
+                        const int rbl = r * NW + wr;
                         double v = 0.0;
                         if (rbl < nr) v = __ldg(Vv + (size_t)(8 * (row0 + rbl) + (lane >> 2)) * R + ro);
 #pragma unroll
