@@ -720,11 +720,17 @@ static int launch_stored_a(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
     const int64_t ntiles = (N + Tt - 1) / Tt;
     size_t per_tile = 0;                                   // doubles of A per tile, all GPs
     for (int g = 0; g < ctx->ngps; ++g) per_tile += (size_t)gpfo_contract_astore_stride(ctx->gps[g].Mp / 8);
-    size_t free_b = 0, total_b = 0;
-    CK(cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = (free_b + ctx->cap_a_scratch * sizeof(double)) / 4;
-    if (budget > ((size_t)8 << 30)) budget = (size_t)8 << 30;
-    if (const char* mb = getenv("GPFO_ASTORE_BUDGET_MB")) budget = (size_t)atoll(mb) << 20;      // tests: force several slabs
+    // scratch budget: a quarter of the free memory, at most 8 GB.  The driver is asked only when the scratch at hand does not
+    // already hold the whole call (cudaMemGetInfo sits between the timing events and takes milliseconds on a busy host).
+    size_t budget = ctx->cap_a_scratch * sizeof(double);
+    const char* mb = getenv("GPFO_ASTORE_BUDGET_MB");
+    if (mb) budget = (size_t)atoll(mb) << 20;                                                    // tests: force several slabs
+    else if (budget < (size_t)ntiles * per_tile * sizeof(double)) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        budget = (free_b + ctx->cap_a_scratch * sizeof(double)) / 4;
+        if (budget > ((size_t)8 << 30)) budget = (size_t)8 << 30;
+    }
     int64_t slab_tiles = (int64_t)(budget / (per_tile * sizeof(double)));
     if (slab_tiles < ctx->num_sms) slab_tiles = ctx->num_sms;
     if (slab_tiles > ntiles) slab_tiles = ntiles;
