@@ -195,8 +195,7 @@ contract5_bwd_kernel(const GpDev* __restrict__ gpp, EvalIO io, int nbuf) {
                     for (int kp = k0; kp < k1; ++kp)
                         mma_static(kb + (kp - k0) * (2 * NB * 32), std::integral_constant<int, 0>(), std::true_type());
                 } else if (full_chunk) {
-#pragma unroll 1
-                    for (int kp = k0; kp < k1; ++kp) mma_diag(kb + (kp - k0) * (2 * NB * 32), kp);
+                    mma_diag_run(kb, k0, k1);         // runs of constant first row block: dispatch outside the column loop
                 } else {
 #pragma unroll 1
                     for (int kp = k0; kp < k1; ++kp) mma_ragged(kb + (kp - k0) * (2 * NB * 32), kp);
