@@ -44,7 +44,7 @@ UNIT = "candidates/s"
 KERNELS = {
     20: {"kernel": "contract5_kernel<8,2,2> (FP64 DMMA.8x8x4 contraction + fused EI epilogue + block argmax; 16-candidate tiles, "
                    "1024-row chunks, K(X*,X) generated once per tile into a resident shared-memory panel, no global scratch)",
-         "traffic": 82820864 + 2439680, "traffic_source": "profiles/r02_contract5_v20_dram_N1e6.csv (2026-10-20; N = 1e6, M = 2048)"},
+         "traffic": 81803264 + 3297792, "traffic_source": "profiles/r02_final_contract5_v20_dram_N1e6.csv (2026-10-20, final build; N = 1e6, M = 2048)"},
     21: {"kernel": "contract5_kernel<4,4,2> (as variant 20 with 32-candidate tiles and 512-row chunks)",
          "traffic": None, "traffic_source": None},
     12: {"kernel": "contract2_kernel<16,2,8,5,*,8> (FP64 DMMA.8x8x4 contraction + fused EI epilogue + block argmax; 64-candidate "
