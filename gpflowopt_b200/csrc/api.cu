@@ -943,7 +943,7 @@ static int launch_standard(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
             }
             gio.kx_scratch_stride = (long long)stride;
         }
-        if ((variant >= 20 && variant <= 39) || variant == 44) {   // v5 reads its block stream and layout from the launch record
+        if (variant >= 20 && variant <= 39) {   // v5 reads its block stream and layout from the launch record
             gio.packed_o = ctx->gps[g].hdev.packed; gio.geom_o = ctx->gps[g].hdev.geom;
             if (variant == 27 || variant == 28) {           // profiling build: phase counters land at the start of the values buffer
                 CK(ensure(&ctx->dvalues, &ctx->cap_values, (size_t)(N > 65536 ? N : 65536)));
@@ -1363,7 +1363,7 @@ int gpfo_timings_get(const gpfo_ctx* ctx, gpfo_timings* out) {
 int gpfo_set_variant(gpfo_ctx* ctx, int variant) {
     if (!ctx) return GPFO_ERR_STATE;
 #ifdef GPFO_BUILD_EXPERIMENTS
-    static const int known[] = {0, 4, 5, 6, 10, 11, 12, 13, 14, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 44, 41, 42, 43, 121, 122, 123, 125, 127};
+    static const int known[] = {0, 4, 5, 6, 10, 11, 12, 13, 14, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 41, 42, 43, 121, 122, 123, 125, 127};
 #else
     static const int known[] = {0, 4, 5, 6, 11, 12, 20, 21, 29};
 #endif

@@ -45,7 +45,7 @@ void gpfo_argmax_final(cudaStream_t st, const double* part_val, const long long*
 struct VarInfo { int rbc, tile; };
 static VarInfo var_info(int v) {
     if (v == 20 || (v >= 22 && v <= 27) || v == 30 || v == 32 || v == 34 || v == 36) return {128, 16};
-    if (v == 29 || v == 44) return {64, 16};
+    if (v == 29) return {64, 16};
     if (v == 21 || v == 28 || v == 31 || v == 33 || v == 35 || (v >= 37 && v <= 39)) return {64, 32};
     if (v == 12 || v == 13 || v == 14 || (v >= 120 && v <= 129)) return {32, 64};
     if (v == 5) return {64, 16};
@@ -74,7 +74,7 @@ cudaError_t gpfo_contract_ws_launch(cudaStream_t st, int kind, const GpDev* d_gp
 
 cudaError_t gpfo_contract_launch(cudaStream_t st, int variant, int kind, const GpDev* d_gp, const ProgramDev* d_prog,
                                  EvalIO io, int grid, int D) {
-    if ((variant >= 20 && variant <= 39) || variant == 44) return gpfo_contract5_launch(st, variant, kind, d_gp, d_prog, io, grid, D);
+    if (variant >= 20 && variant <= 39) return gpfo_contract5_launch(st, variant, kind, d_gp, d_prog, io, grid, D);
 #ifdef GPFO_BUILD_EXPERIMENTS
     if (variant == 13) return gpfo_contract_ws_launch(st, kind, d_gp, d_prog, io, grid, D);
 #else

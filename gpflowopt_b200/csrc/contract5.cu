@@ -21,7 +21,6 @@ cudaError_t gpfo_contract5_launch(cudaStream_t st, int variant, int kind, const 
     if (variant == 33) return launch5<4, 4, 2, 32>(st, kind, d_gp, d_prog, io, grid, D);     // generates last (34 / 35)
     if (variant == 34) return launch5<8, 2, 2, 64>(st, kind, d_gp, d_prog, io, grid, D);
     if (variant == 35) return launch5<4, 4, 2, 64>(st, kind, d_gp, d_prog, io, grid, D);
-    if (variant == 44) return launch5<4, 2, 2>(st, kind, d_gp, d_prog, io, grid, D);         // 44: 16 candidates x 512-row chunks, 16 warps
     if (variant == 36) return launch5<8, 2, 2, 256 + 1024>(st, kind, d_gp, d_prog, io, grid, D);   // 36 / 37: 20 / 21 before paired generation
     if (variant == 37) return launch5<4, 4, 2, 256 + 1024>(st, kind, d_gp, d_prog, io, grid, D);   // and the run-wise triangle dispatch
     if (variant == 38) return launch5<4, 4, 2, 1>(st, kind, d_gp, d_prog, io, grid, D);      // 38 / 39: ablations of 21 (no generation / no L^-1 copies)

@@ -12,7 +12,9 @@
 //     is ever generated twice and nothing is parked anywhere; at M = 4096 / 8192 the columns right of the panel are
 //     regenerated per chunk (1.75 x / 3.6 x, on 1/2 / 1/4 of the per-flop cost of M = 2048).
 //   * Tall chunks also balance the diagonal triangles: a warp owns 8 row blocks dealt cyclically, so inside a triangle the
-//     per-warp work differs by at most one block-step in eight (v2: one in two).
+//     per-warp work differs by at most one block-step in eight (v2: one in two).  The triangles are specialised at compile
+//     time by the first active row block of the warp and dispatched once per run of column blocks with the same first block
+//     (mma_diag_run), so their loop bodies are straight-line code like the dense part.
 //   * No CTA barrier in the column loop.  Column groups (8 KB each) are handed over through mbarriers: every warp arrives on
 //     full[g] after writing its share of group g (generated two groups ahead of use) and waits on it right before the first
 //     B-fragment load; the streaming groups right of the panel cycle through a small ring with empty[] barriers.  Warps of a
@@ -24,7 +26,9 @@
 //   * K(X*,X) generation: the D-term dot products Xs . xc of a group are 8 x 8 tiles of DMMAs themselves (one tile per warp
 //     and group, ceil(D / 4) DMMAs instead of D DFMAs per element) -- on the shared FP64 pipe every generation instruction
 //     waits one arbitration round behind the other warps' 16-cycle DMMAs, so the instruction COUNT of the generation is what
-//     costs (phase counters: profiles/r02_phase5_*.log); the kernel variance is folded into the 64-entry 2^(i/64) table.
+//     costs (phase counters: profiles/r02_phase5_*.log); the kernel variance is folded into the 256-entry 2^(i/256) table,
+//     the kernel's constants into the squared distance (kx5), and resident groups are generated two at a time (four
+//     independent chains per thread).
 //   * L^-1 blocks travel global -> shared with cp.async into a per-warp private ring of QD quads of row blocks (each lane
 //     copies and re-reads its own 16 bytes: no barrier); the slot just read is refilled for the column block one ahead.
 //     One 512-byte block feeds 2 NB DMMAs, so the stream is 4 x (T = 16) the L2 traffic of v2's T = 64 -- 7 TB/s at
