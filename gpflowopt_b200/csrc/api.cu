@@ -1365,7 +1365,7 @@ int gpfo_set_variant(gpfo_ctx* ctx, int variant) {
 #ifdef GPFO_BUILD_EXPERIMENTS
     static const int known[] = {0, 4, 5, 6, 10, 11, 12, 13, 14, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 41, 42, 43, 121, 122, 123, 125, 127};
 #else
-    static const int known[] = {0, 4, 5, 6, 11, 12, 20, 21, 29};
+    static const int known[] = {0, 4, 5, 6, 11, 12, 20, 21};
 #endif
     bool ok = false;
     for (int k : known) ok = ok || k == variant;

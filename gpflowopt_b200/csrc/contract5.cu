@@ -6,8 +6,8 @@
 cudaError_t gpfo_contract5_launch(cudaStream_t st, int variant, int kind, const GpDev* d_gp, const ProgramDev* d_prog,
                                   EvalIO io, int grid, int D) {
     if (variant == 21) return launch5<4, 4, 2>(st, kind, d_gp, d_prog, io, grid, D);
-    if (variant == 29) return launch5<8, 2, 2, 0, 8>(st, kind, d_gp, d_prog, io, grid, D);     // 8 warps, 16 candidates x 512-row chunks, two CTAs per SM
-#ifdef GPFO_BUILD_EXPERIMENTS                 // ablations of variant 20 (timing only; 22: no generation, 23: no L^-1 copies,
+#ifdef GPFO_BUILD_EXPERIMENTS
+    if (variant == 29) return launch5<8, 2, 2, 0, 8>(st, kind, d_gp, d_prog, io, grid, D);     // 8 warps, 16 candidates x 512-row chunks, two CTAs per SM                 // ablations of variant 20 (timing only; 22: no generation, 23: no L^-1 copies,
     if (variant == 22) return launch5<8, 2, 2, 1>(st, kind, d_gp, d_prog, io, grid, D);      // 24: neither, 25: no mbarrier waits,
     if (variant == 23) return launch5<8, 2, 2, 2>(st, kind, d_gp, d_prog, io, grid, D);      // 26: none of the three)
     if (variant == 24) return launch5<8, 2, 2, 3>(st, kind, d_gp, d_prog, io, grid, D);
