@@ -6,11 +6,11 @@
 // row-split form of the DMMA kernel gave every CTA 128 rows (2 MB of K^-1 through one SM, ~17 us at the ~120 GB/s one SM can
 // pull) and regenerated K(X*,X) for all 8 tile slots in every CTA.  Here a CTA takes 16 rows (two 8-row blocks of the same
 // block stream), so one tile spreads over up to all SMs; its 16 warps split the COLUMN blocks of those rows and add their
-// partial rows in shared memory in a fixed order; K(x*,X) is generated for the one candidate only (the row-split kernels pad a
-// call to 8), and the arithmetic is plain DFMA on the DMMA-fragment layout (lane l of a block holds row l/4, columns l%4 and
-// 4 + l%4): 2 DFMA per 16 bytes, far below the L2 port rate.  Calls of 2 ... 8 candidates were measured in this form as well
-// (profiles/r02_latency_thin.log: every CTA then generates the whole 8-wide panel, N = 8 gradients at M = 2048 0.168 ms
-// against 0.114 ms with the row-split kernels) and stay with the row-split kernels.
+// partial rows in shared memory in a fixed order; every CTA works on ONE candidate (K(x*,X) generated for it alone -- the
+// row-split kernels pad a call to a tile of 8), and the arithmetic is plain DFMA on the DMMA-fragment layout (lane l of a block
+// holds row l/4, columns l%4 and 4 + l%4): 2 DFMA per 16 bytes, far below the L2 port rate.  A call of up to four candidates
+// is a grid of N x (CTAs per candidate).  (A tile of 4 / 8 candidates per CTA was measured as well: every CTA then generates
+// the whole panel for all of them, N = 8 gradients at M = 2048 0.168 ms against 0.114 ms with the row-split kernels.)
 // The kernels leave per-CTA partial sums; thin_final_kernel (contract2_aux.cu) adds them in CTA order.
 #include <cstdlib>
 #include "contract_common.cuh"
@@ -43,12 +43,14 @@ thin_contract_kernel(const GpDev* __restrict__ gpp, EvalIO io) {
     double* gsum = ub + (1 + RMAX) * ROWS;                // GRAD: [1 + R][1 + D]
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const double* __restrict__ packed = io.packed_o;
-    const int nsplit = io.nsplit, split = (int)blockIdx.x;            // one candidate: every CTA of the launch works on it
+    // one candidate per CTA: CTAs [c nsplit, (c + 1) nsplit) work on candidate c of the call
+    const int nsplit = io.nsplit, cand = (int)(blockIdx.x / nsplit), split = (int)(blockIdx.x - cand * nsplit);
+    const int tile = cand >> 3, ln = cand & 7;                        // its place in the partial-sum layout of the row-split kernels
     const int nunits = (geom.nrb + RB - 1) / RB;
 
     if (tid < 32) tab32[tid] = exp2(tid * (1.0 / 32.0));
     for (int d = tid; d < D; d += THREADS) {
-        const double xt = __dadd_rn(__dmul_rn(io.X[d], gp.in_scale[d]), gp.in_shift[d]);
+        const double xt = __dadd_rn(__dmul_rn(io.X[(size_t)cand * D + d], gp.in_scale[d]), gp.in_shift[d]);
         xs[d] = xt / gp.ell[d];
     }
     if (GRAD) for (int e = tid; e < (1 + R) * (1 + D); e += THREADS) gsum[e] = 0.0;
@@ -196,15 +198,15 @@ thin_contract_kernel(const GpDev* __restrict__ gpp, EvalIO io) {
             }
         }
     }
-    // partial sums of this CTA in the layouts the row-split kernels use (candidate 0 of tile 0)
+    // partial sums of this CTA in the layouts the row-split kernels use
     if (!GRAD) {
-        if (tid < 1 + RMAX) io.partials[(size_t)split * 8 * (1 + RMAX) + tid] = tots[tid];    // (written by this thread's warp)
+        if (tid < 1 + RMAX) io.partials[(((size_t)tile * nsplit + split) * 8 + ln) * (1 + RMAX) + tid] = tots[tid];   // (written by this thread's warp)
     } else {
         __syncthreads();
-        double* part = io.partials + (size_t)split * (size_t)(8 * (1 + R) * (1 + D));
+        double* part = io.partials + ((size_t)tile * nsplit + split) * (size_t)(8 * (1 + R) * (1 + D));
         for (int e = tid; e < (1 + R) * (1 + D); e += THREADS) {
             const int k = e / (1 + D), c = e - k * (1 + D);
-            part[(size_t)(k * 8) * (1 + D) + c] = gsum[e];
+            part[(size_t)(k * 8 + ln) * (1 + D) + c] = gsum[e];
         }
     }
 }
@@ -232,16 +234,18 @@ int gpfo_thin_nsplit(int64_t N, int num_sms, int nrb) {
     const int nunits = (nrb + TH_RB - 1) / TH_RB;
     return num_sms < nunits ? num_sms : nunits;
 }
-// Largest call the 16-row kernels take: one candidate (GPFO_THIN_MAX_N=0: none, the row-split DMMA kernels take N = 1 too)
+// Largest call the 16-row kernels take, one candidate per CTA: 4.  Measured (profiles/r02_latency_thin.log, gradients, wall
+// clock): M = 2048 N = 2 / 4 / 8: 0.077 / 0.095 / 0.130 ms against 0.108 / 0.115 / 0.121 ms with the row-split DMMA kernels
+// (one tile of 8 for all of them); M = 4096, D = 16: 0.130 / 0.193 / 0.318 against 0.226 / 0.222 / 0.222 ms -- every candidate
+// pulls the whole stream through the SMs again, so from 8 candidates the shared tile wins.  GPFO_THIN_MAX_N moves it (0: none).
 int64_t gpfo_thin_max_n() {
-    static const int64_t v = [] { const char* e = getenv("GPFO_THIN_MAX_N"); return (e && atoll(e) < 1) ? (int64_t)0 : (int64_t)1; }();
+    static const int64_t v = [] { const char* e = getenv("GPFO_THIN_MAX_N"); return e ? atoll(e) : (int64_t)4; }();
     return v;
 }
 // training points whose K(X*,X) fits the panel of a call (one pass)
-int gpfo_thin_panel_cols(int64_t N) { return N == 1 ? TH_MAX_COLS : 0; }
+int gpfo_thin_panel_cols(int64_t N) { (void)N; return TH_MAX_COLS; }
 cudaError_t gpfo_thin_contract_launch(cudaStream_t st, int kind, const GpDev* d_gp, EvalIO io, int D, int grad) {
-    const int64_t ntiles = (io.N + 7) / 8;
-    const int grid = (int)(ntiles * io.nsplit);
+    const int grid = (int)(io.N * io.nsplit);             // one candidate per CTA
     if (grad) switch (kind) {
         case GPFO_KERN_RBF: return thin_launch_kind<GPFO_KERN_RBF, true>(st, d_gp, io, grid, D);
         case GPFO_KERN_MATERN52: return thin_launch_kind<GPFO_KERN_MATERN52, true>(st, d_gp, io, grid, D);

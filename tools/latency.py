@@ -21,7 +21,7 @@ for M, D in ((20, 2), (512, 8), (2048, 8), (4096, 16)):
     kern = gpfo.RBF(D, variance=h["variance"], lengthscales=h["lengthscales"], ARD=True) if M == 20 else \
         gpfo.Matern52(D, variance=h["variance"], lengthscales=h["lengthscales"], ARD=True)
     acq = ExpectedImprovement(gpfo.GPR(X, Y, kern, noise_variance=h["noise_variance"]))
-    for N in (1, 4, 8, 32, 1000):
+    for N in (1, 2, 4, 8, 32, 1000):
         Xc = synthetic.candidates(N, D)
         tv = bench(lambda: acq.evaluate(Xc))
         tg = bench(lambda: acq.evaluate_with_gradients(Xc))
