@@ -356,7 +356,12 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) { acc[r][nb][0] = 0.0; acc[r][nb][1] = 0.0; }
 
-            for (int g = 0; g < ngroups; ++g) {
+            // pair: the two groups generated together are contracted together as well -- one barrier round and one dispatch for
+            // 2 GK column blocks (they sit next to each other in the resident panel): +1.7 points at M = 512, +0.5 at M = 1024.
+            // Not in the instantiation for tiles of several chunks (bit 4096), where it costs 1.6 points
+            // (profiles/r02_v5_pair_run_lean.log).
+            const int gstep = (pair && !(ABL & (2048 | 4096))) ? 2 : 1;
+            for (int g = 0; g < ngroups; g += gstep) {
                 const int gg = g + la;
                 const bool do_gen = pair ? false : (gg >= g_first && gg < ngroups);
                 const bool do_pair = pair && (g & 1) == 0 && gg < ngroups;
@@ -367,7 +372,10 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 // wait for group g
                 const double* kb;
                 if (g < RG) {
-                    if (p == 0 && !(ABL & 4)) mbar_wait_par(bar_res + 8 * g, res_par);
+                    if (p == 0 && !(ABL & 4)) {
+                        mbar_wait_par(bar_res + 8 * g, res_par);
+                        if (gstep == 2) mbar_wait_par(bar_res + 8 * (g + 1), res_par);
+                    }
                     kb = kres + (size_t)g * GS + lane;
                 } else {
                     if (!(ABL & 4)) mbar_wait_par(bar_full + 8 * use_buf, (full_ph >> use_buf) & 1u);
@@ -376,7 +384,7 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 }
                 if (TIM) { const double probe = kb[0]; if (probe == 123.456) t_gen += 1; const long long t = clock64(); t_wait += t - t_mark; t_mark = t; }
                 const int k0 = g * GK;
-                const int k1 = (k0 + GK < kp_end) ? k0 + GK : kp_end;
+                const int k1 = (k0 + gstep * GK < kp_end) ? k0 + gstep * GK : kp_end;
                 if (full_chunk && k1 + KA <= row0) {  // group and its refills in the dense part of a full chunk: no predicates
 #pragma unroll 1
                     for (int kp = k0; kp < k1; ++kp)
