@@ -21,7 +21,7 @@ cudaError_t gpfo_contract5_launch(cudaStream_t st, int variant, int kind, const 
     if (variant == 33) return launch5<4, 4, 2, 32>(st, kind, d_gp, d_prog, io, grid, D);     // generates last (34 / 35)
     if (variant == 34) return launch5<8, 2, 2, 64>(st, kind, d_gp, d_prog, io, grid, D);
     if (variant == 35) return launch5<4, 4, 2, 64>(st, kind, d_gp, d_prog, io, grid, D);
-    if (variant == 36) {                                    // 36 / 37: 20 / 21 contracting one group per step (before the paired steps)
+    if (variant == 36) {                                    // 36 / 37: 20 / 21 with one group per contraction step (before the wide steps)
         if (io.geom_o.nchunks > 1) return launch5<8, 2, 2, 2048 + 4096>(st, kind, d_gp, d_prog, io, grid, D);
         return launch5<8, 2, 2, 2048>(st, kind, d_gp, d_prog, io, grid, D);
     }

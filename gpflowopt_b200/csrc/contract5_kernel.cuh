@@ -344,7 +344,16 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             // PAIR: resident groups are generated two at a time, at even steps (needs the default lookahead of two groups and
             // an even group count, i.e. whole pairs inside the panel; otherwise the single-group schedule below)
             const bool pair = PAIR && p == 0 && la == 2 && (ngroups & 1) == 0;
-            if (pair) gen_pair(0);
+            // WIDE steps (instantiations for single-chunk tiles): NB groups = NW column blocks per step -- one run of constant
+            // first row block: one barrier round, one dispatch, NB / 2 generated pairs per step.  Measured
+            // (profiles/r02_v5_pair_run_lean.log): M = 512 (T = 32: four groups per step) 58.3 -> 62.9 %, M = 1024 (T = 16:
+            // two groups per step) 72.0 -> 72.5 %; 32 column blocks per step at M = 1024: 71.9 %; in the instantiation for
+            // tiles of several chunks (bit 4096) wide steps cost 1.6 points and are off.
+            constexpr int GSTEP = NB;
+            const bool wide = pair && !(ABL & (2048 | 4096)) && (ngroups % GSTEP) == 0;
+            static_assert(GSTEP == 2 || GSTEP == 4, "wide steps: one or two generated pairs per step");
+            if (wide) { gen_pair(0); if (GSTEP == 4) gen_pair(2); }
+            else if (pair) gen_pair(0);
             else for (int g = g_first; g < la && g < ngroups; ++g) gen_group(g);
             if (TIM) { const long long t = clock64(); t_gen += t - t_mark; t_mark = t; }
             // the previous tile's epilogue: warp 0 has delivered its share of the first groups, the other warps are contracting
@@ -356,17 +365,16 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) { acc[r][nb][0] = 0.0; acc[r][nb][1] = 0.0; }
 
-            // pair: the two groups generated together are contracted together as well -- one barrier round and one dispatch for
-            // 2 GK column blocks (they sit next to each other in the resident panel): +1.7 points at M = 512, +0.5 at M = 1024.
-            // Not in the instantiation for tiles of several chunks (bit 4096), where it costs 1.6 points
-            // (profiles/r02_v5_pair_run_lean.log).
-            const int gstep = (pair && !(ABL & (2048 | 4096))) ? 2 : 1;
+            const int gstep = wide ? GSTEP : 1;
             for (int g = 0; g < ngroups; g += gstep) {
-                const int gg = g + la;
+                const int gg = wide ? g + GSTEP : g + la;
                 const bool do_gen = pair ? false : (gg >= g_first && gg < ngroups);
                 const bool do_pair = pair && (g & 1) == 0 && gg < ngroups;
                 if (TIM) t_mark = clock64();
-                if (do_pair && gen_first) gen_pair(gg);
+                if (do_pair && gen_first) {
+                    gen_pair(gg);
+                    if (GSTEP == 4 && wide) gen_pair(gg + 2);
+                }
                 if (do_gen && gen_first) gen_group(gg);
                 if (TIM) { const long long t = clock64(); t_gen += t - t_mark; t_mark = t; }
                 // wait for group g
@@ -374,7 +382,10 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 if (g < RG) {
                     if (p == 0 && !(ABL & 4)) {
                         mbar_wait_par(bar_res + 8 * g, res_par);
-                        if (gstep == 2) mbar_wait_par(bar_res + 8 * (g + 1), res_par);
+                        if (wide) {
+#pragma unroll
+                            for (int q = 1; q < GSTEP; ++q) mbar_wait_par(bar_res + 8 * (g + q), res_par);
+                        }
                     }
                     kb = kres + (size_t)g * GS + lane;
                 } else {
@@ -405,7 +416,10 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
                 }
                 if (TIM) { const long long t = clock64(); t_mma += t - t_mark; t_mark = t; }
                 if (do_gen && !gen_first) gen_group(gg);
-                if (do_pair && !gen_first) gen_pair(gg);
+                if (do_pair && !gen_first) {
+                    gen_pair(gg);
+                    if (GSTEP == 4 && wide) gen_pair(gg + 2);
+                }
                 if (TIM) { const long long t = clock64(); t_gen += t - t_mark; }
             }
             cp_async_wait<0>();
