@@ -229,6 +229,7 @@ int gpfo_ctx_destroy(gpfo_ctx* ctx) {
 // chunks (profiles/r02_v5_sweep_3_pipelined_tiles.log: v20 69-82 %, v21 55-72 %, v12 51-76 %).
 static double large_batch_cost(int variant, int Mp) {
     const int nrb = Mp / 8;
+    // measured fractions of the DMMA peak (profiles/r02_v5_sweep_final.log)
     if (variant == 12) return (double)nrb * (nrb + 1) / 2 / (Mp >= 1536 ? 0.74 : (Mp >= 768 ? 0.65 : 0.51));
     const int rbc = variant == 20 ? 128 : 64, rbw = rbc / 16;
     double steps = 0.0;
@@ -241,7 +242,7 @@ static double large_batch_cost(int variant, int Mp) {
             steps += (double)rows_per_warp * 16 * (row0 + nr);
         }
     }
-    return steps / (variant == 20 ? (Mp >= 1536 ? 0.79 : 0.68) : (Mp >= 1536 ? 0.71 : (Mp >= 768 ? 0.68 : 0.55)));
+    return steps / (variant == 20 ? (Mp >= 1536 ? 0.815 : 0.725) : (Mp >= 1536 ? 0.73 : (Mp >= 768 ? 0.70 : 0.625)));
 }
 
 static int effective_variant(const gpfo_ctx* ctx, int64_t N, int Mp) {
@@ -746,14 +747,20 @@ static int launch_stored_a(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
     // large-batch forward), unless a kernel was pinned or the input is too wide for its shared memory
     int mp_max = 0;
     for (int g = 0; g < ctx->ngps; ++g) mp_max = std::max(mp_max, ctx->gps[g].Mp);
-    const bool v5_forward = ctx->variant == 0 && D <= gpfo_contract5_max_dim(20) && !getenv("GPFO_GRAD_FWD_V12") &&
-                            large_batch_cost(20, mp_max) < large_batch_cost(12, mp_max);
+    bool v5_forward = ctx->variant == 0 && D <= gpfo_contract5_max_dim(20) && !getenv("GPFO_GRAD_FWD_V12") &&
+                      large_batch_cost(20, mp_max) < large_batch_cost(12, mp_max);
+    // small training sets: the 32-candidate x 512-row tiling as the forward kernel (A in the 64-candidate layout of round 1's
+    // backward kernel), where it beats both
+    const bool v21_forward = ctx->variant == 0 && D <= gpfo_contract5_max_dim(21) && !getenv("GPFO_GRAD_FWD_V12") &&
+                             large_batch_cost(21, mp_max) < large_batch_cost(12, mp_max) &&
+                             large_batch_cost(21, mp_max) < large_batch_cost(20, mp_max);
+    if (v21_forward) v5_forward = true;
     // ... and then the backward launch in the same tiling (A in 16-candidate tiles, bulk copies), GPFO_GRAD_BWD_V2=1 keeps round
     // 1's 64-candidate backward kernel (comparisons)
     // (measured, profiles/r02_grad_bench_tall_backward.log: stored-A total 63.1 / 75.2 / 79.9 / 85.1 % of peak at M = 1024 / 2048 /
     // 4096 / 8192 against 62.0 / 70.9 / 74.9 / 75.1 % with the 64-candidate backward kernel)
     static const int bwd5_min_m = getenv("GPFO_BWD5_MIN_M") ? atoi(getenv("GPFO_BWD5_MIN_M")) : 1024;
-    const bool v5_backward = v5_forward && mp_max >= bwd5_min_m && gpfo_contract5_bwd_ok(D) && !getenv("GPFO_GRAD_BWD_V2");
+    const bool v5_backward = v5_forward && !v21_forward && mp_max >= bwd5_min_m && gpfo_contract5_bwd_ok(D) && !getenv("GPFO_GRAD_BWD_V2");
     size_t kx_need = 0;
     for (int g = 0; g < ctx->ngps && !v5_forward; ++g) {
         const size_t cols = ((size_t)ctx->gps[g].Mp + 127) / 128 * 128;
@@ -785,10 +792,11 @@ static int launch_stored_a(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
             a_off += (size_t)slab_tiles * (size_t)gio.a_stride;
             if (k == 0) CK(cudaEventRecord(ctx->gp_ev[g][0], st));
             if (v5_forward) {              // resident-panel forward (no K(X*,X) scratch), same A layout
-                rc = ensure_pack(ctx, ctx->gps[g], gpfo_contract_rbc(20), &gio.packed_o, &gio.geom_o);
+                rc = ensure_pack(ctx, ctx->gps[g], gpfo_contract_rbc(v21_forward ? 21 : 20), &gio.packed_o, &gio.geom_o);
                 if (rc != GPFO_OK) return rc;
                 if (v5_backward) gio.a_stride = gpfo_contract5_astore_stride(gh.Mp / 8);
-                CK(gpfo_contract5_astore_launch(st, gh.kind, gh.ddev, ctx->dprog, gio, ctx->num_sms, D, v5_backward ? 1 : 0));
+                CK(gpfo_contract5_astore_launch(st, gh.kind, gh.ddev, ctx->dprog, gio, ctx->num_sms, D, v5_backward ? 1 : 0,
+                                                v21_forward ? 21 : 20));
             } else {
                 CK(gpfo_contract_astore_launch(st, gh.kind, gh.ddev, ctx->dprog, gio, g_s, D));
             }

@@ -37,8 +37,13 @@ cudaError_t gpfo_contract5_launch(cudaStream_t st, int variant, int kind, const 
 // forward launch of the stored-A gradient pass (large batches): variant 20's tiling, A parked in the layout the backward launch
 // (contract2_kernel, 64-candidate tiles) reads; the grid walks 16-candidate tiles
 // (`native` = 1: A in the 16-candidate tile layout the tall-chunk backward kernel reads, one contiguous 8 KB block per group)
+// (`variant` 21: the 32-candidate x 512-row tiling for small training sets, A always in the 64-candidate tile layout)
 cudaError_t gpfo_contract5_astore_launch(cudaStream_t st, int kind, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io,
-                                         int num_sms, int D, int native) {
+                                         int num_sms, int D, int native, int variant) {
+    if (variant == 21) {
+        const int64_t nt = (io.N + 31) / 32;
+        return launch5<4, 4, 2, 128>(st, kind, d_gp, d_prog, io, (int)(nt < num_sms ? (nt > 0 ? nt : 1) : num_sms), D);
+    }
     const int64_t ntiles = (io.N + 15) / 16;
     const int grid = (int)(ntiles < num_sms ? (ntiles > 0 ? ntiles : 1) : num_sms);
     if (native) {

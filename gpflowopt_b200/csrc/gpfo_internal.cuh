@@ -355,7 +355,7 @@ int gpfo_contract3_clusters(int64_t N, int num_sms);
 // contract5.cu (resident-panel kernel)
 int gpfo_contract5_max_dim(int variant);
 cudaError_t gpfo_contract5_astore_launch(cudaStream_t st, int kind, const GpDev* d_gp, const ProgramDev* d_prog, EvalIO io,
-                                         int num_sms, int D, int native);
+                                         int num_sms, int D, int native, int variant);
 cudaError_t gpfo_contract5_bwd_launch(cudaStream_t st, int kind, const GpDev* d_gp, EvalIO io, int num_sms, int D);
 int gpfo_contract5_bwd_ok(int D);
 long long gpfo_contract5_astore_stride(int nrb);
