@@ -273,7 +273,18 @@ static int effective_variant(const gpfo_ctx* ctx, int64_t N, int Mp) {
         const double cost = (double)((tiles + ctx->num_sms - 1) / ctx->num_sms) * wave_cost[k];
         if (k == 0 || cost <= best_cost) { best = k; best_cost = cost; }
     }
-    return var[best];
+    int best_var = var[best];
+    // ... and the resident-panel kernels, whose wave of 16 / 32 candidates costs what the large-batch model says relative to a
+    // wave of the 64-candidate tiles (M = 2048: 0.33 ms per wave of 16 against 0.50 ms for the round-1 tiling of 16): from a few
+    // waves of their tiles on they win the mid-size batches as well (MCOptimizer(domain, 10^4) at M = 2048: 2.3 -> 1.7 ms)
+    const double c12 = large_batch_cost(12, Mp);
+    for (int v : {20, 21}) {
+        const int T = v == 20 ? 16 : 32;
+        const int64_t tiles = (N + T - 1) / T;
+        const double cost = (double)((tiles + ctx->num_sms - 1) / ctx->num_sms) * 1.46 * (T * large_batch_cost(v, Mp)) / (64.0 * c12);
+        if (cost < best_cost) { best_var = v; best_cost = cost; }
+    }
+    return best_var;
 }
 
 static PackGeom make_geom(int nrb, int rbc, int dense) {
