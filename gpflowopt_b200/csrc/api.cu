@@ -1059,13 +1059,17 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     for (int g = 0; g < ctx->ngps; ++g) mp_max = std::max(mp_max, ctx->gps[g].Mp);
     int variant = effective_variant(ctx, N, mp_max);
     if (generate && variant == 10) variant = 12;
-    if ((variant == 20 || variant == 21) && (want_grad || D > gpfo_contract5_max_dim(variant)))
-        variant = 12;     // the gradient pass parks A in the 64-candidate tile layout; very wide inputs exceed v5's shared memory
+    if ((variant == 20 || variant == 21) && D > gpfo_contract5_max_dim(variant)) variant = 12;   // very wide inputs exceed v5's shared memory
+    // gradients with a resident-panel variant: a large batch (or a pinned variant) means the stored-A pass, which is entered as
+    // variant 12 (it picks its own forward kernel); a mid-size batch below the stored-A threshold keeps the variant as the
+    // forward launch of the dense K^-1 pass
+    const bool v5_choice = variant == 20 || variant == 21;
+    if (v5_choice && want_grad && (ctx->variant != 0 || N >= (int64_t)64 * 4 * ctx->num_sms)) variant = 12;
     // Gradient batches from about 40 candidates per SM up take the stored-A pass (2 M^2 flop) as well: its forward launch walks
     // 16-candidate tiles (all SMs busy from N = 16 SMs), and from there on even a partly filled wave of 64-candidate backward
     // tiles costs less than the dense K^-1 pass (3 M^2 flop); measured in profiles/r02_grad_mid_stored_a.log.
     // GPFO_ASTORE_MIN_N moves the threshold.
-    if (want_grad && ctx->variant == 0 && variant != 12) {
+    if (want_grad && ctx->variant == 0 && variant != 12) {      // (variant 12 from the wave model already means stored-A)
         const char* e = getenv("GPFO_ASTORE_MIN_N");
         // both launches of the pass on 16-candidate tiles (tall-chunk kernels): worth it from one wave of such tiles
         // (profiles/r02_grad_mid_stored_a.log: x1.0-1.6 over the dense pass for N = 2.4e3 ... 4.7e3, x1.3-1.8 from 1.2e4)
