@@ -231,7 +231,7 @@ static double large_batch_cost(int variant, int Mp) {
     const int nrb = Mp / 8;
     // measured fractions of the DMMA peak (profiles/r02_v5_sweep_final.log)
     if (variant == 12) return (double)nrb * (nrb + 1) / 2 / (Mp >= 1536 ? 0.74 : (Mp >= 768 ? 0.65 : 0.51));
-    const int rbc = variant == 20 ? 128 : 64, rbw = rbc / 16;
+    const int rbc = (variant == 20 || variant == 19) ? 128 : 64, rbw = rbc / 16;
     double steps = 0.0;
     for (int row0 = 0; row0 < nrb; row0 += rbc) {
         const int nr = nrb - row0 < rbc ? nrb - row0 : rbc;
@@ -242,6 +242,8 @@ static double large_batch_cost(int variant, int Mp) {
             steps += (double)rows_per_warp * 16 * (row0 + nr);
         }
     }
+    // (variant 19 = variant 20's tiling with 8 candidates: 0.8 of its efficiency, profiles/r02_midsize_batches.log)
+    if (variant == 19) return steps / (0.8 * (Mp >= 1536 ? 0.815 : 0.725));
     return steps / (variant == 20 ? (Mp >= 1536 ? 0.815 : 0.725) : (Mp >= 1536 ? 0.73 : (Mp >= 768 ? 0.70 : 0.625)));
 }
 
@@ -278,8 +280,8 @@ static int effective_variant(const gpfo_ctx* ctx, int64_t N, int Mp) {
     // wave of the 64-candidate tiles (M = 2048: 0.33 ms per wave of 16 against 0.50 ms for the round-1 tiling of 16): from a few
     // waves of their tiles on they win the mid-size batches as well (MCOptimizer(domain, 10^4) at M = 2048: 2.3 -> 1.7 ms)
     const double c12 = large_batch_cost(12, Mp);
-    for (int v : {20, 21}) {
-        const int T = v == 20 ? 16 : 32;
+    for (int v : {19, 20, 21}) {
+        const int T = v == 19 ? 8 : (v == 20 ? 16 : 32);
         const int64_t tiles = (N + T - 1) / T;
         const double cost = (double)((tiles + ctx->num_sms - 1) / ctx->num_sms) * 1.46 * (T * large_batch_cost(v, Mp)) / (64.0 * c12);
         if (cost < best_cost) { best_var = v; best_cost = cost; }
@@ -962,7 +964,7 @@ static int launch_standard(gpfo_ctx* ctx, const EvalPlan& pl, EvalIO io, int* la
             }
             gio.kx_scratch_stride = (long long)stride;
         }
-        if (variant >= 20 && variant <= 39) {   // v5 reads its block stream and layout from the launch record
+        if (variant >= 19 && variant <= 39) {   // v5 reads its block stream and layout from the launch record
             gio.packed_o = ctx->gps[g].hdev.packed; gio.geom_o = ctx->gps[g].hdev.geom;
             if (variant == 27 || variant == 28) {           // profiling build: phase counters land at the start of the values buffer
                 CK(ensure(&ctx->dvalues, &ctx->cap_values, (size_t)(N > 65536 ? N : 65536)));
@@ -1059,6 +1061,7 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     for (int g = 0; g < ctx->ngps; ++g) mp_max = std::max(mp_max, ctx->gps[g].Mp);
     int variant = effective_variant(ctx, N, mp_max);
     if (generate && variant == 10) variant = 12;
+    if (variant == 19 && (want_grad || D > gpfo_contract5_max_dim(20))) variant = 6;             // (8-candidate tiles: values only)
     if ((variant == 20 || variant == 21) && D > gpfo_contract5_max_dim(variant)) variant = 12;   // very wide inputs exceed v5's shared memory
     // gradients with a resident-panel variant: a large batch (or a pinned variant) means the stored-A pass, which is entered as
     // variant 12 (it picks its own forward kernel); a mid-size batch below the stored-A threshold keeps the variant as the
@@ -1341,6 +1344,7 @@ int gpfo_predict(gpfo_ctx* ctx, int gp_id, const double* X, int64_t N, int D, do
     int rc = stage_candidates(ctx, X, N, D, &dX);
     if (rc != GPFO_OK) return rc;
     int variant = effective_variant(ctx, N, g.Mp);
+    if (variant == 19 && D > gpfo_contract5_max_dim(20)) variant = 6;
     if ((variant == 20 || variant == 21) && D > gpfo_contract5_max_dim(variant)) variant = 12;
     if (variant == 10 || variant == 11 || variant == 12 || variant == 13 || variant == 14) variant = (N >= (int64_t)32 * ctx->num_sms) ? 4 : ((N >= (int64_t)16 * ctx->num_sms) ? 5 : 6);
     const int rbc = gpfo_contract_rbc(variant);
@@ -1355,7 +1359,7 @@ int gpfo_predict(gpfo_ctx* ctx, int gp_id, const double* X, int64_t N, int D, do
     io.X = dX; io.N = N; io.mstride = N; io.mom_mean = ctx->dmom_mean; io.mom_var = ctx->dmom_var;
     io.part_val = ctx->dpart_val; io.part_idx = ctx->dpart_idx;
     io.write_moments = 1; io.run_program = 0;
-    if (variant >= 20 && variant <= 39) { io.packed_o = g.hdev.packed; io.geom_o = g.hdev.geom; }
+    if (variant >= 19 && variant <= 39) { io.packed_o = g.hdev.packed; io.geom_o = g.hdev.geom; }
     const int ns = split_count(ctx, N, gpfo_split_tile(), g.geom_s.nchunks);
     if (ns > 1) {
         rc = ensure_partials(ctx);
@@ -1386,9 +1390,9 @@ int gpfo_timings_get(const gpfo_ctx* ctx, gpfo_timings* out) {
 int gpfo_set_variant(gpfo_ctx* ctx, int variant) {
     if (!ctx) return GPFO_ERR_STATE;
 #ifdef GPFO_BUILD_EXPERIMENTS
-    static const int known[] = {0, 4, 5, 6, 10, 11, 12, 13, 14, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 41, 42, 43, 121, 122, 123, 125, 127};
+    static const int known[] = {0, 4, 5, 6, 10, 11, 12, 13, 14, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 41, 42, 43, 121, 122, 123, 125, 127};
 #else
-    static const int known[] = {0, 4, 5, 6, 11, 12, 20, 21};
+    static const int known[] = {0, 4, 5, 6, 11, 12, 19, 20, 21};
 #endif
     bool ok = false;
     for (int k : known) ok = ok || k == variant;

@@ -39,6 +39,7 @@ void gpfo_argmax_final(cudaStream_t st, const double* part_val, const long long*
 //   14: 12 with the scratch re-reads as 1-D bulk copies (cp.async.bulk / UBLKCP + mbarrier): same speed, not default
 //   13: the tiling of 12, warp-specialised (contract4.cu: 4 producer warps feed 16 DMMA warps through mbarrier stages)
 //   20: v5, 16 candidates x 1024-row chunks, resident K(X*,X) panel in shared memory, no scratch (contract5_kernel.cuh)
+//   19: v5, 8 candidates x 1024-row chunks (one wave of 8-candidate tiles: 592 < N <= 1184)
 //   21: v5, 32 candidates x 512-row chunks
 //   41-43, 121-123: ablations (no generation / no L^-1 loads / neither), 127: per-phase cycle counters -- profiling only
 //   (10, 13, 14, 4x and 12x exist only in builds with GPFO_BUILD_EXPERIMENTS=1)
@@ -46,6 +47,7 @@ struct VarInfo { int rbc, tile; };
 static VarInfo var_info(int v) {
     if (v == 20 || (v >= 22 && v <= 27) || v == 30 || v == 32 || v == 34 || v == 36) return {128, 16};
     if (v == 29) return {64, 16};
+    if (v == 19) return {128, 8};
     if (v == 21 || v == 28 || v == 31 || v == 33 || v == 35 || (v >= 37 && v <= 39)) return {64, 32};
     if (v == 12 || v == 13 || v == 14 || (v >= 120 && v <= 129)) return {32, 64};
     if (v == 5) return {64, 16};
@@ -74,7 +76,7 @@ cudaError_t gpfo_contract_ws_launch(cudaStream_t st, int kind, const GpDev* d_gp
 
 cudaError_t gpfo_contract_launch(cudaStream_t st, int variant, int kind, const GpDev* d_gp, const ProgramDev* d_prog,
                                  EvalIO io, int grid, int D) {
-    if (variant >= 20 && variant <= 39) return gpfo_contract5_launch(st, variant, kind, d_gp, d_prog, io, grid, D);
+    if (variant >= 19 && variant <= 39) return gpfo_contract5_launch(st, variant, kind, d_gp, d_prog, io, grid, D);
 #ifdef GPFO_BUILD_EXPERIMENTS
     if (variant == 13) return gpfo_contract_ws_launch(st, kind, d_gp, d_prog, io, grid, D);
 #else

@@ -2,10 +2,15 @@
 #include "contract5_kernel.cuh"
 #include "contract5_bwd_kernel.cuh"
 
-// variants: 20 = 16 candidates x 1024-row chunks, 21 = 32 candidates x 512-row chunks (ring: 2 quads of row blocks per warp)
+// variants: 20 = 16 candidates x 1024-row chunks, 21 = 32 candidates x 512-row chunks, 19 = 8 candidates x 1024-row chunks
+// (ring: 2 quads of row blocks per warp)
 cudaError_t gpfo_contract5_launch(cudaStream_t st, int variant, int kind, const GpDev* d_gp, const ProgramDev* d_prog,
                                   EvalIO io, int grid, int D) {
     if (variant == 21) return launch5<4, 4, 2>(st, kind, d_gp, d_prog, io, grid, D);
+    if (variant == 19) {                          // 8 candidates x 1024-row chunks: small batches (one wave of 8-candidate tiles)
+        if (io.geom_o.nchunks > 1) return launch5<8, 1, 2, 4096>(st, kind, d_gp, d_prog, io, grid, D);
+        return launch5<8, 1, 2>(st, kind, d_gp, d_prog, io, grid, D);
+    }
 #ifdef GPFO_BUILD_EXPERIMENTS
     if (variant == 29) return launch5<8, 2, 2, 0, 8>(st, kind, d_gp, d_prog, io, grid, D);     // 8 warps, 16 candidates x 512-row chunks, two CTAs per SM                 // ablations of variant 20 (timing only; 22: no generation, 23: no L^-1 copies,
     if (variant == 22) return launch5<8, 2, 2, 1>(st, kind, d_gp, d_prog, io, grid, D);      // 24: neither, 25: no mbarrier waits,

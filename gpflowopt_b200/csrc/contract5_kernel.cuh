@@ -349,8 +349,8 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             // (profiles/r02_v5_pair_run_lean.log): M = 512 (T = 32: four groups per step) 58.3 -> 62.9 %, M = 1024 (T = 16:
             // two groups per step) 72.0 -> 72.5 %; 32 column blocks per step at M = 1024: 71.9 %; in the instantiation for
             // tiles of several chunks (bit 4096) wide steps cost 1.6 points and are off.
-            constexpr int GSTEP = NB;
-            const bool wide = pair && !(ABL & (2048 | 4096)) && (ngroups % GSTEP) == 0;
+            constexpr int GSTEP = NB >= 2 ? NB : 2;
+            const bool wide = NB >= 2 && pair && !(ABL & (2048 | 4096)) && (ngroups % GSTEP) == 0;
             static_assert(GSTEP == 2 || GSTEP == 4, "wide steps: one or two generated pairs per step");
             if (wide) { gen_pair(0); if (GSTEP == 4) gen_pair(2); }
             else if (pair) gen_pair(0);

@@ -14,7 +14,7 @@ KINDS = {"rbf": ogp.RBF, "matern52": ogp.MATERN52, "matern32": ogp.MATERN32}
 
 # kernel variants of the contraction (csrc/contract.cu): production ones first; 10 / 13 / 14 (rejected experiments) exist only
 # in libraries built with GPFO_BUILD_EXPERIMENTS=1 and are skipped otherwise
-PRODUCTION_VARIANTS = [20, 21, 12, 11, 4, 5, 6]
+PRODUCTION_VARIANTS = [20, 21, 12, 11, 4, 5, 6, 19]
 EXPERIMENT_VARIANTS = [14, 13, 10]
 
 
@@ -233,7 +233,7 @@ def test_hvpoi_reference_fixture(ctx):
         ctx.gp_count_set(1)
 
 
-@pytest.mark.parametrize("variant", [20, 21, 12, 11, 4] + EXPERIMENT_VARIANTS)
+@pytest.mark.parametrize("variant", [20, 21, 19, 12, 11, 4] + EXPERIMENT_VARIANTS)
 def test_multi_chunk_variants_agree_with_oracle(ctx, variant):
     """M = 1100 spans several row chunks in every layout (256/512/1024-row chunks, partial last chunk): the resident-panel
     variants (20, 21), the scratch variants (11, 12) and the regenerating variant (4) all meet the oracle."""
@@ -253,7 +253,7 @@ def test_multi_chunk_variants_agree_with_oracle(ctx, variant):
         ctx.set_variant(0)
 
 
-@pytest.mark.parametrize("variant", [20, 21])
+@pytest.mark.parametrize("variant", [20, 21, 19])
 @pytest.mark.parametrize("M,D,kind", [(2300, 16, "matern52"), (1541, 3, "rbf"), (3100, 8, "matern32")])
 def test_resident_panel_kernel_streaming_groups(ctx, variant, M, D, kind):
     """v5 (csrc/contract5_kernel.cuh) beyond its resident panel: M > 1024 (variant 20) / > 512 (variant 21) regenerates the

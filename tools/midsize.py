@@ -10,11 +10,11 @@ ctx = _lib.Context(0)
 X, Y = synthetic.training_set(M, D)
 ctx.gp_set(0, X, Y, _lib.KERN_MATERN52, **synthetic.hypers(D))
 ctx.program_set([[_lib.OP_EI, 0, 0, 0]], [-1.5])
-for N in (1000, 2368, 3000, 5000, 10000, 20000, 30000, 37888):
+for N in [int(a) for a in sys.argv[2].split(',')] if len(sys.argv) > 2 else (1000, 2368, 3000, 5000, 10000, 20000, 30000, 37888):
     Xc = synthetic.candidates(N, D)
     row = []
     ref = None
-    for v in (0, 6, 5, 11, 12, 20, 21):
+    for v in (0, 6, 5, 11, 12, 19, 20, 21):
         ctx.set_variant(v)
         ctx.eval(Xc)
         best = 1e30
