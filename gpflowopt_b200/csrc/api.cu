@@ -1061,7 +1061,7 @@ int gpfo_eval(gpfo_ctx* ctx, const double* Xcand, int64_t N, int D, double* out_
     for (int g = 0; g < ctx->ngps; ++g) mp_max = std::max(mp_max, ctx->gps[g].Mp);
     int variant = effective_variant(ctx, N, mp_max);
     if (generate && variant == 10) variant = 12;
-    if (variant == 19 && (want_grad || D > gpfo_contract5_max_dim(20))) variant = 6;             // (8-candidate tiles: values only)
+    if (variant == 19 && D > gpfo_contract5_max_dim(20)) variant = 6;
     if ((variant == 20 || variant == 21) && D > gpfo_contract5_max_dim(variant)) variant = 12;   // very wide inputs exceed v5's shared memory
     // gradients with a resident-panel variant: a large batch (or a pinned variant) means the stored-A pass, which is entered as
     // variant 12 (it picks its own forward kernel); a mid-size batch below the stored-A threshold keeps the variant as the
