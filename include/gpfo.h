@@ -156,12 +156,17 @@ int gpfo_predict(gpfo_ctx* ctx, int gp_id, const double* X, int64_t N, int D, do
 
 int gpfo_timings_get(const gpfo_ctx* ctx, gpfo_timings* out);
 
-/* Tuning knob for the contraction kernel.  variant 0 = automatic (by batch size: row-split launches for N <= 4 * SMs,
- * 8/16/32-candidate tiles for mid-size batches, 64-candidate tiles + K(X*,X) scratch for large ones; large gradient batches
- * take the stored-A pass).  Explicit values (4, 5, 6, 11, 12: tile widths; 10, 13: experimental cluster / warp-specialised
- * kernels; 41-43, 121-127: profiling builds) pin one kernel; see the table in csrc/contract.cu and DESIGN.md 4.1 / 8.
- * Environment switches: GPFO_STRICT_ONCHIP=1 (read once: never park K(X*,X) in global memory); per call GPFO_GRAD_DENSE=1
- * (gradient pass over the dense K^-1 stream for every batch size), GPFO_ASTORE_BUDGET_MB (bound of the stored-A scratch). */
+/* Tuning knob for the contraction kernel.  variant 0 = automatic: calls of one to four candidates take the latency path
+ * (16-row kernels, csrc/thin.cu), up to 4 * SMs candidates the row-split launches, beyond that the kernel with the least
+ * waves x cost per wave -- the resident-panel kernels (19 / 20 / 21: 8 / 16 / 32 candidates per tile, K(X*,X) kept in shared
+ * memory) or round 1's tilings (6 / 5 / 11 / 12: 8 / 16 / 32 / 64 candidates, the last two with a K(X*,X) scratch in global
+ * memory); large gradient batches take the stored-A pass.  Explicit values pin one kernel (4, 5, 6, 11, 12, 19, 20, 21 in
+ * every build; 10, 13, 14, 22-39, 41-43, 121-127 only with GPFO_BUILD_EXPERIMENTS=1: rejected kernels, ablations, phase
+ * counters); see the table in csrc/contract.cu and DESIGN.md 4.0 / 4.1 / 8.
+ * Environment switches: GPFO_STRICT_ONCHIP=1 (read once: never park K(X*,X) in global memory); GPFO_NO_THIN=1 /
+ * GPFO_THIN_MAX_N (latency path off / its candidate limit); GPFO_NO_GRAPHS=1 (no CUDA-graph replay of small calls); per call
+ * GPFO_GRAD_DENSE=1 (gradient pass over the dense K^-1 stream for every batch size), GPFO_ASTORE_MIN_N (stored-A threshold),
+ * GPFO_ASTORE_BUDGET_MB (bound of the stored-A scratch). */
 int gpfo_set_variant(gpfo_ctx* ctx, int variant);
 
 /* The forward kernel gpfo_eval would select for a batch of N candidates with the models registered now (what variant 0 =
