@@ -89,3 +89,41 @@ def test_sharded_argmax_world_size_2(tmp_path):
         assert p.returncode == 0, o
     # both ranks agree on the winner
     assert outs[0].split("ok")[1] == outs[1].split("ok")[1]
+
+
+def test_single_process_pipeline_matches_one_shot():
+    """dist.pipelined_argmax without a process group: large draws are produced chunk by chunk on a worker thread while the
+    previous chunk is scored; rows, order, winner and tie-break are those of one produce(0, n) call; a producer error is
+    re-raised on the caller's thread."""
+    import numpy as np
+    from gpflowopt_b200 import dist
+    n, d = 300000, 8                                   # 2.4 M numbers: above the single-process pipelining threshold
+
+    def produce(first, count, out=None):
+        X = np.random.rand(count, d)
+        if out is not None:
+            out[...] = X
+            return out
+        return X
+
+    def score(block):
+        v = np.round(np.sin(block).sum(axis=1), 3)     # rounded: many exact ties across chunks
+        i = int(np.argmax(v))
+        return float(v[i]), i
+
+    seen = []
+    np.random.seed(5)
+    v, i, x = dist.pipelined_argmax(n, d, produce, score, on_chunk_rows=seen.append)
+    np.random.seed(5)
+    rows = np.random.rand(n, d)
+    ref = np.round(np.sin(rows).sum(axis=1), 3)
+    assert seen == [37500] and i == int(np.argmax(ref)) and v == ref[i] and np.array_equal(x, rows[i:i + 1])
+    assert np.array_equal(np.random.rand(3), np.random.RandomState(5).rand(n * d + 3)[-3:])     # the stream went on from the same place
+
+    def bad(first, count, out=None):
+        if first > 0:
+            raise RuntimeError("boom")
+        return produce(first, count, out)
+    import pytest
+    with pytest.raises(RuntimeError):
+        dist.pipelined_argmax(n, d, bad, score)
