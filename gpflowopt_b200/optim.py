@@ -318,7 +318,9 @@ class MultiStartOptimizer(Optimizer):
             order = self._lowest(scores, self._nstarts)
             points = np.vstack([random_rows(seed, int(i), 1, self.domain.lower, self.domain.upper) for i in order])
             return points, np.ravel(scores)[order]
-        points = RandomDesign(self._nsamples, self.domain).generate()
+        # the rows RandomDesign(n, domain).generate() would draw (same np.random stream, same affine map), produced natively
+        # and without its two domain-membership passes over the N x D array (MCOptimizer._get_eval_rows)
+        points = MCOptimizer(self.domain, self._nsamples)._get_eval_rows(0, self._nsamples)
         if acq is not None:                      # value-only scoring kernel; minimise -acq (bo.py:244-245)
             scores = -acq.evaluate(points)
             objective.counter += points.shape[0]
