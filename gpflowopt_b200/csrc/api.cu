@@ -231,20 +231,17 @@ static double large_batch_cost(int variant, int Mp) {
     const int nrb = Mp / 8;
     // measured fractions of the DMMA peak (profiles/r02_v5_sweep_final.log)
     if (variant == 12) return (double)nrb * (nrb + 1) / 2 / (Mp >= 1536 ? 0.74 : (Mp >= 768 ? 0.65 : 0.51));
-    const int rbc = (variant == 20 || variant == 19) ? 128 : 64, rbw = rbc / 16;
+    const int rbc = (variant == 20 || variant == 19) ? 128 : 64;
     double steps = 0.0;
     for (int row0 = 0; row0 < nrb; row0 += rbc) {
         const int nr = nrb - row0 < rbc ? nrb - row0 : rbc;
         if (nr == rbc) steps += (double)nr * row0 + (double)nr * (nr + 1) / 2;
-        else {                                      // ragged chunk: every warp runs whole quads of row blocks, predicated
-            const int rq = rbw >= 4 ? 4 : rbw;
-            const int rows_per_warp = ((nr + 15) / 16 + rq - 1) / rq * rq;
-            steps += (double)rows_per_warp * 16 * (row0 + nr);
-        }
+        else                                        // short last chunk: run as a full one whose missing row blocks are zero rows
+            steps += (double)rbc * row0 + (double)rbc * nr - (double)nr * (nr - 1) / 2;
     }
     // (variant 19 = variant 20's tiling with 8 candidates: 0.8 of its efficiency, profiles/r02_midsize_batches.log)
     if (variant == 19) return steps / (0.8 * (Mp >= 1536 ? 0.815 : 0.725));
-    return steps / (variant == 20 ? (Mp >= 1536 ? 0.815 : 0.725) : (Mp >= 1536 ? 0.73 : (Mp >= 768 ? 0.70 : 0.625)));
+    return steps / (variant == 20 ? (Mp >= 1536 ? 0.815 : 0.725) : (Mp >= 1536 ? 0.75 : (Mp >= 768 ? 0.70 : 0.625)));
 }
 
 static int effective_variant(const gpfo_ctx* ctx, int64_t N, int Mp) {

@@ -6,8 +6,17 @@
 // (ring: 2 quads of row blocks per warp)
 cudaError_t gpfo_contract5_launch(cudaStream_t st, int variant, int kind, const GpDev* d_gp, const ProgramDev* d_prog,
                                   EvalIO io, int grid, int D) {
-    if (variant == 21) return launch5<4, 4, 2>(st, kind, d_gp, d_prog, io, grid, D);
+    // a last chunk that the row blocks do not fill: the instantiation that runs it through the specialised paths (bit 16384)
+    const bool short_last = io.geom_o.nrb % io.geom_o.rbc != 0;
+    if (variant == 21) {
+        if (short_last) return launch5<4, 4, 2, 16384>(st, kind, d_gp, d_prog, io, grid, D);
+        return launch5<4, 4, 2>(st, kind, d_gp, d_prog, io, grid, D);
+    }
     if (variant == 19) {                          // 8 candidates x 1024-row chunks: small batches (one wave of 8-candidate tiles)
+        if (short_last) {
+            if (io.geom_o.nchunks > 1) return launch5<8, 1, 2, 4096 + 16384>(st, kind, d_gp, d_prog, io, grid, D);
+            return launch5<8, 1, 2, 16384>(st, kind, d_gp, d_prog, io, grid, D);
+        }
         if (io.geom_o.nchunks > 1) return launch5<8, 1, 2, 4096>(st, kind, d_gp, d_prog, io, grid, D);
         return launch5<8, 1, 2>(st, kind, d_gp, d_prog, io, grid, D);
     }
@@ -35,6 +44,10 @@ cudaError_t gpfo_contract5_launch(cudaStream_t st, int variant, int kind, const 
     if (variant == 39) return launch5<4, 4, 2, 2>(st, kind, d_gp, d_prog, io, grid, D);
 #endif
     // tiles of several chunks (M > 1024): row slots balanced over the schedulers (ABL bit 4096, contract5_kernel.cuh)
+    if (short_last) {
+        if (io.geom_o.nchunks > 1) return launch5<8, 2, 2, 4096 + 16384>(st, kind, d_gp, d_prog, io, grid, D);
+        return launch5<8, 2, 2, 16384>(st, kind, d_gp, d_prog, io, grid, D);
+    }
     if (io.geom_o.nchunks > 1) return launch5<8, 2, 2, 4096>(st, kind, d_gp, d_prog, io, grid, D);
     return launch5<8, 2, 2>(st, kind, d_gp, d_prog, io, grid, D);
 }

@@ -256,7 +256,14 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             const int nr = pg_chunk_rows(geom, p);
             const int row0 = p * geom.rbc;            // first row block of this chunk = first diagonal column block
             const int kp_end = row0 + nr;
-            const bool full_chunk = nr == C::RBC;
+            // A last chunk with fewer than RBC row blocks runs the same compile-time specialised paths as a full one: the row blocks
+            // a warp does not have (r >= r_hi) are ZERO rows -- their ring slots are cleared below and never refilled -- so their
+            // DMMAs add nothing.  (The generic predicated path this replaces ran at 63-65 % of peak at M = 2000 / 2040, where the
+            // ragged chunk is three quarters of the work; profiles/r02_v5_ragged_chunks.log.)
+            // (ABL bit 16384 = SHORT, chosen at launch when the row blocks do not fill the last chunk: the guards this needs in the
+            // refill code cost 4-5 points when compiled into the kernel for whole chunks, which therefore stays as it was.)
+            constexpr bool SHORT = (ABL & 16384) != 0;
+            const bool full_chunk = SHORT ? true : (nr == C::RBC);
             const bool last_chunk = p + 1 == geom.nchunks;
 
             double acc[RBW][NB][2];                  // zeroed right before the column loop (after the deferred epilogue)
@@ -331,6 +338,13 @@ contract5_kernel(const GpDev* __restrict__ gpp, const ProgramDev* __restrict__ p
             const int ngroups = (kp_end + GK - 1) / GK;
             const int g_first = p == 0 ? 0 : RG;      // groups left of it are resident since chunk 0 of this tile
 
+            if (SHORT && nr != C::RBC) {              // clear the ring slots of this warp's missing row blocks (all stages)
+#pragma unroll
+                for (int sq = 0; sq < QD; ++sq)
+#pragma unroll
+                    for (int i = 0; i < RQ; ++i)
+                        if ((sq % QPC) * RQ + i >= r_hi) *reinterpret_cast<double2*>(myring + (sq * RQ + i) * 64) = make_double2(0.0, 0.0);
+            }
             // ring prologue: KA column blocks ahead
 #pragma unroll
             for (int a = 0; a < KA; ++a) {
