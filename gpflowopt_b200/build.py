@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "build")
 LIB = os.path.join(HERE, "libgpfo.so")
-SOURCES = ["api.cu", "factor.cu", "contract.cu", "contract2.cu", "contract2_aux.cu", "thin.cu", "contract5.cu", "hvpoi.cu", "grad.cu", "pareto_host.cu"]
+SOURCES = ["api.cu", "factor.cu", "contract.cu", "contract2.cu", "contract2_aux.cu", "thin.cu", "contract5.cu", "contract5_grad.cu", "hvpoi.cu", "grad.cu", "pareto_host.cu"]
 # Kernels that were measured and rejected (2-CTA cluster, warp-specialised, bulk-copy re-reads) and the profiling builds
 # (ablations, phase counters) are compiled only with GPFO_BUILD_EXPERIMENTS=1; the production library holds reachable code only.
 EXPERIMENT_SOURCES = ["contract2_prof.cu", "contract3.cu", "contract4.cu"]
